@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the CBREE hot path (BASELINE.json: particle-iterations/s and HBM fraction at N=1e7, d=100).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one CBREE iteration (solver.py:413-437 of the reference): step-size controller, sigma (Brent) and
+beta (hybr) adaptation with device objective sweeps, the Euler-Maruyama sweep and the Mahalanobis / IS / weighted
+moments sweep, convergence bookkeeping.  Workload: affine LSF, d=100, N=1e7 particles PER GPU (weak scaling),
+fp64, synthetic standard-normal particles (Philox, rank-invariant counters).  Inputs (8 GB per ensemble) are far
+larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = the same metric through
+CBREE(...).solve(problem) with the sample in pinned HOST memory (H2D of the sample and D2H of the results inside
+the timed region); `roofline` = dominant sweep against the measured HBM peak (plus the fp64 pipe fraction that
+actually binds at d=100); `cpu_baseline` = the NumPy oracle port of the reference on this box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cbree_particle_iterations_per_sec"
+UNIT = "particle-iterations/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=10_000_000, help="particles per GPU")
+    ap.add_argument("--d", type=int, default=100)
+    ap.add_argument("--ref-n", type=int, default=100_000, help="particles of the bounded CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- #
+# CPU arm: the oracle port of the reference's CBREE (the reference itself cannot travel to the GPU box)
+# --------------------------------------------------------------------------- #
+def cpu_cbree(n, d, steps, warmup):
+    """Time `steps` CBREE iterations of the NumPy port after `warmup` untimed ones.  Returns (p-it/s, seconds)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+
+    import cbree_oracle as co
+    import lsf_oracle as lo
+
+    rng = np.random.default_rng(1)
+    X0 = rng.standard_normal((n, d))
+    opts = co.Options(convergence_check=False, divergence_check=False, num_steps=10**9)
+    orc = co.CbreeOracle(lo.lsf_affine, opts, rng=np.random.default_rng(2))
+    st = co.IterState(X0, orc.lsf(X0), orc.e_fun(X0), sigma=opts.initial_sigma(), beta=opts.initial_beta())
+    orc.compute_weights(st)
+    orc.initial_stepsize(st)
+    states = [st]
+
+    def one():
+        if len(states) > 1 and states[-1].iteration % 2 == 0:
+            orc.update_stepsize(states)
+        orc.update_beta_and_sigma(states[-1])
+        states.append(orc.perform_step(states[-1]))
+        if len(states) > opts.observation_window:
+            states.pop(0)
+        orc.convergence_check(states)
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return n * steps / dt, dt
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, dt = cpu_cbree(args.ref_n, args.d, args.steps, args.warmup)
+    cores = blas_threads()
+    sample = f"CBREE affine d={args.d}, N={args.ref_n} particles, {args.steps} iterations, NumPy/SciPy oracle port"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"CBREE affine LSF d={args.d} fp64 (bounded CPU sample N={args.ref_n})",
+                   "particles": args.ref_n, "d": args.d},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- #
+# clocks
+# --------------------------------------------------------------------------- #
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- #
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import rareeventestimation_b200 as ree
+    from rareeventestimation_b200 import _lib
+    from rareeventestimation_b200.engine import Comm, Engine
+    from rareeventestimation_b200.problem import DeviceSample, ShardedHostSample
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    eng = Engine.get(dev, Comm())
+    n_local, d, K, W = args.n, args.d, args.steps, args.warmup
+    n_total = n_local * world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # per-call device timing of the two sweeps (CUDA events on the launching stream)
+    marks = {"step": [], "maha": []}
+
+    def timed(name, fn):
+        def wrapper(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            marks[name].append((e0, e1))
+            return out
+        return wrapper
+
+    eng.cbree_step = timed("step", eng.cbree_step)
+    eng.cbree_maha = timed("maha", eng.cbree_maha)
+
+    kw = dict(seed=1, convergence_check=False, divergence_check=False, quiet=True)
+    prob = ree.make_linear_problem(d)
+    prob.sample = DeviceSample(n_total, d, seed=0x5EED)
+    solver = ree.CBREE(num_steps=10**9, **kw)
+    cache_list = solver.start(prob)
+    for _ in range(W):
+        solver.advance(cache_list)
+    for v in marks.values():
+        v.clear()
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.ree_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(K):
+        solver.advance(cache_list)
+    ev1.record()
+    barrier()
+    launches = lib.ree_launch_count() - launches0
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clk = clocks.stop() if rank == 0 else None
+    value = n_total * K / (ms * 1e-3)
+    sweep_ms = {k: (sum(a.elapsed_time(b) for a, b in v) / max(1, len(v))) for k, v in marks.items()}
+    sigma_now, beta_now = cache_list[-1].sigma, cache_list[-1].beta
+    del cache_list, solver
+    torch.cuda.empty_cache()
+
+    # ---- roofline of the dominant sweep (per launch, this rank) -------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    fp64_peak = None
+    try:
+        fp64_peak = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))
+    except Exception:
+        pass
+    # algorithmic bytes per particle (DESIGN.md "Roofline"): sweep 1 reads X, writes X', g', e';
+    # sweep 2 reads X', g', e' and writes the weights.
+    alg = {"step": n_local * (16 * d + 16), "maha": n_local * (8 * d + 24)}
+    # algorithmic flops: triangular noise transform + symmetric Gram (sweep 1), triangular Mahalanobis + symmetric
+    # weighted Gram (sweep 2): 2*d^2 each, plus O(d).
+    flops = {"step": n_local * (2.0 * d * d + 8 * d), "maha": n_local * (2.0 * d * d + 8 * d)}
+    dom = max(sweep_ms, key=lambda k: sweep_ms[k])
+    ach = alg[dom] / (sweep_ms[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "ree_cbree_step" if dom == "step" else "ree_cbree_maha",
+                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "peak_source": peak_src, "ms_per_launch": sweep_ms[dom],
+                "sweeps_ms": sweep_ms,
+                "hbm_frac_whole_iteration": (n_local * (24 * d + 48)) / (ms / K * 1e-3) / 1e9 / hbm_peak}
+    tfl = flops[dom] / (sweep_ms[dom] * 1e-3) / 1e12
+    roofline["fp64"] = {"achieved_tflops": tfl, "note": "binding pipe at d=100 (SURVEY 8d)"}
+    if fp64_peak:
+        pk = max(fp64_peak.get("dfma_tflops", 0), fp64_peak.get("dmma_m8n8k4_tflops", 0))
+        roofline["fp64"].update({"peak_tflops": pk, "frac": tfl / pk if pk else None,
+                                 "peak_source": "tools/fp64_peak.cu -> profiles/fp64_peak.json"})
+
+    # ---- end to end through the reference-facing API with HOST buffers ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        lo, hi = eng.comm.shard(n_total)
+        host = torch.empty((hi - lo, d), dtype=torch.float64, pin_memory=True)
+        src = DeviceSample(n_total, d, seed=0x5EED).materialise(eng, lo, hi)
+        eng.download(src, out=host.numpy())
+        del src
+        torch.cuda.empty_cache()
+        prob2 = ree.make_linear_problem(d)
+        prob2.sample = ShardedHostSample(host.numpy(), n_total, lo)
+        solver2 = ree.CBREE(num_steps=K - 1, **kw)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        sol = solver2.solve(prob2)
+        pf = float(sol.prob_fail_hist[-1])
+        last_g = np.asarray(sol.lsf_eval_hist[-1])
+        f1.record()
+        barrier()
+        ms2 = max_over_ranks(f0.elapsed_time(f1))
+        n_steps = sol.num_steps + 1  # trial step of the initial step size + num_steps iterations
+        e2e = {"value": n_total * n_steps / (ms2 * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": (hi - lo) * d * 8 / n_steps,
+               "d2h_bytes_per_step": (last_g.nbytes + 8 * len(sol.prob_fail_hist)) / n_steps,
+               "steps": n_steps, "seconds": ms2 * 1e-3, "prob_fail": pf, "msg": sol.msg}
+        del sol, solver2, host
+        torch.cuda.empty_cache()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        steps_cpu = 8
+        v, dt = cpu_cbree(args.ref_n, d, steps_cpu, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+               "sample": f"CBREE affine d={d}, N={args.ref_n}, {steps_cpu} iterations of oracle/cbree_oracle.py "
+                         f"({dt:.1f} s)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"CBREE affine LSF d={d}, N={n_local} particles per GPU, fp64 (BASELINE configs[1])",
+                       "particles_per_gpu": n_local, "particles_total": n_total, "d": d, "tgt_fun": "algebraic",
+                       "noise": "philox", "sharding": f"particles x{world}",
+                       "l2": "inputs (8*N*d bytes per ensemble) exceed L2; no flush",
+                       "sigma_at_end": sigma_now, "beta_at_end": beta_now},
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

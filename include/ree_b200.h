@@ -1,0 +1,178 @@
+/*
+ * ree_b200.h -- C ABI of the B200-native CBREE engine (libree_b200.so).
+ *
+ * The reference (AlthausKonstantin/RareEventEstimation) is pure Python/NumPy and has
+ * no FFI layer; every entry point below therefore cites the
+ * reference NumPy/SciPy call site it replaces (paths relative to
+ * src/rareeventestimation/).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all `double*` / `const double*` arguments are
+ *     DEVICE pointers unless the name starts with `host_`.
+ *   - ensembles are SoA: element (particle i, dimension j) lives at X[j*ld + i],
+ *     ld >= n, ld a multiple of 8 (64-byte rows).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are
+ *     asynchronous on that stream; nothing synchronises unless stated.
+ *   - return value: 0 = ok, >0 = cudaError_t, <0 = argument error (REE_E_*).
+ *     ree_last_error() returns a thread-local message for the last failure.
+ *   - results of reductions are deterministic (fixed-order two-stage reductions, no
+ *     floating-point atomics): same inputs + same launch => same bits.
+ */
+#ifndef REE_B200_H
+#define REE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REE_ABI_VERSION 1
+
+/* argument errors */
+#define REE_E_BADARG (-1)
+#define REE_E_UNSUPPORTED (-2)
+#define REE_E_WORKSPACE (-3)
+
+/* smoothed-indicator kinds, solver.py:321-363 */
+enum ree_tgt_kind {
+    REE_TGT_ALGEBRAIC = 0,
+    REE_TGT_TANH = 1,
+    REE_TGT_ARCTAN = 2,
+    REE_TGT_ERF = 3,
+    REE_TGT_RELU = 4,
+    REE_TGT_SIGMOID = 5
+};
+
+/* limit-state functions */
+enum ree_lsf_kind {
+    REE_LSF_EXTERNAL = 0,        /* evaluated by the caller (arbitrary Python callable) */
+    REE_LSF_AFFINE = 1,          /* g = offset + sum_j coef[j]*x_j ; coef == NULL: g = -sum(x)/sqrt(d) + offset,
+                                    the reference's linear problem, problem/toy_problems.py:35-48, README.md:31-49 */
+    REE_LSF_CONVEX = 2,          /* problem/toy_problems.py:12-13 (d = 2) */
+    REE_LSF_FUJITA_RACKWITZ = 3, /* g = -sum_j log Phi(-x_j) - offset ; toy_problems.py:57-58 */
+    REE_LSF_OSCILLATOR = 4,      /* problem/toy_problems.py:72-80 (d = 6) */
+    REE_LSF_DIFFUSION = 5        /* problem/diffusion.py:131-171, 232-242 (d = n_modes) */
+};
+
+/* Limit-state descriptor.  `coef` (device) is kind specific:
+ *   AFFINE     d doubles
+ *   DIFFUSION  mode table, row-major [n_quad = 3*n_ele][d]  (diffusion.py:222-229 `function_values`)
+ *   others     unused (NULL)                                                                       */
+typedef struct ree_lsf {
+    int32_t kind;
+    int32_t d;
+    const double* coef;
+    double offset;   /* AFFINE: beta ; FUJITA_RACKWITZ: c ; DIFFUSION: u_max */
+    double p0;       /* DIFFUSION: mu  of log-field (diffusion.py:203) */
+    double p1;       /* DIFFUSION: sigma of log-field (diffusion.py:202) */
+    int32_t n_ele;   /* DIFFUSION: number of finite elements (512) */
+    int32_t reserved;
+} ree_lsf;
+
+/* noise source of the Euler-Maruyama step */
+enum ree_noise_mode {
+    REE_NOISE_INJECT = 0, /* Z given as an SoA device array (parity with Generator.multivariate_normal, solver.py:667) */
+    REE_NOISE_PHILOX = 1  /* Philox4x32-10 + Box-Muller, counter = (global particle, dim pair, draw) */
+};
+
+/* ---- library ----------------------------------------------------------------------- */
+int ree_abi_version(void);
+const char* ree_last_error(void);
+/* kernels launched by this library in this process so far (bench.py reports the delta as gpu_launches) */
+int64_t ree_launch_count(void);
+/* number of CTAs every reduction kernel uses on the current device (partials per launch) */
+int ree_num_ctas(void);
+/* bytes of scratch a call with dimension d may need (partials of the d x d sums).  The workspace
+ * must be zero-filled once after allocation (it holds a self-resetting ticket counter).          */
+int64_t ree_workspace_bytes(int d);
+
+/* ---- layout (host (N,d) C-order <-> device SoA); replaces nothing, it is the boundary -- */
+int ree_aos_to_soa(const double* aos, double* soa, int64_t n, int d, int64_t ld, void* stream);
+int ree_soa_to_aos(const double* soa, double* aos, int64_t n, int d, int64_t ld, void* stream);
+/* HOST-buffer convenience: chunked cudaMemcpyAsync + transpose through `staging`
+ * (device, staging_elems doubles).  Synchronises the stream before returning.          */
+int ree_upload_ensemble(const double* host_aos, double* soa, int64_t n, int d, int64_t ld,
+                        double* staging, int64_t staging_elems, void* stream);
+int ree_download_ensemble(const double* soa, double* host_aos, int64_t n, int d, int64_t ld,
+                          double* staging, int64_t staging_elems, void* stream);
+
+/* ---- noise / initial sample --------------------------------------------------------- */
+/* Z[j*ld+i] ~ N(0,1), counter (first_particle+i, j, draw).  With draw = REE_DRAW_SAMPLE this is
+ * the device replacement of NormalProblem.sample_gen (problem/problem.py:115-118).      */
+int ree_philox_normal(double* z, int64_t n, int d, int64_t ld, uint64_t seed, uint64_t draw,
+                      int64_t first_particle, void* stream);
+
+/* ---- limit-state and energy evaluation ----------------------------------------------- */
+/* g[i] = lsf(x_i)            replaces prob.lsf(x), solver.py:376-378 */
+int ree_lsf_eval(const ree_lsf* lsf, const double* x, int64_t n, int64_t ld, double* g, void* stream);
+/* e[i] = 0.5*|x_i|^2 + d/2 log(2 pi)   replaces NormalProblem.e_fun, problem/problem.py:112-113 */
+int ree_energy(const double* x, int64_t n, int d, int64_t ld, double* e, void* stream);
+
+/* ---- N-vector kernels ------------------------------------------------------------------ */
+/* ell[i] = log target(g_i, e_i; sigma)    solver.py:321-363 (same operation order, no FMA contraction) */
+int ree_logtgt(const double* g, const double* e, int64_t n, double sigma, int tgt_kind, double* ell,
+               void* stream);
+/* One pass over (g,e): a = beta*logtgt(g,e;sigma), masked to finite a.
+ *   out[0] = M = max a, out[1] = sum exp(a-M), out[2] = sum exp(2(a-M)), out[3] = #finite
+ * ESS = out[1]^2/out[2].   replaces my_softmax + ESS, utilities.py:105-142, solver.py:523, 591-597.
+ * `e` may be NULL (treated as 0).                                                            */
+int ree_reduce_ess(const double* g, const double* e, int64_t n, double sigma, double beta, int tgt_kind,
+                   double* workspace, double* out4, void* stream);
+/* One pass over g: a = logtgt(g,0;sigma_new) - logtgt(g,0;sigma_old), masked to finite a; same
+ * four outputs.  cvar = sqrt(out[2]/nf - (out[1]/nf)^2)/(out[1]/nf).
+ * replaces the sigma objective, solver.py:538-545 + my_log_cvar utilities.py:76-102.        */
+int ree_reduce_cvar(const double* g, int64_t n, double sigma_new, double sigma_old, int tgt_kind,
+                    double* workspace, double* out4, void* stream);
+/* out[0] = #{g_i <= 0} (as double)       replaces sum(lsf_evals <= 0), solver.py:534, 570, 709-712 */
+int ree_count_failed(const double* g, int64_t n, double* workspace, double* out1, void* stream);
+
+/* ---- the CBREE step (sweep 1) ------------------------------------------------------------ */
+/* X'[.,i] = t*X[.,i] + m_noise + F z_i ; g' = lsf(X') (unless EXTERNAL) ; e' = energy(X') ;
+ * sums[0..d)      = sum_i (x'_i - shift)          sums[d..d+d*d) = sum_i (x'_i-shift)(x'_i-shift)^T
+ * sums[d+d*d]     = #{g'_i <= 0}                  sums[d+d*d+1]  = n
+ * replaces the Euler step and the unweighted moments, solver.py:665-671, 677-682.
+ *   F        d x d row-major device matrix (U*sqrt(S) in parity mode, Cholesky factor otherwise)
+ *   z        SoA noise block (INJECT) or NULL (PHILOX: seed, draw, first_particle)
+ *   shift    d doubles (device) subtracted before accumulating (conditioning of the one-pass Gram)  */
+int ree_cbree_step(const double* x, double* x_new, int64_t n, int d, int64_t ld, double t,
+                   const double* m_noise, const double* F, int noise_mode, const double* z,
+                   uint64_t seed, uint64_t draw, int64_t first_particle, const ree_lsf* lsf,
+                   const double* shift, double* g_new, double* e_new, double* workspace, double* sums,
+                   void* stream);
+/* number of doubles in `sums` of ree_cbree_step / ree_cbree_maha / ree_ensemble_sums: d + d*d + 2 */
+int64_t ree_sums_len(int d);
+/* The same unweighted sums for an existing ensemble (initial sample, or after a callback replaced it);
+ * g may be NULL (count = 0).  replaces average/cov in solver.py:790-791, 840-841.                 */
+int ree_ensemble_sums(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* shift,
+                      double* workspace, double* sums, void* stream);
+
+/* ---- small dense algebra (single CTA) ---------------------------------------------------- */
+/* From raw shifted sums (after any cross-rank allreduce) compute
+ *   mean[d], cov[d*d] (ddof given), L = chol(cov) (lower, row-major), Linv = L^-1, stats[0] = log det cov,
+ *   stats[1] = info (0 ok, k>0: pivot k not positive / matrix numerically singular by SciPy's test),
+ *   stats[2] = min pivot, stats[3] = max diag.
+ * replaces average/cov (solver.py:670-671) + the factorisation inside multivariate_normal.logpdf (672-674). */
+int ree_moments_chol(const double* sums, const double* shift, int d, int ddof, int weighted, double* mean,
+                     double* cov, double* L, double* Linv, double* stats4, void* stream);
+/* L = chol(scale * C) for the noise covariance (solver.py:666-667), stats as above (no Linv). */
+int ree_chol_scaled(const double* C, int d, double scale, double* L, double* stats4, void* stream);
+
+/* ---- IS density + weighted moments (sweep 2) ---------------------------------------------- */
+/* For every particle: q = |Linv (x - mean)|^2, logq = -(d log 2pi + logdet + q)/2   (solver.py:672-674)
+ *   r = -e - logq ; IS statistics with an online max shift over finite r:
+ *     is4[0] = R = max r, is4[1] = sum exp(r-R) 1[g<=0], is4[2] = sum (exp(r-R) 1[g<=0])^2, is4[3] = #finite r
+ *   (cvar_is_weights, solver.py:683-686; importance_sampling, utilities.py:43-45)
+ * and, with w_i = exp(beta*logtgt(g_i,e_i;sigma) - wmax[0]) (0 where non-finite):
+ *     sums as in ree_cbree_step but weighted; sums[d+d*d] = sum w, sums[d+d*d+1] = sum w^2
+ *   (weighted mean/cov, solver.py:629-636).  wmax is a DEVICE scalar (out[0] of ree_reduce_ess).
+ * logq may be NULL (not stored).  w (n doubles) receives the unnormalised weights w_i.          */
+int ree_cbree_maha(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* e,
+                   const double* mean, const double* Linv, const double* logdet, double sigma, double beta,
+                   int tgt_kind, const double* wmax, const double* shift, double* logq, double* w,
+                   double* workspace, double* sums, double* is4, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REE_B200_H */

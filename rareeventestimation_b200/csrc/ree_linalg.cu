@@ -1,0 +1,163 @@
+// Small dense algebra on the d x d consensus statistics: moments from raw sums, Cholesky, inverse
+// of the factor.  One CTA per call; the matrix lives in shared memory (d <= REE_MAX_D).
+#include "common.cuh"
+
+#define REE_MAX_D 160
+#define REE_LA_THREADS 256
+
+// in-place lower Cholesky of A (row-major, leading dimension lda) in shared memory.
+// psd = true: a pivot <= tiny * max_diag gives a zero column (semi-definite factor, no failure);
+// psd = false: the first non-positive pivot is reported in *info (1-based) and the sweep stops.
+__device__ void chol_smem(double* A, int d, int lda, bool psd, double* s_stat /* [4] smem */) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) {
+        double mx = 0.0;
+        for (int j = 0; j < d; ++j) mx = fmax(mx, A[j * lda + j]);
+        s_stat[0] = 0.0;          // logdet accumulator
+        s_stat[1] = 0.0;          // info
+        s_stat[2] = CUDART_INF;   // min pivot
+        s_stat[3] = mx;           // max diag
+    }
+    __syncthreads();
+    const double mx = s_stat[3];
+    for (int k = 0; k < d; ++k) {
+        if (tid == 0) {
+            double piv = A[k * lda + k];
+            s_stat[2] = fmin(s_stat[2], piv);
+            if (!(piv > 0.0) || !isfinite(piv)) {
+                if (psd && isfinite(piv)) {
+                    A[k * lda + k] = 0.0;
+                } else if (s_stat[1] == 0.0) {
+                    s_stat[1] = (double)(k + 1);
+                }
+            } else if (psd && piv <= 1e-14 * mx) {
+                A[k * lda + k] = 0.0;
+            } else {
+                s_stat[0] += log(piv);
+                A[k * lda + k] = sqrt(piv);
+            }
+        }
+        __syncthreads();
+        if (s_stat[1] != 0.0) break;
+        const double lkk = A[k * lda + k];
+        const double inv = lkk > 0.0 ? 1.0 / lkk : 0.0;
+        for (int j = k + 1 + tid; j < d; j += nt) A[j * lda + k] *= inv;
+        __syncthreads();
+        // trailing update of the lower triangle: A[j][l] -= A[j][k]*A[l][k], k < l <= j
+        const int m = d - k - 1;
+        for (int idx = tid; idx < m * m; idx += nt) {
+            int jj = idx / m, ll = idx - jj * m;
+            if (ll <= jj) {
+                int j = k + 1 + jj, l = k + 1 + ll;
+                A[j * lda + l] = fma(-A[j * lda + k], A[l * lda + k], A[j * lda + l]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// mean / cov from shifted raw sums, then chol(cov) and its inverse.
+// sums = [S1 (d) | S2 (d*d) | a | b]; unweighted: n = b ; weighted: W = a (sum of weights).
+__global__ void __launch_bounds__(REE_LA_THREADS) k_moments_chol(const double* __restrict__ sums,
+                                                                 const double* __restrict__ shift, int d, int ddof,
+                                                                 int weighted, double* __restrict__ mean,
+                                                                 double* __restrict__ cov, double* __restrict__ L,
+                                                                 double* __restrict__ Linv, double* __restrict__ stats4) {
+    extern __shared__ double sm[];
+    const int lda = d + 1;
+    double* A = sm;                 // d x lda
+    double* ybar = A + d * lda;     // d
+    double* s_stat = ybar + d;      // 4
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double tot = weighted ? sums[d + d * d] : sums[d + d * d + 1];
+    for (int j = tid; j < d; j += nt) {
+        double yb = sums[j] / tot;
+        ybar[j] = yb;
+        mean[j] = (shift ? shift[j] : 0.0) + yb;
+    }
+    __syncthreads();
+    // np.cov: fact = W - ddof*sum(w^2)/W ; for the unweighted case w=1: fact = n - ddof.  The
+    // reference only uses (aweights, ddof=0) and (no weights, ddof=1)   solver.py:634-636, 671.
+    const double fact = tot - (double)ddof;
+    for (int idx = tid; idx < d * d; idx += nt) {
+        int j = idx / d, k = idx - j * d;
+        double c = (sums[d + idx] - tot * ybar[j] * ybar[k]) / fact;
+        A[j * lda + k] = c;
+        cov[idx] = c;
+    }
+    __syncthreads();
+    if (!L) return;
+    if (Linv)  // stays zero if the factorisation fails (callers check stats4[1])
+        for (int idx = tid; idx < d * d; idx += nt) Linv[idx] = 0.0;
+    chol_smem(A, d, lda, false, s_stat);
+    __syncthreads();
+    for (int idx = tid; idx < d * d; idx += nt) {
+        int j = idx / d, k = idx - j * d;
+        L[idx] = (k <= j) ? A[j * lda + k] : 0.0;
+    }
+    if (tid == 0) {
+        stats4[0] = s_stat[0];
+        stats4[1] = s_stat[1];
+        stats4[2] = s_stat[2];
+        stats4[3] = s_stat[3];
+    }
+    if (!Linv || s_stat[1] != 0.0) return;
+    // inverse of the lower factor, one column per thread: solve L x = e_c by forward substitution.
+    // x lives in global memory (row-major Linv => coalesced across the threads of a warp).
+    for (int c = tid; c < d; c += nt) {
+        for (int j = c; j < d; ++j) {
+            double s = (j == c) ? 1.0 : 0.0;
+            for (int k = c; k < j; ++k) s = fma(-A[j * lda + k], Linv[k * d + c], s);
+            Linv[j * d + c] = s / A[j * lda + j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(REE_LA_THREADS) k_chol_scaled(const double* __restrict__ C, int d, double scale,
+                                                                double* __restrict__ L, double* __restrict__ stats4) {
+    extern __shared__ double sm[];
+    const int lda = d + 1;
+    double* A = sm;
+    double* s_stat = A + d * lda;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int idx = tid; idx < d * d; idx += nt) {
+        int j = idx / d, k = idx - j * d;
+        // symmetrise from the lower triangle so that the factor does not depend on upper-triangle noise
+        double v = (k <= j) ? C[idx] : C[k * d + j];
+        A[j * lda + k] = scale * v;
+    }
+    __syncthreads();
+    chol_smem(A, d, lda, true, s_stat);
+    __syncthreads();
+    for (int idx = tid; idx < d * d; idx += nt) {
+        int j = idx / d, k = idx - j * d;
+        L[idx] = (k <= j) ? A[j * lda + k] : 0.0;
+    }
+    if (tid == 0 && stats4) {
+        stats4[0] = s_stat[0];
+        stats4[1] = s_stat[1];
+        stats4[2] = s_stat[2];
+        stats4[3] = s_stat[3];
+    }
+}
+
+extern "C" int ree_moments_chol(const double* sums, const double* shift, int d, int ddof, int weighted, double* mean,
+                                double* cov, double* L, double* Linv, double* stats4, void* stream) {
+    if (!sums || !mean || !cov || d < 1 || (L && !stats4))
+        return ree_set_error(REE_E_BADARG, "ree_moments_chol: bad argument");
+    if (d > REE_MAX_D) return ree_set_error(REE_E_UNSUPPORTED, "ree_moments_chol: d > 160 not supported");
+    size_t smem = ((size_t)d * (d + 1) + d + 4) * sizeof(double);
+    cudaFuncSetAttribute(k_moments_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_moments_chol<<<1, REE_LA_THREADS, smem, ree_stream(stream)>>>(sums, shift, d, ddof, weighted, mean, cov, L, Linv,
+                                                                    stats4);
+    return ree_check_launch("ree_moments_chol");
+}
+
+extern "C" int ree_chol_scaled(const double* C, int d, double scale, double* L, double* stats4, void* stream) {
+    if (!C || !L || d < 1) return ree_set_error(REE_E_BADARG, "ree_chol_scaled: bad argument");
+    if (d > REE_MAX_D) return ree_set_error(REE_E_UNSUPPORTED, "ree_chol_scaled: d > 160 not supported");
+    size_t smem = ((size_t)d * (d + 1) + 4) * sizeof(double);
+    cudaFuncSetAttribute(k_chol_scaled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_chol_scaled<<<1, REE_LA_THREADS, smem, ree_stream(stream)>>>(C, d, scale, L, stats4);
+    return ree_check_launch("ree_chol_scaled");
+}

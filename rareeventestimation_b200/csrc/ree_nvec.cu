@@ -1,0 +1,139 @@
+// N-vector kernels of the CBREE engine: log-target, ESS / CVAR / failure-count reductions.
+// HBM-bound streaming kernels (8-16 B per particle); fp64 warp-shuffle + block reductions with a
+// fixed-order two-stage combine (deterministic, no floating-point atomics).
+#include "common.cuh"
+
+// workspace layout for the small reductions: [0,8) doubles reserved for the ticket counter,
+// partial 4-tuples start at double index 8.
+#define REE_WS_HEADER 8
+
+// ---------------------------------------------------------------------------------------
+// last-block finalisation of per-CTA ExpSums partials (fixed order => run-to-run identical)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void expsums_grid_finalize(ExpSums blk, double* ws, double* out4, ExpSums* sh,
+                                                      bool* is_last) {
+    double* part = ws + REE_WS_HEADER;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
+    if (threadIdx.x == 0) {
+        double* p = part + 4 * (size_t)blockIdx.x;
+        p[0] = blk.m; p[1] = blk.s1; p[2] = blk.s2; p[3] = blk.cnt;
+        __threadfence();
+        unsigned int t = atomicInc(ticket, gridDim.x - 1);  // wraps to 0: self-resetting
+        *is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!*is_last) return;
+    __threadfence();
+    ExpSums v = expsums_empty();
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        const volatile double* p = part + 4 * (size_t)b;
+        ExpSums o{p[0], p[1], p[2], p[3]};
+        v = expsums_merge(v, o);
+    }
+    v = expsums_block_reduce(v, sh);
+    if (threadIdx.x == 0) {
+        out4[0] = v.m; out4[1] = v.s1; out4[2] = v.s2; out4[3] = v.cnt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(REE_THREADS) k_logtgt(const double* __restrict__ g, const double* __restrict__ e,
+                                                        int64_t n, double sigma, int kind, double* __restrict__ ell) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        ell[i] = ree_logtgt(g[i], e ? e[i] : 0.0, sigma, kind);
+}
+
+// a_i = beta * logtgt(g_i, e_i; sigma)   (my_softmax(log_tgt_evals * beta), solver.py:522, 595)
+__global__ void __launch_bounds__(REE_THREADS) k_reduce_ess(const double* __restrict__ g, const double* __restrict__ e,
+                                                            int64_t n, double sigma, double beta, int kind,
+                                                            double* ws, double* out4) {
+    __shared__ ExpSums sh[32];
+    __shared__ bool is_last;
+    ExpSums acc = expsums_empty();
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double a = __dmul_rn(ree_logtgt(g[i], e ? e[i] : 0.0, sigma, kind), beta);
+        if (isfinite(a)) expsums_add(acc, a, 1.0);
+    }
+    ExpSums blk = expsums_block_reduce(acc, sh);
+    expsums_grid_finalize(blk, ws, out4, sh, &is_last);
+}
+
+// a_i = logtgt(g_i,0;sigma_new) - logtgt(g_i,0;sigma_old)   (solver.py:538-545)
+__global__ void __launch_bounds__(REE_THREADS) k_reduce_cvar(const double* __restrict__ g, int64_t n,
+                                                             double sigma_new, double sigma_old, int kind,
+                                                             double* ws, double* out4) {
+    __shared__ ExpSums sh[32];
+    __shared__ bool is_last;
+    ExpSums acc = expsums_empty();
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double gi = g[i];
+        double a = __dsub_rn(ree_logtgt(gi, 0.0, sigma_new, kind), ree_logtgt(gi, 0.0, sigma_old, kind));
+        if (isfinite(a)) expsums_add(acc, a, 1.0);
+    }
+    ExpSums blk = expsums_block_reduce(acc, sh);
+    expsums_grid_finalize(blk, ws, out4, sh, &is_last);
+}
+
+__global__ void __launch_bounds__(REE_THREADS) k_count_failed(const double* __restrict__ g, int64_t n, double* ws,
+                                                              double* out1) {
+    __shared__ double sh[32];
+    __shared__ bool is_last;
+    double cnt = 0.0;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) cnt += (g[i] <= 0.0) ? 1.0 : 0.0;
+    cnt = block_sum(cnt, sh);
+    double* part = ws + REE_WS_HEADER;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = cnt;
+        __threadfence();
+        unsigned int t = atomicInc(ticket, gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double v = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) v += ((const volatile double*)part)[b];
+    v = block_sum(v, sh);  // integer-valued doubles: exact in any order
+    if (threadIdx.x == 0) out1[0] = v;
+}
+
+// ---------------------------------------------------------------------------------------
+static int nvec_grid(int64_t n) {
+    int64_t want = (n + REE_THREADS - 1) / REE_THREADS;
+    int cap = ree_grid_ctas();
+    return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+extern "C" int ree_logtgt(const double* g, const double* e, int64_t n, double sigma, int tgt_kind, double* ell,
+                          void* stream) {
+    if (!g || !ell || n < 0) return ree_set_error(REE_E_BADARG, "ree_logtgt: bad argument");
+    if (n == 0) return 0;
+    k_logtgt<<<nvec_grid(n), REE_THREADS, 0, ree_stream(stream)>>>(g, e, n, sigma, tgt_kind, ell);
+    return ree_check_launch("ree_logtgt");
+}
+
+extern "C" int ree_reduce_ess(const double* g, const double* e, int64_t n, double sigma, double beta, int tgt_kind,
+                              double* workspace, double* out4, void* stream) {
+    if (!g || !workspace || !out4 || n < 0) return ree_set_error(REE_E_BADARG, "ree_reduce_ess: bad argument");
+    k_reduce_ess<<<nvec_grid(n), REE_THREADS, 0, ree_stream(stream)>>>(g, e, n, sigma, beta, tgt_kind, workspace, out4);
+    return ree_check_launch("ree_reduce_ess");
+}
+
+extern "C" int ree_reduce_cvar(const double* g, int64_t n, double sigma_new, double sigma_old, int tgt_kind,
+                               double* workspace, double* out4, void* stream) {
+    if (!g || !workspace || !out4 || n < 0) return ree_set_error(REE_E_BADARG, "ree_reduce_cvar: bad argument");
+    k_reduce_cvar<<<nvec_grid(n), REE_THREADS, 0, ree_stream(stream)>>>(g, n, sigma_new, sigma_old, tgt_kind, workspace,
+                                                                        out4);
+    return ree_check_launch("ree_reduce_cvar");
+}
+
+extern "C" int ree_count_failed(const double* g, int64_t n, double* workspace, double* out1, void* stream) {
+    if (!g || !workspace || !out1 || n < 0) return ree_set_error(REE_E_BADARG, "ree_count_failed: bad argument");
+    k_count_failed<<<nvec_grid(n), REE_THREADS, 0, ree_stream(stream)>>>(g, n, workspace, out1);
+    return ree_check_launch("ree_count_failed");
+}

@@ -1,0 +1,326 @@
+"""Device engine: owns the HBM-resident particle ensemble (SoA) and drives the sm_100a kernels of
+``libree_b200.so`` through the C ABI.  PyTorch is used for device memory, streams and
+``torch.distributed`` only; every N-sized computation is a hand-written CUDA kernel.
+
+Sharding: one process per GPU; each rank keeps a contiguous slice of the particles
+for the whole solve.  Only per-iteration partial sums cross ranks (``all_reduce`` of the packed raw
+sums, ``all_gather`` of the max-shifted 4-tuples), so every rank holds bit-identical consensus
+statistics and runs the identical host control flow.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ReeError, ReeLsf, check
+
+F64 = torch.float64
+
+
+# --------------------------------------------------------------------------- #
+# cross-rank combination of partial statistics (pure tensor logic: testable on CPU/gloo)
+# --------------------------------------------------------------------------- #
+def merge_expsums(parts: torch.Tensor) -> torch.Tensor:
+    """Merge (R,4) rows [M, S1, S2, cnt] of max-shifted exponential sums in fixed rank order.
+
+    sum exp(a) = exp(M) S1, sum exp(2a) = exp(2M) S2; result is shifted to the global max."""
+    M = parts[:, 0]
+    top = torch.max(M)
+    if not torch.isfinite(top):
+        out = parts.sum(dim=0)
+        out[0] = top
+        return out
+    f = torch.exp(M - top)
+    f = torch.where(torch.isfinite(M), f, torch.zeros_like(f))
+    return torch.stack([top, (parts[:, 1] * f).sum(), (parts[:, 2] * f * f).sum(), parts[:, 3].sum()])
+
+
+class Comm:
+    """Thin wrapper over a torch.distributed process group (or a single process)."""
+
+    def __init__(self, group=None, enabled: Optional[bool] = None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        if enabled is None:
+            enabled = dist.is_available() and dist.is_initialized()
+        self.enabled = bool(enabled) and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.group = group
+        self.rank = dist.get_rank(group) if self.enabled else 0
+        self.world = dist.get_world_size(group) if self.enabled else 1
+
+    def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+        if self.enabled:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def combine_expsums_(self, out4: torch.Tensor) -> torch.Tensor:
+        """all_gather the local 4-tuple and merge in rank order (identical bits on every rank)."""
+        if self.enabled:
+            gathered = torch.empty((self.world, 4), dtype=out4.dtype, device=out4.device)
+            self.dist.all_gather_into_tensor(gathered, out4.contiguous(), group=self.group)
+            out4.copy_(merge_expsums(gathered))
+        return out4
+
+    def shard(self, n_global: int):
+        """Contiguous slice [lo, hi) of this rank."""
+        base, rem = divmod(int(n_global), self.world)
+        lo = self.rank * base + min(self.rank, rem)
+        return lo, lo + base + (1 if self.rank < rem else 0)
+
+
+# --------------------------------------------------------------------------- #
+@dataclass
+class DeviceLsf:
+    """Device descriptor of a limit-state function (struct ree_lsf) + the tensors it points to."""
+
+    kind: int
+    d: int
+    coef: Optional[torch.Tensor] = None
+    offset: float = 0.0
+    p0: float = 0.0
+    p1: float = 0.0
+    n_ele: int = 0
+
+    def struct(self) -> ReeLsf:
+        return ReeLsf(self.kind, self.d, self.coef.data_ptr() if self.coef is not None else None, self.offset,
+                      self.p0, self.p1, self.n_ele, 0)
+
+
+class Ensemble:
+    """An HBM-resident ensemble: X is SoA ``[d][ld]`` fp64, g / e are the per-particle LSF and energy."""
+
+    __slots__ = ("X", "g", "e", "n", "d", "ld", "first")
+
+    def __init__(self, X, n, d, ld, first=0, g=None, e=None):
+        self.X, self.n, self.d, self.ld, self.first = X, int(n), int(d), int(ld), int(first)
+        self.g, self.e = g, e
+
+
+def _pad(n: int) -> int:
+    return max(8, (int(n) + 7) // 8 * 8)
+
+
+class Engine:
+    """One engine per (process, device)."""
+
+    _instances = {}
+
+    @classmethod
+    def get(cls, device=None, comm: Optional[Comm] = None) -> "Engine":
+        if not torch.cuda.is_available():
+            raise ReeError("rareeventestimation_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        device = torch.device(device)
+        key = (device.index if device.index is not None else torch.cuda.current_device())
+        eng = cls._instances.get(key)
+        if eng is None:
+            eng = cls._instances[key] = Engine(torch.device("cuda", key))
+        eng.comm = comm if comm is not None else Comm()
+        return eng
+
+    def __init__(self, device: torch.device):
+        self.lib = _lib.load()
+        self.device = device
+        self.comm = Comm(enabled=False)
+        self._ws = {}
+        self._staging = None
+        with torch.cuda.device(self.device):
+            self.num_ctas = self.lib.ree_num_ctas()
+
+    # -- plumbing ------------------------------------------------------------ #
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def sync(self):
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def workspace(self, d: int) -> torch.Tensor:
+        ws = self._ws.get(d)
+        if ws is None:
+            with torch.cuda.device(self.device):
+                nbytes = self.lib.ree_workspace_bytes(d)
+            ws = self._ws[d] = torch.zeros(nbytes // 8 + 8, dtype=F64, device=self.device)
+        return ws
+
+    def staging(self, elems: int) -> torch.Tensor:
+        if self._staging is None or self._staging.numel() < elems:
+            self._staging = torch.empty(elems, dtype=F64, device=self.device)
+        return self._staging
+
+    def empty(self, *shape):
+        return torch.empty(*shape, dtype=F64, device=self.device)
+
+    def zeros(self, *shape):
+        return torch.zeros(*shape, dtype=F64, device=self.device)
+
+    def to_device(self, arr) -> torch.Tensor:
+        a = np.ascontiguousarray(np.asarray(arr, dtype=np.float64))
+        return torch.from_numpy(a).to(self.device, non_blocking=False)
+
+    # -- ensemble I/O ---------------------------------------------------------- #
+    def alloc_ensemble(self, n: int, d: int, first: int = 0, with_vectors=True) -> Ensemble:
+        ld = _pad(n)
+        X = self.empty(d, ld)
+        g = self.empty(ld) if with_vectors else None
+        e = self.empty(ld) if with_vectors else None
+        return Ensemble(X, n, d, ld, first, g, e)
+
+    def upload(self, host: np.ndarray, first: int = 0) -> Ensemble:
+        """Host (n,d) C-order array -> SoA ensemble (chunked H2D + device transpose)."""
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        if host.ndim != 2:
+            raise ValueError("ensemble must be a 2-d array (n, d)")
+        n, d = host.shape
+        ens = self.alloc_ensemble(n, d, first)
+        rows = max(1, min(n, (64 << 20) // (8 * d)))
+        st = self.staging(rows * d)
+        check(self.lib.ree_upload_ensemble(host.ctypes.data, ens.X.data_ptr(), n, d, ens.ld, st.data_ptr(),
+                                           st.numel(), self.stream), "ree_upload_ensemble")
+        return ens
+
+    def download(self, ens: Ensemble, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((ens.n, ens.d), dtype=np.float64)
+        rows = max(1, min(ens.n, (64 << 20) // (8 * ens.d)))
+        st = self.staging(rows * ens.d)
+        check(self.lib.ree_download_ensemble(ens.X.data_ptr(), out.ctypes.data, ens.n, ens.d, ens.ld, st.data_ptr(),
+                                             st.numel(), self.stream), "ree_download_ensemble")
+        return out
+
+    def upload_vector(self, v: np.ndarray, ld: int) -> torch.Tensor:
+        t = self.empty(ld)
+        t[: v.shape[0]].copy_(torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)))
+        return t
+
+    def philox_normal(self, n: int, d: int, seed: int, draw: int, first: int = 0, out: Optional[Ensemble] = None):
+        """Device N(0,1) block with rank-invariant counters (global particle index)."""
+        ens = out if out is not None else self.alloc_ensemble(n, d, first)
+        check(self.lib.ree_philox_normal(ens.X.data_ptr(), n, d, ens.ld, seed & (2**64 - 1), draw, first,
+                                         self.stream), "ree_philox_normal")
+        return ens
+
+    # -- evaluation ------------------------------------------------------------ #
+    def lsf_eval(self, lsf: DeviceLsf, ens: Ensemble, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        g = out if out is not None else self.empty(ens.ld)
+        s = lsf.struct()
+        check(self.lib.ree_lsf_eval(C.byref(s), ens.X.data_ptr(), ens.n, ens.ld, g.data_ptr(), self.stream),
+              "ree_lsf_eval")
+        return g
+
+    def energy(self, ens: Ensemble, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        e = out if out is not None else self.empty(ens.ld)
+        check(self.lib.ree_energy(ens.X.data_ptr(), ens.n, ens.d, ens.ld, e.data_ptr(), self.stream), "ree_energy")
+        return e
+
+    def logtgt(self, g, e, n, sigma, kind) -> torch.Tensor:
+        out = self.empty(g.numel())
+        check(self.lib.ree_logtgt(g.data_ptr(), e.data_ptr() if e is not None else None, n, float(sigma), kind,
+                                  out.data_ptr(), self.stream), "ree_logtgt")
+        return out
+
+    # -- reductions (return device 4-vectors, already combined across ranks) ----- #
+    def reduce_ess(self, ens: Ensemble, sigma, beta, kind, out=None, use_e=True) -> torch.Tensor:
+        out = out if out is not None else self.empty(4)
+        ws = self.workspace(ens.d)
+        check(self.lib.ree_reduce_ess(ens.g.data_ptr(), ens.e.data_ptr() if use_e else None, ens.n, float(sigma),
+                                      float(beta), kind, ws.data_ptr(), out.data_ptr(), self.stream),
+              "ree_reduce_ess")
+        return self.comm.combine_expsums_(out)
+
+    def reduce_cvar(self, ens: Ensemble, sigma_new, sigma_old, kind, out=None) -> torch.Tensor:
+        out = out if out is not None else self.empty(4)
+        ws = self.workspace(ens.d)
+        check(self.lib.ree_reduce_cvar(ens.g.data_ptr(), ens.n, float(sigma_new), float(sigma_old), kind,
+                                       ws.data_ptr(), out.data_ptr(), self.stream), "ree_reduce_cvar")
+        return self.comm.combine_expsums_(out)
+
+    def count_failed(self, ens: Ensemble, out=None) -> torch.Tensor:
+        out = out if out is not None else self.empty(1)
+        ws = self.workspace(ens.d)
+        check(self.lib.ree_count_failed(ens.g.data_ptr(), ens.n, ws.data_ptr(), out.data_ptr(), self.stream),
+              "ree_count_failed")
+        return self.comm.allreduce_sum_(out)
+
+    # -- sweeps ------------------------------------------------------------------- #
+    def ensemble_sums(self, ens: Ensemble, shift: Optional[torch.Tensor], sums: torch.Tensor, with_g=True):
+        ws = self.workspace(ens.d)
+        check(self.lib.ree_ensemble_sums(ens.X.data_ptr(), ens.n, ens.d, ens.ld,
+                                         ens.g.data_ptr() if (with_g and ens.g is not None) else None,
+                                         shift.data_ptr() if shift is not None else None, ws.data_ptr(),
+                                         sums.data_ptr(), self.stream), "ree_ensemble_sums")
+        return self.comm.allreduce_sum_(sums)
+
+    def cbree_step(self, src: Ensemble, dst: Ensemble, t: float, m_noise: torch.Tensor, F: torch.Tensor,
+                   lsf: Optional[DeviceLsf], shift: Optional[torch.Tensor], sums: torch.Tensor,
+                   z: Optional[Ensemble] = None, seed: int = 0, draw: int = 0, reduce=True):
+        ws = self.workspace(src.d)
+        s = lsf.struct() if lsf is not None else None
+        mode = _lib.NOISE_INJECT if z is not None else _lib.NOISE_PHILOX
+        if z is not None and z.ld != src.ld:
+            raise ValueError("noise block must share the ensemble's leading dimension")
+        check(self.lib.ree_cbree_step(src.X.data_ptr(), dst.X.data_ptr(), src.n, src.d, src.ld, float(t),
+                                      m_noise.data_ptr(), F.data_ptr(), mode,
+                                      z.X.data_ptr() if z is not None else None, seed & (2**64 - 1), draw,
+                                      src.first, C.byref(s) if s is not None else None,
+                                      shift.data_ptr() if shift is not None else None, dst.g.data_ptr(),
+                                      dst.e.data_ptr(), ws.data_ptr(), sums.data_ptr(), self.stream),
+              "ree_cbree_step")
+        if reduce:
+            self.comm.allreduce_sum_(sums)
+        return sums
+
+    def moments_chol(self, sums, shift, d, ddof, weighted, mean, cov, L=None, Linv=None, stats=None):
+        check(self.lib.ree_moments_chol(sums.data_ptr(), shift.data_ptr() if shift is not None else None, d, ddof,
+                                        1 if weighted else 0, mean.data_ptr(), cov.data_ptr(),
+                                        L.data_ptr() if L is not None else None,
+                                        Linv.data_ptr() if Linv is not None else None,
+                                        stats.data_ptr() if stats is not None else None, self.stream),
+              "ree_moments_chol")
+
+    def chol_scaled(self, Cmat: torch.Tensor, d: int, scale: float, L: torch.Tensor, stats: torch.Tensor):
+        check(self.lib.ree_chol_scaled(Cmat.data_ptr(), d, float(scale), L.data_ptr(), stats.data_ptr(),
+                                       self.stream), "ree_chol_scaled")
+
+    def cbree_maha(self, ens: Ensemble, mean, Linv, logdet, sigma, beta, kind, wmax, shift, w, sums, is4,
+                   logq=None):
+        ws = self.workspace(ens.d)
+        check(self.lib.ree_cbree_maha(ens.X.data_ptr(), ens.n, ens.d, ens.ld, ens.g.data_ptr(), ens.e.data_ptr(),
+                                      mean.data_ptr(), Linv.data_ptr(), logdet.data_ptr(), float(sigma),
+                                      float(beta), kind, wmax.data_ptr(),
+                                      shift.data_ptr() if shift is not None else None,
+                                      logq.data_ptr() if logq is not None else None, w.data_ptr(), ws.data_ptr(),
+                                      sums.data_ptr(), is4.data_ptr(), self.stream), "ree_cbree_maha")
+        self.comm.allreduce_sum_(sums)
+        self.comm.combine_expsums_(is4)
+
+
+# --------------------------------------------------------------------------- #
+# host-side formulas on the reduced 4-tuples
+# --------------------------------------------------------------------------- #
+def ess_from(t4) -> float:
+    """(sum w)^2 / sum w^2 from [M, S1, S2, cnt]   (solver.py:523, 596)."""
+    return float(t4[1]) ** 2 / float(t4[2])
+
+
+def cvar_from(t4) -> float:
+    """Coefficient of variation of exp(a)*mult from the shifted sums, with my_log_cvar's conventions
+    (utilities.py:76-102): inf if the mean is zero or the result is NaN; mean/std over the finite entries."""
+    nf = float(t4[3])
+    if nf <= 0:
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")
+    mean = float(t4[1]) / nf
+    if mean == 0:
+        return math.inf
+    var = float(t4[2]) / nf - mean * mean
+    out = math.sqrt(max(var, 0.0)) / mean
+    return math.inf if math.isnan(out) else out

@@ -1,0 +1,803 @@
+"""Solvers with the reference's API (``src/rareeventestimation/solver.py``) on the B200 engine.
+
+``CBREE.solve`` keeps the reference's *scalar* control flow on the host -- sigma/beta adaptation,
+step-size controller, convergence checks, Solution assembly (solver.py:365-503) -- while every
+N-sized operation runs in the CUDA kernels behind :class:`~.engine.Engine`.  The host only sees
+d x d / scalar statistics.
+"""
+from __future__ import annotations
+
+import logging
+import math
+import warnings
+from copy import deepcopy
+from numbers import Real
+from typing import Optional
+
+import numpy as np
+from scipy.optimize import minimize_scalar, root
+
+from . import _lib
+from .engine import Comm, DeviceLsf, Engine, Ensemble, cvar_from, ess_from
+from .lsf import DeviceLSF
+from .problem import DeviceSample, NormalProblem, Problem, ShardedHostSample
+from .solution import Solution
+
+_log = logging.getLogger(__name__)
+_STREAM_STEP = 0x01 << 24  # Philox draw index base of the Euler-Maruyama noise
+
+
+def warn(msg):
+    """The reference reports step failures through ``distutils.log.warn`` (solver.py:5, 430)."""
+    warnings.warn(str(msg), RuntimeWarning, stacklevel=2)
+
+
+class MixtureModel:
+    """Placeholder stored in every cache (mixturemodel.py:29-40); the GM path never fits it."""
+
+    def __init__(self, num_comps: int) -> None:
+        self.num_comps = num_comps
+        self.fitted = False
+
+
+class LazyHistory:
+    """(S, N, d) or (S, N) history that lives in HBM and is downloaded on access."""
+
+    def __init__(self, caches, attr):
+        self._caches, self._attr = list(caches), attr
+        first = getattr(caches[0], "_shape_" + attr)
+        self.shape = (len(caches),) + tuple(first)
+        self.ndim = len(self.shape)
+        self.dtype = np.dtype(np.float64)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, idx):
+        if isinstance(idx, (int, np.integer)):
+            return getattr(self._caches[idx], self._attr)
+        if isinstance(idx, tuple) and isinstance(idx[0], (int, np.integer)):
+            return getattr(self._caches[idx[0]], self._attr)[idx[1:]]
+        return np.asarray(self)[idx]
+
+    def __array__(self, dtype=None, copy=None):
+        return np.array([getattr(c, self._attr) for c in self._caches]).squeeze()
+
+
+class CBREECache:
+    """Per-iteration state with the reference's field names (solver.py:63-116).
+
+    ``ensemble`` / ``lsf_evals`` / ``e_fun_evals`` are HBM resident; reading the attributes downloads
+    them, assigning to them (as callbacks may, solver.py:439-446) uploads on the next use."""
+
+    def __init__(self, engine: Engine, dev: Ensemble, sigma=1, beta=1, t_step=0.5, mixture_model=None,
+                 num_lsf_evals=0):
+        self._engine = engine
+        self._dev = dev
+        self._host = {}
+        self._dirty = set()
+        self._shape_ensemble = (dev.n, dev.d)
+        self._shape_lsf_evals = (dev.n,)
+        self._shape_e_fun_evals = (dev.n,)
+        self._cw_dirty = False
+        self.weighted_mean = None
+        self.weighted_cov = None
+        self.sigma = sigma
+        self.beta = beta
+        self.t_step = t_step
+        self.cvar_is_weights = math.nan
+        self.mixture_model = mixture_model if mixture_model is not None else MixtureModel(1)
+        self.converged = False
+        self.iteration = 0
+        self.slope_cvar = math.nan
+        self.sfp_slope = math.nan
+        self.estimate = 0.0
+        self.estimate_uniform_avg = 0.0
+        self.estimate_sqrt_avg = 0.0
+        self.estimate_cvar_avg = 0.0
+        self.sfp = 0.0
+        self.ess = math.nan
+        self.num_lsf_evals = num_lsf_evals
+        self.msg = ""
+        # engine-side extras: unweighted moments of the ensemble and their device copies
+        self.ens_mean = None
+        self.ens_cov = None
+        self.num_failed = 0.0
+        self._stats = None  # device tensors of the last post-processing (see CBREE._post_ensemble)
+        self._chol_info = 0
+
+    FIELDS = ["ensemble", "lsf_evals", "e_fun_evals", "weighted_mean", "weighted_cov", "sigma", "beta", "t_step",
+              "cvar_is_weights", "mixture_model", "converged", "iteration", "slope_cvar", "sfp_slope", "estimate",
+              "estimate_uniform_avg", "estimate_sqrt_avg", "estimate_cvar_avg", "sfp", "ess", "num_lsf_evals", "msg"]
+
+    # -- lazily materialised N-sized fields ---------------------------------- #
+    def _get(self, name):
+        if name not in self._host:
+            eng, dev = self._engine, self._dev
+            if name == "ensemble":
+                self._host[name] = eng.download(dev)
+            else:
+                t = dev.g if name == "lsf_evals" else dev.e
+                self._host[name] = t[: dev.n].cpu().numpy()
+        return self._host[name]
+
+    def _set(self, name, value):
+        self._host[name] = np.asarray(value, dtype=np.float64)
+        self._dirty.add(name)
+
+    ensemble = property(lambda s: s._get("ensemble"), lambda s, v: s._set("ensemble", v))
+    lsf_evals = property(lambda s: s._get("lsf_evals"), lambda s, v: s._set("lsf_evals", v))
+    e_fun_evals = property(lambda s: s._get("e_fun_evals"), lambda s, v: s._set("e_fun_evals", v))
+
+    def sync_to_device(self) -> bool:
+        """Upload fields a callback replaced.  Returns True if anything changed."""
+        if not self._dirty:
+            return False
+        eng, dev = self._engine, self._dev
+        if "ensemble" in self._dirty:
+            new = eng.upload(self._host["ensemble"], first=dev.first)
+            new.g, new.e = dev.g, dev.e
+            if new.ld != dev.ld:
+                new.g, new.e = eng.empty(new.ld), eng.empty(new.ld)
+            self._dev = dev = new
+            self._shape_ensemble = (dev.n, dev.d)
+            self._shape_lsf_evals = (dev.n,)
+        if "lsf_evals" in self._dirty:
+            dev.g[: dev.n].copy_(eng.to_device(self._host["lsf_evals"]))
+        if "e_fun_evals" in self._dirty:
+            dev.e[: dev.n].copy_(eng.to_device(self._host["e_fun_evals"]))
+        self._dirty.clear()
+        return True
+
+    def __deepcopy__(self, memo):
+        new = CBREECache.__new__(CBREECache)
+        for k, v in self.__dict__.items():
+            if k in ("_engine", "_dev", "_stats"):
+                new.__dict__[k] = v  # device buffers are immutable once a cache is finished
+            else:
+                new.__dict__[k] = deepcopy(v, memo)
+        return new
+
+
+def flatten_cache_list(cache_list: list, attrs=None, lazy_bytes=64 << 20) -> dict:
+    """dict attr -> stacked values over the caches (solver.py:119-136).  N-sized attributes above
+    ``lazy_bytes`` stay in HBM behind a :class:`LazyHistory`."""
+    if attrs is None:
+        attrs = CBREECache.FIELDS
+    out = dict.fromkeys(attrs)
+    for a in attrs:
+        if a in ("ensemble", "lsf_evals", "e_fun_evals"):
+            shp = cache_list[0]._shape_ensemble if a == "ensemble" else cache_list[0]._shape_lsf_evals
+            if len(cache_list) * int(np.prod(shp)) * 8 > lazy_bytes:
+                out[a] = LazyHistory(cache_list, a)
+                continue
+        v = [getattr(c, a) for c in cache_list if getattr(c, a) is not None]
+        out[a] = np.array(v).squeeze()
+    return out
+
+
+def get_slope(y) -> float:
+    """Slope of a least-squares line through (i, y[i]); NaN if any entry is non-finite (utilities.py:145-163)."""
+    y = np.atleast_1d(np.asarray(y, dtype=np.float64))
+    if not np.all(np.isfinite(y)):
+        return math.nan
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return np.polyfit(np.arange(len(y)), y, deg=1, full=True)[0][0]
+    except Exception:
+        return math.nan
+
+
+class Solver:
+    """Methods to estimate the rare event probability of a `Problem` (solver.py:139-165)."""
+
+    def __init__(self) -> None:
+        pass
+
+    def solve(self, prob: Problem):
+        raise NotImplementedError
+
+    def set_options(self, options: dict, in_situ=True):
+        """Reset members already in ``vars(self)``; ``in_situ=False`` returns a configured deep copy."""
+        if in_situ:
+            for k, v in options.items():
+                if k in vars(self):
+                    setattr(self, k, v)
+        else:
+            other = deepcopy(self)
+            other.set_options(options)
+            return other
+
+
+class _CountingLsf:
+    """``solver.lsf``: counts evaluations like ``my_lsf`` in solver.py:376-381."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self.counter = 0
+
+    def __call__(self, x):
+        self.counter += int(np.prod(np.shape(x)[:-1]))
+        return self.fn(x)
+
+
+class CBREE(Solver):
+    """Consensus-based rare event estimation.  Constructor options and defaults are the reference's
+    (solver.py:176-200); engine options are keyword-only additions that default to reference behaviour:
+
+    noise: "philox" (device Philox4x32-10 counters, seeded by ``seed``) or "numpy" (draw Z on the host
+           from ``self.rng`` exactly like ``rng.multivariate_normal`` does, then inject -- parity mode).
+    """
+
+    def __init__(self, stepsize_tolerance=0.5, t_step=-1, num_steps=100, tgt_fun="algebraic", observation_window=5,
+                 seed=None, sigma_adaptivity="cvar", beta_adaptivity=True, cvar_tgt=2, sfp_tgt=1 / 3, ess_tgt=1 / 2,
+                 lip_sigma=1, divergence_check=True, convergence_check=True, mixture_model="GM", resample=False,
+                 verbose=False, save_history=False, return_other=False, return_caches=False, name=None,
+                 callback=None, *, noise="philox", quiet=False) -> None:
+        super().__init__()
+        if t_step > 0:
+            self.stepsize_adaptivity = False
+            self.t_step = t_step
+        else:
+            self.stepsize_adaptivity = True
+        if not quiet:
+            print(f"adaptive: {self.stepsize_adaptivity}")  # solver.py:267
+        if isinstance(sigma_adaptivity, str):
+            assert sigma_adaptivity in ["cvar", "sfp"]
+            self.sigma = 0
+            self.sigma_adaptivity = sigma_adaptivity
+        else:
+            assert sigma_adaptivity > 0, \
+                f"sigma_adaptivity must be either `cvar`, `sfp` or `True`. I got '{sigma_adaptivity}'"
+            self.sigma = sigma_adaptivity
+            self.sigma_adaptivity = "constant"
+        if beta_adaptivity is True:
+            self.beta = 1
+            self.beta_adaptivity = beta_adaptivity
+        else:
+            assert beta_adaptivity > 0, \
+                f"beta_adaptivity must be either a positive number or `True`. I got '{beta_adaptivity}'"
+            self.beta = beta_adaptivity
+            self.beta_adaptivity = False
+        self.num_comps = 1
+        self.stepsize_tolerance = stepsize_tolerance
+        self.num_steps = num_steps
+        self.tgt_fun = tgt_fun
+        self.observation_window = observation_window
+        self.seed = seed
+        self.rng = np.random.default_rng(self.seed)
+        self.cvar_tgt = cvar_tgt
+        self.sfp_tgt = sfp_tgt
+        self.ess_tgt = ess_tgt
+        self.lip_sigma = lip_sigma
+        self.divergence_check = divergence_check
+        self.convergence_check = convergence_check
+        self.mixture_model = mixture_model
+        self.resample = resample
+        self.verbose = verbose
+        self.save_history = save_history
+        self.return_other = return_other
+        self.return_caches = return_caches
+        self.name = name
+        self.callback = callback
+        assert noise in ("philox", "numpy")
+        self.noise = noise
+
+    def __str__(self) -> str:
+        return self.name if self.name is not None else "CBREE"
+
+    # ------------------------------------------------------------------ #
+    # engine glue
+    # ------------------------------------------------------------------ #
+    def _tgt_kind(self) -> int:
+        # unknown names fall through to the sigmoid like the reference's else-branch (solver.py:361)
+        return _lib.TGT_KINDS.get(self.tgt_fun, _lib.TGT_KINDS["sigmoid"])
+
+    def _setup(self, prob: Problem):
+        if self.resample or self.mixture_model != "GM":
+            raise NotImplementedError("only the Gaussian (GM, resample=False) CBREE path is built "
+                                      "(vMFNM resampling: SURVEY.md 8f rank 2)")
+        self._eng = Engine.get()
+        self._prob = prob
+        lsf = prob.lsf
+        self._dev_lsf_obj = lsf if isinstance(lsf, DeviceLSF) else None
+        self._device_energy = getattr(prob.e_fun, "is_standard_normal", False)
+        self.lsf = _CountingLsf(prob.lsf)
+        self.e_fun = prob.e_fun
+        self._step_draws = 0
+        self._philox_seed = int(self.rng.integers(0, 2**63 - 1)) if self.noise == "philox" else 0
+
+    def _lsf_descriptor(self, d) -> Optional[DeviceLsf]:
+        return self._dev_lsf_obj.descriptor(self._eng, d) if self._dev_lsf_obj is not None else None
+
+    def _evaluate_external(self, dev: Ensemble, need_g: bool, need_e: bool):
+        """Host callbacks for user-supplied Python LSFs / energies (README example): a D2H/H2D bridge
+        around *user* code, not an engine fallback."""
+        eng = self._eng
+        X = eng.download(dev)
+        if need_g:
+            g = np.asarray(self._prob.lsf(X), dtype=np.float64).reshape(-1)
+            dev.g[: dev.n].copy_(eng.to_device(g))
+        if need_e:
+            e = np.asarray(self._prob.e_fun(X), dtype=np.float64).reshape(-1)
+            dev.e[: dev.n].copy_(eng.to_device(e))
+
+    def _n_global(self, dev: Ensemble) -> int:
+        return self._n_total
+
+    def _initial_ensemble(self, prob: Problem) -> Ensemble:
+        eng = self._eng
+        sample = prob.sample
+        n_total = int(sample.shape[0])
+        self._n_total = n_total
+        lo, hi = eng.comm.shard(n_total)
+        if isinstance(sample, DeviceSample):
+            dev = sample.materialise(eng, lo, hi)
+        elif isinstance(sample, ShardedHostSample):
+            if sample.lo != lo or sample.local.shape[0] != hi - lo:
+                raise ValueError("ShardedHostSample does not match this rank's particle range")
+            dev = eng.upload(sample.local, first=lo)
+        else:
+            dev = eng.upload(np.asarray(sample)[lo:hi], first=lo)
+        desc = self._lsf_descriptor(dev.d)
+        if desc is not None:
+            eng.lsf_eval(desc, dev, out=dev.g)
+        if self._device_energy:
+            eng.energy(dev, out=dev.e)
+        if desc is None or not self._device_energy:
+            self._evaluate_external(dev, desc is None, not self._device_energy)
+        self.lsf.counter += n_total
+        return dev
+
+    # ------------------------------------------------------------------ #
+    # post-processing of an ensemble: moments, IS density, weights  (device)
+    # ------------------------------------------------------------------ #
+    def _post_ensemble(self, cache: CBREECache, sums_ready=None,
+                       shift_u=None, shift_w=None):
+        """Everything the reference derives from (X, g, e, sigma, beta) of one cache:
+        unweighted mean/cov + factorisation (solver.py:670-674), ESS shift (my_softmax), Mahalanobis sweep with
+        IS statistics (683-686, 843-846) and the weighted mean/cov (629-636).  One D2H copy at the end."""
+        eng, dev = self._eng, cache._dev
+        d = dev.d
+        kind = self._tgt_kind()
+        slen = d + d * d + 2
+        # packed result buffer: [mean d | cov d*d | m_w d | C_w d*d | stats 4 | is4 4 | ess4 4 | sums_u tail 2 | sums_w tail 2]
+        res = eng.empty(2 * d + 2 * d * d + 16)
+        mean, cov = res[0:d], res[d:d + d * d]
+        m_w, C_w = res[d + d * d:2 * d + d * d], res[2 * d + d * d:2 * d + 2 * d * d]
+        o = 2 * d + 2 * d * d
+        stats, is4, ess4 = res[o:o + 4], res[o + 4:o + 8], res[o + 8:o + 12]
+        tails = res[o + 12:o + 16]
+        L, Linv = eng.empty(d * d), eng.empty(d * d)
+        if sums_ready is None:
+            sums_u = eng.empty(slen)
+            eng.ensemble_sums(dev, shift_u, sums_u)
+        else:
+            sums_u = sums_ready
+        eng.moments_chol(sums_u, shift_u, d, 1, False, mean, cov, L, Linv, stats)
+        eng.reduce_ess(dev, cache.sigma, cache.beta, kind, out=ess4)
+        sums_w = eng.empty(slen)
+        w = eng.empty(dev.ld)
+        eng.cbree_maha(dev, mean, Linv, stats[0:1], cache.sigma, cache.beta, kind, ess4[0:1], shift_w, w, sums_w,
+                       is4)
+        eng.moments_chol(sums_w, shift_w, d, 0, True, m_w, C_w)
+        tails[0:2].copy_(sums_u[d + d * d:])
+        tails[2:4].copy_(sums_w[d + d * d:])
+        host = res.cpu().numpy()  # the one synchronising D2H of the iteration
+        cache.ens_mean = host[0:d].copy()
+        cache.ens_cov = host[d:d + d * d].reshape(d, d).copy()
+        cache.weighted_mean = host[d + d * d:2 * d + d * d].copy()
+        cache.weighted_cov = host[2 * d + d * d:o].reshape(d, d).copy()
+        st, i4, e4, tl = host[o:o + 4], host[o + 4:o + 8], host[o + 8:o + 12], host[o + 12:o + 16]
+        cache._stats = dict(C_w=C_w)  # view into `res`; the O(N) scratch (w, L, Linv) is released here
+        cache._chol_info = int(st[1])
+        cache._min_pivot, cache._max_diag = float(st[2]), float(st[3])
+        cache.num_failed = float(tl[0])
+        n_tot = float(tl[1])
+        cache._is4 = i4.copy()
+        cache._ess4 = e4.copy()
+        cache._n_total = n_tot
+        if e4[3] <= 0:  # my_softmax on an all-non-finite vector (utilities.py:121)
+            raise ValueError("attempt to get argmax of an empty sequence")
+        return cache
+
+    def _finish_is_stats(self, cache: CBREECache):
+        """cvar_is_weights (solver.py:683-686) and the IS estimate (843-846) from the sweep-2 sums."""
+        self._check_density(cache)
+        cache.cvar_is_weights = cvar_from(cache._is4)
+        cache.estimate = self._estimate_of(cache)
+
+    def _estimate_of(self, cache: CBREECache) -> float:
+        R, s1 = float(cache._is4[0]), float(cache._is4[1])
+        if s1 == 0.0 or not math.isfinite(R):
+            return 0.0
+        return math.exp(R) * s1 / cache._n_total
+
+    def _check_density(self, cache: CBREECache):
+        """SciPy's multivariate_normal refuses (numerically) singular covariances;
+        the factorisation reports the same condition through its pivots."""
+        if cache._chol_info != 0 or not (cache._min_pivot > 2.220446049250313e-10 * cache._max_diag):
+            raise np.linalg.LinAlgError(
+                "When `allow_singular is False`, the input matrix must be symmetric positive definite.")
+
+    def _compute_weights_check(self, cache: CBREECache):
+        if not np.isfinite(cache.weighted_cov).all():  # solver.py:637-638
+            raise ValueError("Weighted covariance contains non-finite elements.")
+
+    # ------------------------------------------------------------------ #
+    # sigma / beta (host optimisers, device objectives)
+    # ------------------------------------------------------------------ #
+    def _sfp_now(self, cache: CBREECache) -> float:
+        return cache.num_failed / cache._n_total
+
+    def _update_sigma_sfp(self, cache: CBREECache) -> None:
+        """solver.py:564-580."""
+        current = self._sfp_now(cache)
+        delta_max = self.lip_sigma * np.log(1 / cache.t_step)
+        if self.sfp_tgt > np.finfo(float).eps:
+            delta = np.sqrt(np.maximum(0, self.sfp_tgt - current)) * delta_max / np.sqrt(self.sfp_tgt)
+        else:
+            delta = 0
+        cache.sigma += delta
+
+    def _update_sigma_cvar(self, cache: CBREECache) -> None:
+        """solver.py:525-562: closed form while too few particles failed, else bounded Brent on the
+        squared CVAR mismatch; each objective evaluation is one ``ree_reduce_cvar`` sweep over g."""
+        eng, dev, kind = self._eng, cache._dev, self._tgt_kind()
+        try:
+            if self._sfp_now(cache) < self.sfp_tgt:
+                self._update_sigma_sfp(cache)
+            else:
+                out = eng.empty(4)
+
+                def obj_fun(sigma):
+                    t4 = eng.reduce_cvar(dev, sigma, cache.sigma, kind, out=out).cpu().numpy()
+                    return (cvar_from(t4) - self.cvar_tgt) ** 2
+
+                opt_sol = minimize_scalar(
+                    obj_fun, bounds=[cache.sigma, cache.sigma + self.lip_sigma * np.log(1 / cache.t_step)],
+                    method="Bounded")
+                cache.sigma = opt_sol.x
+        except Exception as e:
+            msg = f"Failed to update sigma: {str(e)}"
+            if self.verbose:
+                cache.msg += msg
+            else:
+                _log.info(f"Iteration {cache.iteration}: {msg}")
+
+    def _ess(self, cache: CBREECache, beta, out=None) -> float:
+        t4 = self._eng.reduce_ess(cache._dev, cache.sigma, beta, self._tgt_kind(), out=out).cpu().numpy()
+        if t4[3] <= 0:
+            raise ValueError("attempt to get argmax of an empty sequence")
+        return ess_from(t4)
+
+    def _update_beta(self, cache: CBREECache) -> None:
+        """solver.py:582-612: MINPACK hybr root of ESS(beta) - ess_tgt*N; objective = ``ree_reduce_ess``."""
+        out = self._eng.empty(4)
+        n_tot = cache._n_total
+
+        def obj_fun(temperature):
+            return self._ess(cache, float(np.asarray(temperature).reshape(-1)[0]), out) - self.ess_tgt * n_tot
+
+        try:
+            sol = root(obj_fun, cache.beta)
+            new_beta = cache.beta if sol.x.item() <= 0 else sol.x.item()
+            cache.beta = new_beta
+        except Exception as e:
+            msg = f"Failed to update beta: {str(e)}"
+            if self.verbose:
+                cache.msg += msg
+            else:
+                _log.info(f"Iteration {cache.iteration}: {msg}")
+
+    def _update_beta_and_sigma(self, cache: CBREECache) -> None:
+        """solver.py:505-523."""
+        if self.sigma_adaptivity == "cvar":
+            self._update_sigma_cvar(cache)
+        if self.sigma_adaptivity == "sfp":
+            self._update_sigma_sfp(cache)
+        if self.beta_adaptivity:
+            self._update_beta(cache)
+        cache.ess = self._ess(cache, cache.beta)
+
+    # ------------------------------------------------------------------ #
+    # the step
+    # ------------------------------------------------------------------ #
+    def _perform_step(self, cache: CBREECache) -> CBREECache:
+        """solver.py:642-694 (GM branch).  sweep 1 (``ree_cbree_step``) + post-processing (sweep 2)."""
+        eng, src = self._eng, cache._dev
+        n, d = src.n, src.d
+        t = float(cache.t_step)
+        m_noise = (1 - t) * cache.weighted_mean
+        scale = (1 - t**2) * (1 + cache.beta)
+        dst = eng.alloc_ensemble(n, d, first=src.first)
+        sums = eng.empty(d + d * d + 2)
+        # conditioning shifts of the one-pass Grams: predicted unweighted mean, previous weighted mean
+        shift_u_h = t * cache.ens_mean + m_noise
+        small = eng.to_device(np.concatenate([m_noise, shift_u_h, cache.weighted_mean]))
+        m_noise_d, shift_u, shift_w = small[0:d], small[d:2 * d], small[2 * d:3 * d]
+        desc = self._lsf_descriptor(d)
+        if self.noise == "numpy":
+            # Generator.multivariate_normal(method="svd"): mean + Z @ (U sqrt(S))^T   (solver.py:667)
+            c_noise = scale * cache.weighted_cov
+            Z = self.rng.standard_normal((self._n_total, d))
+            lo, hi = eng.comm.shard(self._n_total)
+            zdev = eng.upload(Z[lo:hi], first=src.first)
+            u, s, _ = np.linalg.svd(c_noise)
+            F = eng.to_device(u * np.sqrt(s))
+            eng.cbree_step(src, dst, t, m_noise_d, F, desc, shift_u, sums, z=zdev)
+        else:
+            F = eng.empty(d * d)
+            fstats = eng.empty(4)
+            eng.chol_scaled(cache._stats["C_w"] if not cache._cw_dirty else eng.to_device(cache.weighted_cov), d,
+                            scale, F, fstats)
+            self._step_draws += 1
+            eng.cbree_step(src, dst, t, m_noise_d, F, desc, shift_u, sums, seed=self._philox_seed,
+                           draw=_STREAM_STEP + self._step_draws)
+        if desc is None or not self._device_energy:
+            self._evaluate_external(dst, desc is None, not self._device_energy)
+            if desc is None:
+                sums[d + d * d: d + d * d + 1].copy_(eng.count_failed(dst))
+        self.lsf.counter += self._n_total
+        new = CBREECache(eng, dst, mixture_model=MixtureModel(1))
+        new.iteration = cache.iteration + 1
+        new.converged = cache.converged
+        new.sigma = cache.sigma
+        new.beta = cache.beta
+        new.t_step = cache.t_step
+        new.num_lsf_evals = self.lsf.counter
+        new._cw_dirty = False
+        self._post_ensemble(new, sums_ready=sums, shift_u=shift_u, shift_w=shift_w)
+        self._finish_is_stats(new)
+        self._compute_weights_check(new)
+        return new
+
+    # ------------------------------------------------------------------ #
+    # stopping
+    # ------------------------------------------------------------------ #
+    def _convergence_check(self, cache_list: list) -> None:
+        """solver.py:696-738 (the window's failure counts come from the device reductions)."""
+        last = cache_list[-1]
+        iteration = last.iteration
+        window = cache_list[-self.observation_window:]
+        last.sfp = last.num_failed / last._n_total
+        last.slope_cvar = get_slope(np.array([c.cvar_is_weights for c in window]))
+        last.sfp_slope = get_slope(np.array([c.num_failed for c in window]))
+        if self.sigma_adaptivity == "cvar":
+            last.converged = bool((last.cvar_is_weights <= self.cvar_tgt) and self.convergence_check)
+            if last.converged:
+                last.msg += "Converged with given `cvar_tgt`."
+            if self.divergence_check and iteration >= self.observation_window:
+                sfp_mean = np.average([c.sfp for c in window])
+                last.converged = bool(last.converged or (last.slope_cvar > 0.0 and sfp_mean >= self.sfp_tgt))
+                if last.converged:
+                    last.msg += "Converged due to `divergence_check`."
+        if self.sigma_adaptivity == "sfp":
+            last.converged = bool((last.sfp >= self.sfp_tgt) and self.convergence_check)
+            if last.converged:
+                last.msg += "Converged with given `sfp_tgt`."
+
+    # ------------------------------------------------------------------ #
+    # step size
+    # ------------------------------------------------------------------ #
+    @staticmethod
+    def _stack(m, c):
+        return np.concatenate((m[None, ...], np.tril(c)))
+
+    def _update_stepsize(self, cache_list: list) -> None:
+        """Embedded two-stage error estimate on (mean, tril cov) of the last two ensembles (solver.py:740-781);
+        the moments were produced by the sweeps, nothing N-sized is touched."""
+        ch1, ch2 = cache_list[-2], cache_list[-1]
+        h = -np.log(ch1.t_step)
+        phi = (np.exp(-2 * h) - 1) / (-2 * h)
+        bm1 = phi - 2 * (phi - 1) / (-2 * h)
+        bm2 = 2 * (phi - 1) / (-2 * h)
+        m1, m2 = ch1.ens_mean, ch2.ens_mean
+        m2_hat = 2 * h * (bm1 * m1 + bm2 * m2)
+        phi = (np.exp(-4 * h) - 1) / (-2 * h)
+        bc1 = phi - 2 * (phi - 1) / (-2 * h)
+        bc2 = 2 * (phi - 1) / (-2 * h)
+        c1, c2 = ch1.ens_cov, ch2.ens_cov
+        c2_hat = 2 * h * (bc1 * c1 + bc2 * c2)
+        x = self._stack(m2, c2)
+        x_hat = self._stack(m2_hat, c2_hat)
+        delta = x - x_hat
+        w = self.stepsize_tolerance + self.stepsize_tolerance * np.maximum(abs(x), abs(x_hat))
+        err = np.sqrt(np.average((delta / w) ** 2))
+        q = 0.9 * np.sqrt(1 / err)
+        ch2.t_step = np.maximum(np.exp(-100), np.minimum(np.exp(-1e-5), np.exp(-q * h)))
+
+    def _compute_initial_stepsize(self, cache: CBREECache) -> None:
+        """solver.py:783-817, including the trial Euler step and the ``(f0 - f2/w)`` parenthesisation."""
+        m0, c0 = cache.ens_mean, cache.ens_cov
+        x0 = self._stack(m0, c0)
+        w = self.stepsize_tolerance + self.stepsize_tolerance * abs(x0)
+        d0 = np.sqrt(np.average((x0 / w) ** 2))
+        f0 = self._stack(-m0 + cache.weighted_mean, -2 * c0 + 2 * cache.weighted_cov)
+        d1 = np.sqrt(np.average((f0 / w) ** 2))
+        h0 = 0.01 * d0 / d1
+        cache.t_step = np.exp(-h0)
+        self._update_beta_and_sigma(cache)
+        cache_new = self._perform_step(cache)
+        m2, c2 = cache_new.ens_mean, cache_new.ens_cov
+        f2 = self._stack(-m2 + cache_new.weighted_mean, -2 * c2 + 2 * cache_new.weighted_cov)
+        d2 = np.sqrt(np.average((f0 - f2 / w) ** 2)) / h0
+        h1 = np.sqrt(0.01 / np.maximum(d1, d2))
+        cache.t_step = np.exp(-np.maximum(100 * h0, h1))
+        cache.num_lsf_evals = cache_new.num_lsf_evals
+
+    # ------------------------------------------------------------------ #
+    # final estimates
+    # ------------------------------------------------------------------ #
+    def _importance_sampling(self, cache: CBREECache) -> None:
+        """solver.py:819-846 (GM branch).  The statistics were accumulated by sweep 2 when the cache was
+        produced; they are recomputed only if a callback replaced N-sized fields."""
+        if cache.sync_to_device():
+            self._refresh(cache)
+        self._check_density(cache)
+        cache.estimate = self._estimate_of(cache)
+
+    def _refresh(self, cache: CBREECache):
+        sig, bet = cache.sigma, cache.beta
+        self._post_ensemble(cache)
+        cache.sigma, cache.beta = sig, bet
+
+    def _compute_weighted_estimates(self, cache_list: list) -> None:
+        """solver.py:848-864."""
+        k = min(len(cache_list), self.observation_window)
+        sqrt_w = np.sqrt(np.arange(k))
+        with np.errstate(all="ignore"):
+            cvar_w = 1 / np.array([c.cvar_is_weights**2 for c in cache_list[-k:]])
+        cvar_w[~np.isfinite(cvar_w)] = 0.0
+        pfs = [c.estimate for c in cache_list[-k:]]
+        last = cache_list[-1]
+        last.estimate_uniform_avg = np.average(pfs)
+        last.estimate_cvar_avg = np.average(pfs, weights=cvar_w) if np.sum(cvar_w) > 0 else 0.0
+        last.estimate_sqrt_avg = np.average(pfs, weights=sqrt_w)
+
+    # ------------------------------------------------------------------ #
+    # main loop
+    # ------------------------------------------------------------------ #
+    def start(self, prob: Problem) -> list:
+        """Everything ``solve`` does before its loop (solver.py:375-409): upload / evaluate the initial ensemble,
+        initial weights, initial step size.  Returns the cache list."""
+        self._setup(prob)
+        dev = self._initial_ensemble(prob)
+        cache = CBREECache(self._eng, dev, sigma=self.sigma, beta=self.beta, num_lsf_evals=self.lsf.counter)
+        self._post_ensemble(cache)
+        self._compute_weights_check(cache)
+        if self.stepsize_adaptivity:
+            self._compute_initial_stepsize(cache)
+        else:
+            cache.t_step = self.t_step
+        self._table = self._make_table() if self.verbose else None
+        self._msg = "Success"
+        return [cache]
+
+    def advance(self, cache_list: list) -> bool:
+        """One pass of the loop body of ``solve`` (solver.py:413-467).  False if the step or the callback failed
+        (the text is kept for ``Solution.msg``)."""
+        if self.stepsize_adaptivity and len(cache_list) > 1 and cache_list[-1].iteration % 2 == 0:
+            self._update_stepsize(cache_list)
+        self._update_beta_and_sigma(cache_list[-1])
+        try:
+            cache_list.append(self._perform_step(cache_list[-1]))
+        except Exception as e:
+            self._msg = str(e)
+            if not self.verbose:
+                warn(str(e))
+            return False
+        if not self.save_history and len(cache_list) > self.observation_window:
+            cache_list.pop(0)
+        self._convergence_check(cache_list)
+        if self.callback is not None:
+            try:
+                cache_list[-1] = self.callback(cache_list[-1], self)
+                if cache_list[-1].sync_to_device():
+                    self._refresh_after_callback(cache_list[-1])
+            except Exception as e:
+                self._msg = str(e)
+                if not self.verbose:
+                    warn(str(e))
+                return False
+        if self.verbose:
+            self._print_row(self._table, cache_list)
+        return True
+
+    def finish(self, cache_list: list) -> Solution:
+        """solver.py:468-503: exit message, importance sampling of the retained caches, Solution."""
+        msg = self._msg
+        if not cache_list[-1].converged and cache_list[-1].iteration > self.num_steps:
+            msg = "Not Converged."
+        return self._build_solution(cache_list, msg, self.lsf.counter)
+
+    def solve(self, prob: Problem) -> Solution:
+        """Estimate the rare event of `prob` (solver.py:365-503)."""
+        cache_list = self.start(prob)
+        while not cache_list[-1].converged and cache_list[-1].iteration <= self.num_steps:
+            if not self.advance(cache_list):
+                break
+        return self.finish(cache_list)
+
+    def _refresh_after_callback(self, cache: CBREECache):
+        """A callback replaced the ensemble / evaluations: redo the moments the next step needs.  The
+        reference keeps the *old* weighted mean/cov in that case (solver.py:441, 693), so do we."""
+        m_w, C_w, cv = cache.weighted_mean, cache.weighted_cov, cache.cvar_is_weights
+        self._post_ensemble(cache)
+        cache.weighted_mean, cache.weighted_cov, cache.cvar_is_weights = m_w, C_w, cv
+        cache._cw_dirty = True
+
+    def _build_solution(self, cache_list, msg, costs) -> Solution:
+        for c in cache_list:
+            self._importance_sampling(c)
+        self._compute_weighted_estimates(cache_list)
+        last = cache_list[-1]
+        other = {
+            "Average Estimate": last.estimate_uniform_avg,
+            "Root Weighted Average Estimate": last.estimate_sqrt_avg,
+            "VAR Weighted Average Estimate": last.estimate_cvar_avg,
+            "CVAR": last.cvar_is_weights,
+            "SFP": last.sfp,
+        }
+        tmp = flatten_cache_list(cache_list)
+        tmp["sigma"] = np.insert(tmp["sigma"], 0, 0)  # thesis notation, solver.py:486-488
+        tmp["beta"] = np.insert(tmp["beta"], 0, np.nan)
+        tmp["t_step"] = np.insert(tmp["t_step"], 0, np.nan)
+        if self.return_other:
+            other = other | tmp
+        if self.return_caches:
+            other["cache_list"] = cache_list
+        ens_hist = tmp["ensemble"]
+        if not isinstance(ens_hist, LazyHistory) and ens_hist.ndim == 2:
+            ens_hist = ens_hist[None, ...]
+        return Solution(ens_hist, tmp["beta"], tmp["lsf_evals"], tmp["estimate"], costs, msg,
+                        num_steps=last.iteration, other=other)
+
+    def solve_from_caches(self, cache_list: list) -> Solution:
+        """Replay the stopping logic over precomputed caches without LSF calls (solver.py:866-971)."""
+        self._eng = cache_list[0]._engine
+        cache_list_new = [cache_list.pop(0)]
+        table = self._make_table() if self.verbose else None
+        msg = "Success"
+        while (not cache_list_new[-1].converged and cache_list_new[-1].iteration <= self.num_steps
+               and len(cache_list) > 0):
+            cache_list_new.append(cache_list.pop(0))
+            if not self.save_history and len(cache_list_new) > self.observation_window:
+                cache_list_new.pop(0)
+            self._convergence_check(cache_list_new)
+            if self.callback is not None:
+                try:
+                    cache_list_new[-1] = self.callback(cache_list_new[-1], self)
+                except Exception as e:
+                    msg = str(e)
+                    if not self.verbose:
+                        warn(str(e))
+                    break
+            if self.verbose:
+                self._print_row(table, cache_list_new)
+        if not cache_list_new[-1].converged and cache_list_new[-1].iteration > self.num_steps:
+            msg = "Not Converged."
+        return self._build_solution(cache_list_new, msg, cache_list_new[-1].num_lsf_evals)
+
+    # -- verbose table (solver.py:401-406, 448-467) ---------------------------- #
+    def _make_table(self):
+        cols = ["Iteration", "Sigma", "Beta", "Stepsize", "CVAR", "SFP", "Comment"]
+        try:
+            from prettytable import PrettyTable
+
+            width = max(len(s) for s in cols)
+            return PrettyTable(cols, float_format=".5", max_width=width, min_width=width)
+        except ImportError:
+            print(" | ".join(f"{c:>10s}" for c in cols))
+            return None
+
+    def _print_row(self, table, cache_list):
+        c = cache_list[-1]
+        row = [c.iteration, c.sigma, c.beta, np.log(1 / c.t_step), c.cvar_is_weights, c.sfp, cache_list[-2].msg]
+        if table is None:
+            print(" | ".join(f"{v:>10.5g}" if isinstance(v, Real) else f"{v!s:>10s}" for v in row))
+        else:
+            table.add_row(row)
+            print(table.get_string(start=len(table.rows) - 1, end=len(table.rows), header=c.iteration == 1,
+                                   border=False))
