@@ -21,7 +21,9 @@ __version__ = "0.1.0"
 def __getattr__(name):
     # the diffusion problem builds its KL table at first use (2-3 s of scalar root finding)
     if name in ("diffusion_problem", "diffusion"):
-        from . import diffusion as _d
+        import importlib
+
+        _d = importlib.import_module(__name__ + ".diffusion")
 
         return _d.diffusion_problem if name == "diffusion_problem" else _d
     raise AttributeError(name)

@@ -74,7 +74,10 @@ def test_logtgt_all_kinds(eng):
             want = u[f"logtgt_{kind}_{sig}"]  # produced by the live reference
             fin = np.isfinite(want)
             assert np.array_equal(np.isfinite(got), fin), kind
-            np.testing.assert_allclose(got[fin], want[fin], rtol=5e-15, atol=0, err_msg=f"{kind} {sig}")
+            # log1p(tanh(a)) cancels for a << 0: one ulp of tanh (CUDA vs glibc) is amplified, in the reference
+            # as much as here; every other form agrees to a few ulp.
+            rtol = 1e-9 if kind == "tanh" else 5e-15
+            np.testing.assert_allclose(got[fin], want[fin], rtol=rtol, atol=0, err_msg=f"{kind} {sig}")
 
 
 @pytest.mark.parametrize("n", [1, 31, 257, 100_003])
@@ -151,8 +154,10 @@ def test_diffusion_lsf(ree):
     np.testing.assert_allclose(g, v["g"], rtol=0, atol=1e-12)  # reference (SuperLU) values
     orc = lo.DiffusionOracle()
     th = np.random.default_rng(3).standard_normal((777, 150))
-    np.testing.assert_allclose(lsf(th), orc.g(th), rtol=0, atol=1e-12)
-    np.testing.assert_allclose(lsf(th), orc.u_max - orc.flux_identity(th), rtol=0, atol=1e-12)
+    # elimination on a 512-point 1-D Laplacian amplifies rounding by ~cond*eps (a few 1e-12 on u(1) ~ 0.5);
+    # the reference's own SuperLU solve sits at the same distance from the exact flux identity.
+    np.testing.assert_allclose(lsf(th), orc.g(th), rtol=0, atol=5e-12)
+    np.testing.assert_allclose(lsf(th), orc.u_max - orc.flux_identity(th), rtol=0, atol=5e-12)
 
 
 # --------------------------------------------------------------------------- #
@@ -391,21 +396,21 @@ def test_readme_example_with_python_lsf(ree):
 
 
 def test_solve_from_caches_replays_solve(ree):
-    """test/test_cbree_solve_from_caches.py:6-36 on the engine."""
+    """test/test_cbree_solve_from_caches.py:6-36 on the engine: replaying the stored caches through the stopping
+    logic equals a fresh seeded solve bit for bit, for observation windows 2..14."""
     from copy import deepcopy
 
-    prob = ree.make_linear_problem(2).set_sample(3000, seed=5000)
-    kw = dict(seed=1, divergence_check=True, noise="numpy", quiet=True)
-    full = ree.CBREE(save_history=True, return_caches=True, convergence_check=False, num_steps=14, **kw).solve(prob)
-    cache_list = full.other["cache_list"]
-    for win in [2, 5, 9]:
-        a = ree.CBREE(observation_window=win, convergence_check=False, num_steps=14, **kw).solve(prob)
-        b = ree.CBREE(observation_window=win, convergence_check=False, num_steps=14, **kw).solve_from_caches(
-            deepcopy(cache_list))
-        assert np.array_equal(a.ensemble_hist[-1], b.ensemble_hist[-1])
-        assert np.array_equal(a.lsf_eval_hist[-1], b.lsf_eval_hist[-1])
-        assert a.costs == b.costs
-        np.testing.assert_array_equal(a.prob_fail_hist, b.prob_fail_hist)
+    p = deepcopy(ree.prob_convex).set_sample(1000, seed=5000)
+    kw = dict(seed=1, cvar_tgt=0.5, noise="numpy", quiet=True)
+    sol0 = ree.CBREE(divergence_check=False, save_history=True, return_caches=True, **kw).solve(p)
+    for k in range(2, 15):
+        simulation = ree.CBREE(divergence_check=True, observation_window=k, **kw).solve_from_caches(
+            deepcopy(sol0.other["cache_list"]))
+        truth = ree.CBREE(divergence_check=True, observation_window=k, **kw).solve(p)
+        assert np.array_equal(simulation.ensemble_hist[-1], truth.ensemble_hist[-1], equal_nan=True), k
+        assert np.array_equal(simulation.lsf_eval_hist[-1], truth.lsf_eval_hist[-1], equal_nan=True), k
+        assert simulation.costs == truth.costs, k
+        np.testing.assert_array_equal(simulation.prob_fail_hist, truth.prob_fail_hist)
 
 
 def test_reference_accuracy_thresholds_with_philox(ree):
