@@ -81,6 +81,9 @@ int ree_abi_version(void);
 const char* ree_last_error(void);
 /* kernels launched by this library in this process so far (bench.py reports the delta as gpu_launches) */
 int64_t ree_launch_count(void);
+/* 1 if dimension d is served by the fused DMMA sweep kernels (d <= 103), 0 if by the modular kernels
+ * (which need the optional `w` scratch vector of ree_cbree_maha) */
+int ree_fused_path(int d);
 /* number of CTAs every reduction kernel uses on the current device (partials per launch) */
 int ree_num_ctas(void);
 /* bytes of scratch a call with dimension d may need (partials of the d x d sums).  The workspace
@@ -164,13 +167,13 @@ int ree_chol_scaled(const double* C, int d, double scale, double* L, double* sta
  *     is4[0] = R = max r, is4[1] = sum exp(r-R) 1[g<=0], is4[2] = sum (exp(r-R) 1[g<=0])^2, is4[3] = #finite r
  *   (cvar_is_weights, solver.py:683-686; importance_sampling, utilities.py:43-45)
  * and, with w_i = exp(beta*logtgt(g_i,e_i;sigma) - wmax[0]) (0 where non-finite):
- *     sums as in ree_cbree_step but weighted; sums[d+d*d] = sum w, sums[d+d*d+1] = sum w^2
+ *     sums as in ree_cbree_step but weighted and shifted by `mean`; sums[d+d*d] = sum w
  *   (weighted mean/cov, solver.py:629-636).  wmax is a DEVICE scalar (out[0] of ree_reduce_ess).
- * logq may be NULL (not stored).  w (n doubles) receives the unnormalised weights w_i.          */
+ * logq and w (n doubles each, optional) receive log q_i and the unnormalised weights w_i.       */
 int ree_cbree_maha(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* e,
                    const double* mean, const double* Linv, const double* logdet, double sigma, double beta,
-                   int tgt_kind, const double* wmax, const double* shift, double* logq, double* w,
-                   double* workspace, double* sums, double* is4, void* stream);
+                   int tgt_kind, const double* wmax, double* logq, double* w, double* workspace, double* sums,
+                   double* is4, void* stream);
 
 #ifdef __cplusplus
 }

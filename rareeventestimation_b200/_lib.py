@@ -49,6 +49,7 @@ PROTOTYPES = {
     "ree_last_error": (C.c_char_p, []),
     "ree_num_ctas": (_INT, []),
     "ree_launch_count": (_I64, []),
+    "ree_fused_path": (_INT, [_INT]),
     "ree_workspace_bytes": (_I64, [_INT]),
     "ree_aos_to_soa": (_INT, [_P, _P, _I64, _INT, _I64, _P]),
     "ree_soa_to_aos": (_INT, [_P, _P, _I64, _INT, _I64, _P]),
@@ -67,7 +68,7 @@ PROTOTYPES = {
     "ree_ensemble_sums": (_INT, [_P, _I64, _INT, _I64, _P, _P, _P, _P, _P]),
     "ree_moments_chol": (_INT, [_P, _P, _INT, _INT, _INT, _P, _P, _P, _P, _P, _P]),
     "ree_chol_scaled": (_INT, [_P, _INT, _DBL, _P, _P, _P]),
-    "ree_cbree_maha": (_INT, [_P, _I64, _INT, _I64, _P, _P, _P, _P, _P, _DBL, _DBL, _INT, _P, _P, _P, _P, _P, _P, _P,
+    "ree_cbree_maha": (_INT, [_P, _I64, _INT, _I64, _P, _P, _P, _P, _P, _DBL, _DBL, _INT, _P, _P, _P, _P, _P, _P,
                               _P]),
 }
 

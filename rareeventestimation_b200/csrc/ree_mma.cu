@@ -1,0 +1,669 @@
+// Fused DMMA kernels for the two ensemble sweeps of a CBREE iteration (d <= 103).
+//
+//   sweep 1  k_step_mma : X'^T = t X^T + m 1^T + F Z^T   (F Z^T on the fp64 tensor pipe, Z from Philox in
+//                         registers or injected), g'/e' from the accumulator fragments, X' written once,
+//                         shifted Gram  sum_i y_i y_i^T  (y = x' - shift, augmented with a row of ones so that
+//                         sum y and n fall out of the same contraction) accumulated in registers per CTA.
+//   sweep 2  k_maha_mma : y = x' - mean staged in shared memory, u = Linv y (DMMA), q = |u|^2 -> log q,
+//                         IS statistics, weights w; tile rescaled by sqrt(w) in place, weighted Gram.
+//
+// Fragment conventions of mma.sync.aligned.m8n8k4.row.col.f64 (lane = 4*lr + lc):
+//   A (8x4): a = A[lr][lc]      B (4x8): b = B[lc][lr]      C (8x8): c0,c1 = C[lr][2*lc], C[lr][2*lc+1]
+// Orientation: M = dimension, N = particle for the transforms; for the Grams M = N = dimension and K = particle.
+// Because a Gram sums over all particles, the order of particles inside a k-step is free: the pair of k-steps u
+// uses particles {8u+2*lc} and {8u+2*lc+1}, i.e. exactly the double2 a C-fragment holds -> the shared-memory tile
+// is written (st.shared.v2) and read (ld.shared.v2) with the same conflict-free pattern (row stride = 8 mod 16).
+#include <stdlib.h>
+
+#include "common.cuh"
+
+#define MT 256          // threads per CTA (8 warps), one CTA per SM
+#define MAXM_MAX 8      // macro tiles (2x2 tiles of 8x8) per warp, upper bound of the plan table
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// which macro tiles (mr >= mc) of the lower triangle each warp of a k-split group accumulates
+struct GramPlan {
+    int nmac[8];
+    unsigned short mac[8][MAXM_MAX];  // mr | mc << 8
+};
+
+struct MmaArgs {
+    // common
+    const double* x;     // sweep 1: X (input) ; sweep 2: X'
+    int64_t n, ld;
+    int d;
+    const double* A;     // F (sweep 1) or Linv (sweep 2), row-major d x d
+    int tri;             // A is lower triangular (skip zero tiles)
+    const double* shift; // sweep 1: Gram shift ; sweep 2: unused (the mean is the shift)
+    double* partials;    // [(cta*KS + grp)][T][64] packed Gram tiles
+    double* small;       // per-CTA scalars: sweep 1 count of g<=0 ; sweep 2 ExpSums (4 doubles)
+    GramPlan plan;
+    // sweep 1
+    double* x_new;
+    double t;
+    const double* m_noise;
+    const double* z;
+    uint64_t seed, draw;
+    int64_t first;
+    int lsf_mode;        // 0: not fused, 1: affine coef, 2: -sum(x)/sqrt(d) + offset
+    const double* coef;
+    double offset;
+    double* g_new;
+    double* e_new;
+    // sweep 2
+    const double* g;
+    const double* e;
+    const double* mean;
+    const double* logdet;
+    const double* wmax;
+    double sigma, beta;
+    int tgt_kind;
+    double* logq;
+    double* w_out;
+};
+
+// ---------------------------------------------------------------------------------------
+// shared helpers
+// ---------------------------------------------------------------------------------------
+template <int S>
+__device__ __forceinline__ void pack_matrix(double* Lf, const double* __restrict__ A, int d, int ntd, int KT2) {
+    // fragment order: tile (mt, kk) -> 32 consecutive doubles, lane l holds A[8mt + l/4][4kk + l%4]
+    for (int idx = threadIdx.x; idx < ntd * KT2 * 32; idx += MT) {
+        int l = idx & 31, tile = idx >> 5;
+        int mt = tile / KT2, kk = tile - mt * KT2;
+        int r = 8 * mt + (l >> 2), c = 4 * kk + (l & 3);
+        Lf[idx] = (r < d && c < d) ? A[(size_t)r * d + c] : 0.0;
+    }
+}
+
+struct GramRegs {
+    int offR, offC;    // shared-memory offsets (doubles) of the first row / column tile of a macro tile
+    int flags;         // bit0: second row tile exists, bit1: second col tile exists, bit2: diagonal macro tile
+};
+
+template <int MAXM, int S>
+__device__ __forceinline__ void gram_setup(const GramPlan& plan, int wi, int nta, int lr, int lc, GramRegs (&gr)[MAXM],
+                                           int& nmac) {
+    nmac = plan.nmac[wi];
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+        int code = (m < nmac) ? plan.mac[wi][m] : 0;
+        int mr = code & 0xff, mc = code >> 8;
+        gr[m].offR = (16 * mr + lr) * S + 2 * lc;
+        gr[m].offC = (16 * mc + lr) * S + 2 * lc;
+        gr[m].flags = ((2 * mr + 1 < nta) ? 1 : 0) | ((2 * mc + 1 < nta) ? 2 : 0) | ((mr == mc) ? 4 : 0);
+    }
+}
+
+// accumulate the Gram of the k-pairs [u_lo, u_hi) of the shared tile into the warp's macro tiles
+template <int MAXM, int S>
+__device__ __forceinline__ void gram_accumulate(const double* __restrict__ Ys, const GramRegs (&gr)[MAXM], int nmac,
+                                                int u_lo, int u_hi, double (&acc)[MAXM][4][2]) {
+    for (int u = u_lo; u < u_hi; ++u) {
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) {
+            if (m < nmac) {
+                const int f = gr[m].flags;
+                const double2 a0 = *reinterpret_cast<const double2*>(Ys + gr[m].offR + 8 * u);
+                double2 a1 = make_double2(0.0, 0.0), b0 = a0, b1 = make_double2(0.0, 0.0);
+                if (f & 1) a1 = *reinterpret_cast<const double2*>(Ys + gr[m].offR + 8 * S + 8 * u);
+                if (f & 4) {
+                    b1 = a1;
+                } else {
+                    b0 = *reinterpret_cast<const double2*>(Ys + gr[m].offC + 8 * u);
+                    if (f & 2) b1 = *reinterpret_cast<const double2*>(Ys + gr[m].offC + 8 * S + 8 * u);
+                }
+                dmma(acc[m][0][0], acc[m][0][1], a0.x, b0.x);
+                dmma(acc[m][0][0], acc[m][0][1], a0.y, b0.y);
+                if ((f & 2) && !(f & 4)) {  // (2mr, 2mc+1): upper triangle for a diagonal macro tile
+                    dmma(acc[m][1][0], acc[m][1][1], a0.x, b1.x);
+                    dmma(acc[m][1][0], acc[m][1][1], a0.y, b1.y);
+                }
+                if (f & 1) {
+                    dmma(acc[m][2][0], acc[m][2][1], a1.x, b0.x);
+                    dmma(acc[m][2][0], acc[m][2][1], a1.y, b0.y);
+                    if (f & 2) {
+                        dmma(acc[m][3][0], acc[m][3][1], a1.x, b1.x);
+                        dmma(acc[m][3][0], acc[m][3][1], a1.y, b1.y);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// packed tile index of (mt, nt), mt >= nt
+__host__ __device__ __forceinline__ int tri_index(int mt, int nt) { return mt * (mt + 1) / 2 + nt; }
+
+template <int MAXM>
+__device__ __forceinline__ void gram_store(double* __restrict__ part /* [T][64] of this (cta, group) */,
+                                           const GramPlan& plan, int wi, int nmac, int nta, int lr, int lc,
+                                           const double (&acc)[MAXM][4][2]) {
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+        if (m < nmac) {
+            int code = plan.mac[wi][m];
+            int mr = code & 0xff, mc = code >> 8;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int mt = 2 * mr + (q >> 1), nt = 2 * mc + (q & 1);
+                if (mt < nta && nt <= mt) {
+                    double2 v = make_double2(acc[m][q][0], acc[m][q][1]);
+                    *reinterpret_cast<double2*>(part + (size_t)tri_index(mt, nt) * 64 + lr * 8 + 2 * lc) = v;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// sweep 1
+// ---------------------------------------------------------------------------------------
+template <int NTB, int NPT, int MAXM, int KS>
+__global__ void __launch_bounds__(MT, 1) k_step_mma(const MmaArgs a) {
+    constexpr int P = 8 * NPT * 8;  // particles per CTA tile
+    constexpr int S = P + 8;        // row stride of the shared tile (8 mod 16 doubles)
+    extern __shared__ double sm[];
+    const int d = a.d, ntd = (d + 7) >> 3, nta = (d + 8) >> 3, KT2 = 2 * ntd;
+    const int rows = 16 * ((nta + 1) >> 1);  // tile rows padded to full macro tiles
+    double* Lf = sm;
+    double* Ys = Lf + ntd * KT2 * 32;
+    double* vm = Ys + rows * S;
+    double* vs = vm + 8 * NTB;
+    double* vc = vs + 8 * NTB;
+    __shared__ double red[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lc = lane & 3;
+
+    pack_matrix<S>(Lf, a.A, d, ntd, KT2);
+    for (int j = tid; j < 8 * NTB; j += MT) {
+        vm[j] = (j < d) ? a.m_noise[j] : 0.0;
+        vs[j] = (j < d && a.shift) ? a.shift[j] : 0.0;
+        vc[j] = (j < d) ? (a.lsf_mode == 1 ? a.coef[j] : 1.0) : 0.0;
+    }
+    for (int idx = tid; idx < rows * S; idx += MT) Ys[idx] = 0.0;
+
+    constexpr int WG = 8 / KS;
+    const int grp = warp / WG, wi = warp % WG;
+    GramRegs gr[MAXM];
+    int nmac;
+    gram_setup<MAXM, S>(a.plan, wi, nta, lr, lc, gr, nmac);
+    double acc[MAXM][4][2];
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[m][q][0] = acc[m][q][1] = 0.0;
+    __syncthreads();
+
+    double n_fail = 0.0;
+    const int pw = warp * 8 * NPT;  // first tile column of this warp
+    const double e_const = (double)d * REE_LOG_2PI;
+    const int64_t ntiles = (a.n + P - 1) / P;
+    for (int64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
+        const int64_t i0 = tix * P;
+        // ---- F z on the tensor pipe: c[mt][pt] = rows 8mt.., particles pw+8pt.. ------------------
+        double c[NTB][NPT][2];
+#pragma unroll
+        for (int mt = 0; mt < NTB; ++mt)
+#pragma unroll
+            for (int pt = 0; pt < NPT; ++pt) c[mt][pt][0] = c[mt][pt][1] = 0.0;
+        for (int q = 0; q < ntd; ++q) {
+            double b0[NPT], b1[NPT];
+#pragma unroll
+            for (int pt = 0; pt < NPT; ++pt) {
+                const int64_t ip = i0 + pw + 8 * pt + lr;
+                if (a.z) {
+                    const int j0 = 8 * q + lc, j1 = j0 + 4;
+                    b0[pt] = (j0 < d && ip < a.n) ? a.z[(int64_t)j0 * a.ld + ip] : 0.0;
+                    b1[pt] = (j1 < d && ip < a.n) ? a.z[(int64_t)j1 * a.ld + ip] : 0.0;
+                } else {
+                    philox_normal_pair(a.seed, (uint64_t)(a.first + ip), (uint32_t)(4 * q + lc), a.draw, b0[pt],
+                                       b1[pt]);
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < NTB; ++mt) {
+                if (mt < ntd && (!a.tri || mt >= q)) {
+                    const double a0 = Lf[((mt * KT2 + 2 * q) << 5) + lane];
+                    const double a1 = Lf[((mt * KT2 + 2 * q + 1) << 5) + lane];
+#pragma unroll
+                    for (int pt = 0; pt < NPT; ++pt) {
+                        dmma(c[mt][pt][0], c[mt][pt][1], a0, b0[pt]);
+                        dmma(c[mt][pt][0], c[mt][pt][1], a1, b1[pt]);
+                    }
+                }
+            }
+        }
+        // ---- epilogue: x' = t x + (m + F z), store, energy / affine LSF partials, y -> shared tile ----
+        double se[NPT][2], sg[NPT][2];
+#pragma unroll
+        for (int pt = 0; pt < NPT; ++pt) se[pt][0] = se[pt][1] = sg[pt][0] = sg[pt][1] = 0.0;
+#pragma unroll
+        for (int mt = 0; mt < NTB; ++mt) {
+            if (mt < ntd) {
+                const int row = 8 * mt + lr;
+                const bool rv = row < d;
+                const double mrow = vm[row], srow = vs[row], crow = vc[row];
+#pragma unroll
+                for (int pt = 0; pt < NPT; ++pt) {
+                    const int pc = pw + 8 * pt + 2 * lc;
+                    const int64_t ip = i0 + pc;
+                    const bool in_buf = rv && ip < a.ld;
+                    double2 xv = make_double2(0.0, 0.0);
+                    if (in_buf) xv = *reinterpret_cast<const double2*>(a.x + (int64_t)row * a.ld + ip);
+                    // t*X + (m_noise + Z F^T): grouping of solver.py:667
+                    double2 xn;
+                    xn.x = __dadd_rn(__dmul_rn(a.t, xv.x), __dadd_rn(mrow, c[mt][pt][0]));
+                    xn.y = __dadd_rn(__dmul_rn(a.t, xv.y), __dadd_rn(mrow, c[mt][pt][1]));
+                    if (in_buf) *reinterpret_cast<double2*>(a.x_new + (int64_t)row * a.ld + ip) = xn;
+                    const bool v0 = ip < a.n, v1 = ip + 1 < a.n;
+                    double2 y;
+                    y.x = (rv && v0) ? xn.x - srow : 0.0;
+                    y.y = (rv && v1) ? xn.y - srow : 0.0;
+                    if (row == d) {  // augmented row of ones: sum y and n come out of the Gram
+                        y.x = v0 ? 1.0 : 0.0;
+                        y.y = v1 ? 1.0 : 0.0;
+                    }
+                    *reinterpret_cast<double2*>(Ys + row * S + pc) = y;
+                    if (rv) {
+                        se[pt][0] = fma(xn.x, xn.x, se[pt][0]);
+                        se[pt][1] = fma(xn.y, xn.y, se[pt][1]);
+                        sg[pt][0] = fma(crow, xn.x, sg[pt][0]);
+                        sg[pt][1] = fma(crow, xn.y, sg[pt][1]);
+                    }
+                }
+            }
+        }
+        if (nta > ntd && lr == 0) {  // d % 8 == 0: the augmented row lives in a tile of its own
+#pragma unroll
+            for (int pt = 0; pt < NPT; ++pt) {
+                const int pc = pw + 8 * pt + 2 * lc;
+                const int64_t ip = i0 + pc;
+                *reinterpret_cast<double2*>(Ys + d * S + pc) = make_double2(ip < a.n ? 1.0 : 0.0, ip + 1 < a.n ? 1.0 : 0.0);
+            }
+        }
+#pragma unroll
+        for (int pt = 0; pt < NPT; ++pt) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double s = se[pt][h], gsum = sg[pt][h];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    s += __shfl_xor_sync(0xffffffffu, s, o);
+                    gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+                }
+                const int64_t ip = i0 + pw + 8 * pt + 2 * lc + h;
+                if (lr == 0 && ip < a.n) {
+                    if (a.e_new) a.e_new[ip] = 0.5 * (e_const + s);
+                    if (a.lsf_mode) {
+                        double gv = (a.lsf_mode == 1) ? __dadd_rn(gsum, a.offset)
+                                                      : __dadd_rn(__ddiv_rn(-gsum, __dsqrt_rn((double)d)), a.offset);
+                        a.g_new[ip] = gv;
+                        n_fail += (gv <= 0.0) ? 1.0 : 0.0;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- Gram of the tile (k-split across warp groups) ------------------------------------
+        gram_accumulate<MAXM, S>(Ys, gr, nmac, grp * (P / 8 / KS), (grp + 1) * (P / 8 / KS), acc);
+        __syncthreads();
+    }
+    const int T = nta * (nta + 1) / 2;
+    gram_store<MAXM>(a.partials + ((size_t)blockIdx.x * KS + grp) * T * 64, a.plan, wi, nmac, nta, lr, lc, acc);
+    n_fail = block_sum(n_fail, red);
+    if (tid == 0) a.small[blockIdx.x] = n_fail;
+}
+
+// ---------------------------------------------------------------------------------------
+// sweep 2
+// ---------------------------------------------------------------------------------------
+template <int NTB, int NPT, int MAXM, int KS>
+__global__ void __launch_bounds__(MT, 1) k_maha_mma(const MmaArgs a) {
+    constexpr int P = 8 * NPT * 8;
+    constexpr int S = P + 8;
+    extern __shared__ double sm[];
+    const int d = a.d, ntd = (d + 7) >> 3, nta = (d + 8) >> 3, KT2 = 2 * ntd;
+    const int rows = 16 * ((nta + 1) >> 1);
+    double* Lf = sm;
+    double* Ys = Lf + ntd * KT2 * 32;
+    double* vm = Ys + rows * S;  // mean
+    double* sw = vm + 8 * NTB;   // sqrt(w) of the tile's particles [P]
+    __shared__ ExpSums sh[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lc = lane & 3;
+    const bool weighted = a.wmax != nullptr;  // false: plain moments of an existing ensemble (no Linv, no IS)
+
+    if (weighted) pack_matrix<S>(Lf, a.A, d, ntd, KT2);
+    for (int j = tid; j < 8 * NTB; j += MT) vm[j] = (j < d && a.mean) ? a.mean[j] : 0.0;
+    for (int idx = tid; idx < rows * S; idx += MT) Ys[idx] = 0.0;
+
+    constexpr int WG = 8 / KS;
+    const int grp = warp / WG, wi = warp % WG;
+    GramRegs gr[MAXM];
+    int nmac;
+    gram_setup<MAXM, S>(a.plan, wi, nta, lr, lc, gr, nmac);
+    double acc[MAXM][4][2];
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[m][q][0] = acc[m][q][1] = 0.0;
+    __syncthreads();
+
+    ExpSums is_acc = expsums_empty();
+    double n_fail = 0.0;
+    const int pw = warp * 8 * NPT;
+    const double logdet = weighted ? a.logdet[0] : 0.0;
+    const double wmax = weighted ? a.wmax[0] : 0.0;
+    const int64_t ntiles = (a.n + P - 1) / P;
+    for (int64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
+        const int64_t i0 = tix * P;
+        // ---- stage y = x - mean (coalesced 16-byte loads along the particle axis) -----------------
+        for (int idx = tid; idx < d * (P / 2); idx += MT) {
+            const int j = idx / (P / 2), p2 = (idx - j * (P / 2)) * 2;
+            const int64_t ip = i0 + p2;
+            double2 v = make_double2(0.0, 0.0);
+            if (ip < a.ld) v = *reinterpret_cast<const double2*>(a.x + (int64_t)j * a.ld + ip);
+            const double mj = vm[j];
+            v.x = (ip < a.n) ? v.x - mj : 0.0;
+            v.y = (ip + 1 < a.n) ? v.y - mj : 0.0;
+            *reinterpret_cast<double2*>(Ys + j * S + p2) = v;
+        }
+        if (!weighted) {
+            for (int p = tid; p < P; p += MT) {
+                const int64_t ip = i0 + p;
+                Ys[d * S + p] = (ip < a.n) ? 1.0 : 0.0;
+                if (a.g && ip < a.n) n_fail += (a.g[ip] <= 0.0) ? 1.0 : 0.0;
+            }
+        }
+        __syncthreads();
+        if (weighted) {
+            // ---- u = Linv y on the tensor pipe; B fragments come from the shared tile ----------
+            double c[NTB][NPT][2];
+#pragma unroll
+            for (int mt = 0; mt < NTB; ++mt)
+#pragma unroll
+                for (int pt = 0; pt < NPT; ++pt) c[mt][pt][0] = c[mt][pt][1] = 0.0;
+            for (int q = 0; q < ntd; ++q) {
+                double b0[NPT], b1[NPT];
+#pragma unroll
+                for (int pt = 0; pt < NPT; ++pt) {
+                    const int col = pw + 8 * pt + lr;
+                    b0[pt] = Ys[(8 * q + lc) * S + col];
+                    b1[pt] = Ys[(8 * q + 4 + lc) * S + col];
+                }
+#pragma unroll
+                for (int mt = 0; mt < NTB; ++mt) {
+                    if (mt < ntd && (!a.tri || mt >= q)) {
+                        const double a0 = Lf[((mt * KT2 + 2 * q) << 5) + lane];
+                        const double a1 = Lf[((mt * KT2 + 2 * q + 1) << 5) + lane];
+#pragma unroll
+                        for (int pt = 0; pt < NPT; ++pt) {
+                            dmma(c[mt][pt][0], c[mt][pt][1], a0, b0[pt]);
+                            dmma(c[mt][pt][0], c[mt][pt][1], a1, b1[pt]);
+                        }
+                    }
+                }
+            }
+            // ---- q = |u|^2 per particle, log q, IS statistics, weights ---------------------------
+#pragma unroll
+            for (int pt = 0; pt < NPT; ++pt) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    double qq = 0.0;
+#pragma unroll
+                    for (int mt = 0; mt < NTB; ++mt)
+                        if (mt < ntd) qq = fma(c[mt][pt][h], c[mt][pt][h], qq);
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+                    const int p = pw + 8 * pt + 2 * lc + h;
+                    const int64_t ip = i0 + p;
+                    if (lr == 0) {
+                        double swv = 0.0;
+                        if (ip < a.n) {
+                            const double lq = -0.5 * ((double)d * REE_LOG_2PI + logdet + qq);
+                            if (a.logq) a.logq[ip] = lq;
+                            const double gi = a.g[ip], ei = a.e[ip];
+                            const double r = __dsub_rn(-ei, lq);  // -e_fun - log_pdf  (solver.py:684)
+                            if (isfinite(r)) expsums_add(is_acc, r, gi <= 0.0 ? 1.0 : 0.0);
+                            const double al = __dmul_rn(ree_logtgt(gi, ei, a.sigma, a.tgt_kind), a.beta);
+                            const double wv = isfinite(al) ? exp(al - wmax) : 0.0;
+                            if (a.w_out) a.w_out[ip] = wv;
+                            swv = sqrt(wv);
+                        }
+                        sw[p] = swv;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- rescale the tile by sqrt(w); augmented row = sqrt(w) => sum w y and sum w -------
+            for (int idx = tid; idx < (d + 1) * (P / 2); idx += MT) {
+                const int j = idx / (P / 2), p2 = (idx - j * (P / 2)) * 2;
+                const double2 s2 = *reinterpret_cast<const double2*>(sw + p2);
+                double2 v = s2;
+                if (j < d) {
+                    v = *reinterpret_cast<const double2*>(Ys + j * S + p2);
+                    v.x *= s2.x;
+                    v.y *= s2.y;
+                }
+                *reinterpret_cast<double2*>(Ys + j * S + p2) = v;
+            }
+            __syncthreads();
+        }
+        gram_accumulate<MAXM, S>(Ys, gr, nmac, grp * (P / 8 / KS), (grp + 1) * (P / 8 / KS), acc);
+        __syncthreads();
+    }
+    const int T = nta * (nta + 1) / 2;
+    gram_store<MAXM>(a.partials + ((size_t)blockIdx.x * KS + grp) * T * 64, a.plan, wi, nmac, nta, lr, lc, acc);
+    if (weighted) {
+        ExpSums blk = expsums_block_reduce(is_acc, sh);
+        if (tid == 0) {
+            double* p = a.small + 4 * (size_t)blockIdx.x;
+            p[0] = blk.m; p[1] = blk.s1; p[2] = blk.s2; p[3] = blk.cnt;
+        }
+    } else {
+        n_fail = block_sum(n_fail, reinterpret_cast<double*>(sh));
+        if (tid == 0) a.small[blockIdx.x] = n_fail;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// second stage: fixed-order sum over (cta, group) partials, unpack tiles into sums = [S1 | S2 | a | b]
+//   S2[j][k] = G[j][k], S1[j] = G[d][j], b = G[d][d] (n or sum w); a = tail scalar (count / unused)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_unpack_gram(const double* __restrict__ partials, int nparts, int d, int nta,
+                                                     int weighted, double* __restrict__ sums) {
+    const int T = nta * (nta + 1) / 2;
+    const int D1 = d + 1;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= D1 * D1) return;
+    int j = idx / D1, k = idx - j * D1;
+    if (k > j) return;  // lower triangle (incl. augmented row j = d)
+    const size_t off = (size_t)tri_index(j >> 3, k >> 3) * 64 + (j & 7) * 8 + (k & 7);
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * T * 64 + off];
+    if (j < d) {
+        sums[d + j * d + k] = s;
+        sums[d + k * d + j] = s;
+    } else if (k < d) {
+        sums[k] = s;
+    } else if (weighted) {  // sum of weights (moments_chol reads it from the first tail slot)
+        sums[d + d * d] = s;
+        sums[d + d * d + 1] = 0.0;
+    } else {
+        sums[d + d * d + 1] = s;
+    }
+}
+
+// tail scalar of sweep 1 / plain moments: sum of per-CTA failure counts (integers: exact in any order)
+__global__ void __launch_bounds__(256) k_sum_small(const double* __restrict__ small, int n, double* __restrict__ out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += small[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) k_merge_expsums(const double* __restrict__ small, int n, double* __restrict__ out4) {
+    __shared__ ExpSums sh[32];
+    ExpSums v = expsums_empty();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        ExpSums o{small[4 * i], small[4 * i + 1], small[4 * i + 2], small[4 * i + 3]};
+        v = expsums_merge(v, o);
+    }
+    v = expsums_block_reduce(v, sh);
+    if (threadIdx.x == 0) {
+        out4[0] = v.m; out4[1] = v.s1; out4[2] = v.s2; out4[3] = v.cnt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static void make_plan(GramPlan& plan, int nta, int warps_per_group, int maxm) {
+    // longest-processing-time assignment of the lower-triangle macro tiles to the warps of a group
+    int MG = (nta + 1) / 2;
+    struct Item { int mr, mc, w; };
+    Item items[128];
+    int n = 0;
+    for (int mr = 0; mr < MG; ++mr)
+        for (int mc = 0; mc <= mr; ++mc) {
+            int w = 0;
+            for (int q = 0; q < 4; ++q) {
+                int mt = 2 * mr + (q >> 1), nt = 2 * mc + (q & 1);
+                if (mt < nta && nt <= mt) ++w;
+            }
+            items[n++] = {mr, mc, w};
+        }
+    for (int i = 0; i < n; ++i)  // sort by weight, descending (stable insertion sort; n <= 55)
+        for (int j = i; j > 0 && items[j].w > items[j - 1].w; --j) {
+            Item t = items[j]; items[j] = items[j - 1]; items[j - 1] = t;
+        }
+    int load[8] = {0};
+    for (int w = 0; w < 8; ++w) plan.nmac[w] = 0;
+    for (int i = 0; i < n; ++i) {
+        int best = -1;
+        for (int w = 0; w < warps_per_group; ++w)
+            if (plan.nmac[w] < maxm && (best < 0 || load[w] < load[best])) best = w;
+        plan.mac[best][plan.nmac[best]++] = (unsigned short)(items[i].mr | (items[i].mc << 8));
+        load[best] += items[i].w;
+    }
+}
+
+struct MmaCfg {
+    int ntb, npt, maxm, ks;
+};
+
+static bool pick_cfg(int d, MmaCfg& c) {
+    if (d <= 15) c = {2, 2, 1, 8};
+    else if (d <= 31) c = {4, 2, 2, 4};
+    else if (d <= 55) c = {7, 2, 3, 2};
+    else if (d <= 103) c = {13, 2, 4, 1};
+    else return false;
+    return true;
+}
+
+bool ree_mma_supported(int d) {
+    // REE_FORCE_MODULAR=1 routes every dimension through the modular (non-fused) kernels: a test hook that lets
+    // the GPU suite check both CUDA paths against the oracle.  Both are CUDA; neither is a CPU path.
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("REE_FORCE_MODULAR");
+        forced = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (forced) return false;
+    MmaCfg c;
+    return pick_cfg(d, c);
+}
+
+extern "C" int ree_fused_path(int d) { return ree_mma_supported(d) ? 1 : 0; }
+
+static size_t mma_smem_bytes(int d, const MmaCfg& c, bool sweep2) {
+    int ntd = (d + 7) / 8, nta = (d + 8) / 8, KT2 = 2 * ntd, P = 8 * c.npt * 8, S = P + 8;
+    int rows = 16 * ((nta + 1) / 2);
+    size_t n = (size_t)ntd * KT2 * 32 + (size_t)rows * S + (sweep2 ? (8 * c.ntb + P) : 3 * 8 * c.ntb);
+    return n * sizeof(double);
+}
+
+size_t ree_mma_partial_doubles(int d) {
+    MmaCfg c;
+    if (!pick_cfg(d, c)) return 0;
+    int nta = (d + 8) / 8, T = nta * (nta + 1) / 2;
+    return (size_t)ree_grid_ctas() * c.ks * T * 64;
+}
+
+template <int NTB, int NPT, int MAXM, int KS>
+static int launch_cfg(bool sweep2, const MmaArgs& a, int grid, size_t smem, cudaStream_t st) {
+    if (sweep2) {
+        cudaFuncSetAttribute(k_maha_mma<NTB, NPT, MAXM, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_maha_mma<NTB, NPT, MAXM, KS><<<grid, MT, smem, st>>>(a);
+    } else {
+        cudaFuncSetAttribute(k_step_mma<NTB, NPT, MAXM, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_step_mma<NTB, NPT, MAXM, KS><<<grid, MT, smem, st>>>(a);
+    }
+    return ree_check_launch(sweep2 ? "k_maha_mma" : "k_step_mma");
+}
+
+// Runs one sweep and the second-stage reductions.  small_out: sweep 1 -> sums tail [count], sweep 2 -> is4.
+int ree_mma_sweep(bool sweep2, MmaArgs& a, double* workspace_big, double* workspace_small, double* sums, double* is4,
+                  cudaStream_t st) {
+    MmaCfg c;
+    if (!pick_cfg(a.d, c)) return ree_set_error(REE_E_UNSUPPORTED, "mma path: d > 103");
+    const int d = a.d, nta = (d + 8) / 8, P = 8 * c.npt * 8;
+    int sms = ree_grid_ctas() / 2;  // persistent: one CTA per SM
+    int64_t ntiles = (a.n + P - 1) / P;
+    int grid = (int)(ntiles < sms ? ntiles : sms);
+    make_plan(a.plan, nta, 8 / c.ks, c.maxm);
+    a.partials = workspace_big;
+    a.small = workspace_small;
+    size_t smem = mma_smem_bytes(d, c, sweep2);
+    int rc;
+    if (c.ntb == 2) rc = launch_cfg<2, 2, 1, 8>(sweep2, a, grid, smem, st);
+    else if (c.ntb == 4) rc = launch_cfg<4, 2, 2, 4>(sweep2, a, grid, smem, st);
+    else if (c.ntb == 7) rc = launch_cfg<7, 2, 3, 2>(sweep2, a, grid, smem, st);
+    else rc = launch_cfg<13, 2, 4, 1>(sweep2, a, grid, smem, st);
+    if (rc) return rc;
+    const int D1 = d + 1;
+    k_unpack_gram<<<(D1 * D1 + 255) / 256, 256, 0, st>>>(workspace_big, grid * c.ks, d, nta, (sweep2 && a.wmax) ? 1 : 0, sums);
+    rc = ree_check_launch("k_unpack_gram");
+    if (rc) return rc;
+    if (sweep2 && a.wmax) {
+        k_merge_expsums<<<1, 256, 0, st>>>(workspace_small, grid, is4);
+        return ree_check_launch("k_merge_expsums");
+    }
+    k_sum_small<<<1, 256, 0, st>>>(workspace_small, grid, sums + d + (size_t)d * d);
+    return ree_check_launch("k_sum_small");
+}
+
+// ---------------------------------------------------------------------------------------
+// entry points used by ree_step.cu
+// ---------------------------------------------------------------------------------------
+int ree_mma_step(const double* x, double* x_new, int64_t n, int d, int64_t ld, double t, const double* m_noise,
+                 const double* F, int tri, const double* z, uint64_t seed, uint64_t draw, int64_t first, int lsf_mode,
+                 const double* coef, double offset, const double* shift, double* g_new, double* e_new, double* ws_big,
+                 double* ws_small, double* sums, cudaStream_t st) {
+    MmaArgs a{};
+    a.x = x; a.n = n; a.ld = ld; a.d = d; a.A = F; a.tri = tri; a.shift = shift; a.x_new = x_new; a.t = t;
+    a.m_noise = m_noise; a.z = z; a.seed = seed; a.draw = draw; a.first = first; a.lsf_mode = lsf_mode; a.coef = coef;
+    a.offset = offset; a.g_new = g_new; a.e_new = e_new;
+    return ree_mma_sweep(false, a, ws_big, ws_small, sums, nullptr, st);
+}
+
+int ree_mma_maha(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* e, const double* mean,
+                 const double* Linv, const double* logdet, double sigma, double beta, int tgt_kind, const double* wmax,
+                 double* logq, double* w, double* ws_big, double* ws_small, double* sums, double* is4, cudaStream_t st) {
+    MmaArgs a{};
+    a.x = x; a.n = n; a.ld = ld; a.d = d; a.A = Linv; a.tri = 1; a.g = g; a.e = e; a.mean = mean; a.logdet = logdet;
+    a.wmax = wmax; a.sigma = sigma; a.beta = beta; a.tgt_kind = tgt_kind; a.logq = logq; a.w_out = w;
+    return ree_mma_sweep(true, a, ws_big, ws_small, sums, is4, st);
+}
+
+int ree_mma_sums(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* shift, double* ws_big,
+                 double* ws_small, double* sums, cudaStream_t st) {
+    MmaArgs a{};
+    a.x = x; a.n = n; a.ld = ld; a.d = d; a.g = g; a.mean = shift;  // plain moments: y = x - shift, no weights
+    return ree_mma_sweep(true, a, ws_big, ws_small, sums, nullptr, st);
+}

@@ -9,6 +9,17 @@
 #include "common.cuh"
 
 int ree_lsf_launch(const ree_lsf* lsf, const double* x, int64_t n, int64_t ld, double* g, cudaStream_t st);
+bool ree_mma_supported(int d);
+size_t ree_mma_partial_doubles(int d);
+int ree_mma_step(const double* x, double* x_new, int64_t n, int d, int64_t ld, double t, const double* m_noise,
+                 const double* F, int tri, const double* z, uint64_t seed, uint64_t draw, int64_t first, int lsf_mode,
+                 const double* coef, double offset, const double* shift, double* g_new, double* e_new, double* ws_big,
+                 double* ws_small, double* sums, cudaStream_t st);
+int ree_mma_maha(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* e, const double* mean,
+                 const double* Linv, const double* logdet, double sigma, double beta, int tgt_kind, const double* wmax,
+                 double* logq, double* w, double* ws_big, double* ws_small, double* sums, double* is4, cudaStream_t st);
+int ree_mma_sums(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* shift, double* ws_big,
+                 double* ws_small, double* sums, cudaStream_t st);
 
 #define TP 128  // particles per CTA tile in the contraction kernels
 #define JB 4    // output dims per register block
@@ -279,12 +290,17 @@ extern "C" int64_t ree_sums_len(int d) { return (int64_t)d + (int64_t)d * d + 2;
 
 extern "C" int64_t ree_workspace_bytes(int d) {
     size_t len = (size_t)d + (size_t)d * d + 2;
-    return (int64_t)((ws_big_offset() + len * (size_t)ree_grid_ctas()) * sizeof(double));
+    size_t big = len * (size_t)ree_grid_ctas();
+    size_t mma = ree_mma_partial_doubles(d);
+    return (int64_t)((ws_big_offset() + (big > mma ? big : mma)) * sizeof(double));
 }
 
 extern "C" int ree_ensemble_sums(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* shift,
                                  double* workspace, double* sums, void* stream) {
     if (!x || !workspace || !sums || d < 1 || n < 1) return ree_set_error(REE_E_BADARG, "ree_ensemble_sums: bad argument");
+    if (ree_mma_supported(d))
+        return ree_mma_sums(x, n, d, ld, g, shift, workspace + ws_big_offset(), workspace + REE_WS_HEADER, sums,
+                            ree_stream(stream));
     return launch_gram(x, n, d, ld, shift, nullptr, g, workspace, sums, ree_stream(stream));
 }
 
@@ -296,6 +312,24 @@ extern "C" int ree_cbree_step(const double* x, double* x_new, int64_t n, int d, 
         return ree_set_error(REE_E_BADARG, "ree_cbree_step: bad argument");
     if (noise_mode == REE_NOISE_INJECT && !z) return ree_set_error(REE_E_BADARG, "ree_cbree_step: INJECT needs z");
     cudaStream_t st = ree_stream(stream);
+    const bool fused_lsf = lsf && lsf->kind == REE_LSF_AFFINE;
+    if (lsf && lsf->kind != REE_LSF_EXTERNAL && !g_new) return ree_set_error(REE_E_BADARG, "ree_cbree_step: g_new is NULL");
+    if (ree_mma_supported(d)) {
+        // a Cholesky factor is lower triangular; the parity-mode factor U*sqrt(S) is dense
+        const int tri = (noise_mode == REE_NOISE_PHILOX) ? 1 : 0;
+        int lsf_mode = fused_lsf ? (lsf->coef ? 1 : 2) : 0;
+        int rc = ree_mma_step(x, x_new, n, d, ld, t, m_noise, F, tri, noise_mode == REE_NOISE_INJECT ? z : nullptr, seed,
+                              draw, first_particle, lsf_mode, fused_lsf ? lsf->coef : nullptr,
+                              fused_lsf ? lsf->offset : 0.0, shift, g_new, e_new, workspace + ws_big_offset(),
+                              workspace + REE_WS_HEADER, sums, st);
+        if (rc) return rc;
+        if (lsf && lsf->kind != REE_LSF_EXTERNAL && !fused_lsf) {
+            rc = ree_lsf_launch(lsf, x_new, n, ld, g_new, st);
+            if (rc) return rc;
+            return ree_count_failed(g_new, n, workspace, sums + d + (size_t)d * d, stream);
+        }
+        return 0;
+    }
     size_t smem = (size_t)d * TP * sizeof(double);
     if (smem > 200 * 1024) return ree_set_error(REE_E_UNSUPPORTED, "ree_cbree_step: d too large");
     StepArgs a{};
@@ -318,11 +352,15 @@ extern "C" int ree_cbree_step(const double* x, double* x_new, int64_t n, int d, 
 
 extern "C" int ree_cbree_maha(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* e,
                               const double* mean, const double* Linv, const double* logdet, double sigma, double beta,
-                              int tgt_kind, const double* wmax, const double* shift, double* logq, double* w,
-                              double* workspace, double* sums, double* is4, void* stream) {
-    if (!x || !g || !e || !mean || !Linv || !logdet || !wmax || !w || !workspace || !sums || !is4 || d < 1 || n < 1)
+                              int tgt_kind, const double* wmax, double* logq, double* w, double* workspace,
+                              double* sums, double* is4, void* stream) {
+    if (!x || !g || !e || !mean || !Linv || !logdet || !wmax || !workspace || !sums || !is4 || d < 1 || n < 1)
         return ree_set_error(REE_E_BADARG, "ree_cbree_maha: bad argument");
     cudaStream_t st = ree_stream(stream);
+    if (ree_mma_supported(d))
+        return ree_mma_maha(x, n, d, ld, g, e, mean, Linv, logdet, sigma, beta, tgt_kind, wmax, logq, w,
+                            workspace + ws_big_offset(), workspace + REE_WS_HEADER, sums, is4, st);
+    if (!w) return ree_set_error(REE_E_BADARG, "ree_cbree_maha: this dimension needs the weight scratch vector w");
     size_t smem = (size_t)d * TP * sizeof(double);
     if (smem > 200 * 1024) return ree_set_error(REE_E_UNSUPPORTED, "ree_cbree_maha: d too large");
     StepArgs a{};
@@ -333,5 +371,5 @@ extern "C" int ree_cbree_maha(const double* x, int64_t n, int d, int64_t ld, con
     k_contract<1><<<contract_grid(n), TP, smem, st>>>(a);
     int rc = ree_check_launch("ree_cbree_maha(contract)");
     if (rc) return rc;
-    return launch_gram(x, n, d, ld, shift, w, nullptr, workspace, sums, st);
+    return launch_gram(x, n, d, ld, mean, w, nullptr, workspace, sums, st);
 }

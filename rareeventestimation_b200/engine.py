@@ -291,14 +291,16 @@ class Engine:
         check(self.lib.ree_chol_scaled(Cmat.data_ptr(), d, float(scale), L.data_ptr(), stats.data_ptr(),
                                        self.stream), "ree_chol_scaled")
 
-    def cbree_maha(self, ens: Ensemble, mean, Linv, logdet, sigma, beta, kind, wmax, shift, w, sums, is4,
-                   logq=None):
+    def cbree_maha(self, ens: Ensemble, mean, Linv, logdet, sigma, beta, kind, wmax, sums, is4, w=None, logq=None):
+        """Sweep 2.  The weighted sums come back shifted by ``mean``."""
         ws = self.workspace(ens.d)
+        if w is None and not self.lib.ree_fused_path(ens.d):
+            w = self.empty(ens.ld)
         check(self.lib.ree_cbree_maha(ens.X.data_ptr(), ens.n, ens.d, ens.ld, ens.g.data_ptr(), ens.e.data_ptr(),
                                       mean.data_ptr(), Linv.data_ptr(), logdet.data_ptr(), float(sigma),
                                       float(beta), kind, wmax.data_ptr(),
-                                      shift.data_ptr() if shift is not None else None,
-                                      logq.data_ptr() if logq is not None else None, w.data_ptr(), ws.data_ptr(),
+                                      logq.data_ptr() if logq is not None else None,
+                                      w.data_ptr() if w is not None else None, ws.data_ptr(),
                                       sums.data_ptr(), is4.data_ptr(), self.stream), "ree_cbree_maha")
         self.comm.allreduce_sum_(sums)
         self.comm.combine_expsums_(is4)

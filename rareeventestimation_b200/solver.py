@@ -378,10 +378,8 @@ class CBREE(Solver):
         eng.moments_chol(sums_u, shift_u, d, 1, False, mean, cov, L, Linv, stats)
         eng.reduce_ess(dev, cache.sigma, cache.beta, kind, out=ess4)
         sums_w = eng.empty(slen)
-        w = eng.empty(dev.ld)
-        eng.cbree_maha(dev, mean, Linv, stats[0:1], cache.sigma, cache.beta, kind, ess4[0:1], shift_w, w, sums_w,
-                       is4)
-        eng.moments_chol(sums_w, shift_w, d, 0, True, m_w, C_w)
+        eng.cbree_maha(dev, mean, Linv, stats[0:1], cache.sigma, cache.beta, kind, ess4[0:1], sums_w, is4)
+        eng.moments_chol(sums_w, mean, d, 0, True, m_w, C_w)  # weighted sums are centred at the unweighted mean
         tails[0:2].copy_(sums_u[d + d * d:])
         tails[2:4].copy_(sums_w[d + d * d:])
         host = res.cpu().numpy()  # the one synchronising D2H of the iteration
