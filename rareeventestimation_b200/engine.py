@@ -64,9 +64,9 @@ class Comm:
     def combine_expsums_(self, out4: torch.Tensor) -> torch.Tensor:
         """all_gather the local 4-tuple and merge in rank order (identical bits on every rank)."""
         if self.enabled:
-            gathered = torch.empty((self.world, 4), dtype=out4.dtype, device=out4.device)
+            gathered = torch.empty(self.world * 4, dtype=out4.dtype, device=out4.device)
             self.dist.all_gather_into_tensor(gathered, out4.contiguous(), group=self.group)
-            out4.copy_(merge_expsums(gathered))
+            out4.copy_(merge_expsums(gathered.view(self.world, 4)))
         return out4
 
     def shard(self, n_global: int):
