@@ -68,71 +68,126 @@ struct MmaArgs {
 };
 
 // ---------------------------------------------------------------------------------------
-// shared helpers
+// shared-memory access with explicit 32-bit shared addresses (immediate offsets, no generic->shared conversion in
+// the inner loops) and cp.async staging
 // ---------------------------------------------------------------------------------------
-template <int S>
-__device__ __forceinline__ void pack_matrix(double* Lf, const double* __restrict__ A, int d, int ntd, int KT2) {
-    // fragment order: tile (mt, kk) -> 32 consecutive doubles, lane l holds A[8mt + l/4][4kk + l%4]
-    for (int idx = threadIdx.x; idx < ntd * KT2 * 32; idx += MT) {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds128(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// DMMA under a warp-uniform guard (predication instead of a branch keeps the block schedulable)
+__device__ __forceinline__ void dmma_if(double& c0, double& c1, double a, double b, int on) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %4, 0;\n\t"
+        "@p mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n\t}"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b), "r"(on));
+}
+
+template <int NTB>
+__device__ __forceinline__ void pack_matrix(double* Lf, const double* __restrict__ A, int d) {
+    // fragment order with a compile-time stride: tile (mt, kk) -> 32 consecutive doubles at (mt*2*NTB + kk)*32,
+    // lane l holds A[8mt + l/4][4kk + l%4]
+    constexpr int KT2B = 2 * NTB;
+    for (int idx = threadIdx.x; idx < NTB * KT2B * 32; idx += MT) {
         int l = idx & 31, tile = idx >> 5;
-        int mt = tile / KT2, kk = tile - mt * KT2;
+        int mt = tile / KT2B, kk = tile - mt * KT2B;
         int r = 8 * mt + (l >> 2), c = 4 * kk + (l & 3);
-        Lf[idx] = (r < d && c < d) ? A[(size_t)r * d + c] : 0.0;
+        Lf[idx] = (A && r < d && c < d) ? A[(size_t)r * d + c] : 0.0;
+    }
+}
+
+// C[mt][pt] += A(mt, 2q..2q+1) * B(q)[pt] for all k-pairs q; B fragments come from `gen` (Philox / global loads),
+// generated one k-pair ahead so that their instruction stream interleaves with the DMMAs of the current pair.
+template <int NTB, int NPT, class Gen>
+__device__ __forceinline__ void transform_tiles(uint32_t lf_lane_addr, int ntd, int tri, Gen& gen,
+                                                double (&c)[NTB][NPT][2]) {
+    constexpr int KT2B = 2 * NTB;
+    double nb0[NPT], nb1[NPT];
+    gen(0, nb0, nb1);
+#pragma unroll 1
+    for (int q = 0; q < ntd; ++q) {
+        double b0[NPT], b1[NPT];
+#pragma unroll
+        for (int pt = 0; pt < NPT; ++pt) {
+            b0[pt] = nb0[pt];
+            b1[pt] = nb1[pt];
+        }
+        gen(q + 1, nb0, nb1);
+        const uint32_t col = lf_lane_addr + (uint32_t)q * 512u;  // tile (0, 2q)
+#pragma unroll
+        for (int mt = 0; mt < NTB; ++mt) {
+            const int on = (mt < ntd && (!tri || mt >= q)) ? 1 : 0;
+            const double a0 = lds64(col + mt * KT2B * 256);
+            const double a1 = lds64(col + mt * KT2B * 256 + 256);
+#pragma unroll
+            for (int pt = 0; pt < NPT; ++pt) {
+                dmma_if(c[mt][pt][0], c[mt][pt][1], a0, b0[pt], on);
+                dmma_if(c[mt][pt][0], c[mt][pt][1], a1, b1[pt], on);
+            }
+        }
     }
 }
 
 struct GramRegs {
-    int offR, offC;    // shared-memory offsets (doubles) of the first row / column tile of a macro tile
-    int flags;         // bit0: second row tile exists, bit1: second col tile exists, bit2: diagonal macro tile
+    uint32_t addrR, addrC;  // shared byte addresses of this lane's element of the first row / column tile
+    int flags;              // bit q: tile q of the 2x2 macro tile (q = 2*row + col) is accumulated
 };
 
 template <int MAXM, int S>
-__device__ __forceinline__ void gram_setup(const GramPlan& plan, int wi, int nta, int lr, int lc, GramRegs (&gr)[MAXM],
-                                           int& nmac) {
+__device__ __forceinline__ void gram_setup(const GramPlan& plan, int wi, int nta, int lr, int lc, uint32_t ys_addr,
+                                           GramRegs (&gr)[MAXM], int& nmac) {
     nmac = plan.nmac[wi];
 #pragma unroll
     for (int m = 0; m < MAXM; ++m) {
-        int code = (m < nmac) ? plan.mac[wi][m] : 0;
+        const bool live = m < nmac;
+        int code = live ? plan.mac[wi][m] : 0;
         int mr = code & 0xff, mc = code >> 8;
-        gr[m].offR = (16 * mr + lr) * S + 2 * lc;
-        gr[m].offC = (16 * mc + lr) * S + 2 * lc;
-        gr[m].flags = ((2 * mr + 1 < nta) ? 1 : 0) | ((2 * mc + 1 < nta) ? 2 : 0) | ((mr == mc) ? 4 : 0);
+        gr[m].addrR = ys_addr + (uint32_t)(((16 * mr + lr) * S + 2 * lc) * 8);
+        gr[m].addrC = ys_addr + (uint32_t)(((16 * mc + lr) * S + 2 * lc) * 8);
+        const bool r1 = 2 * mr + 1 < nta, c1 = 2 * mc + 1 < nta, diag = mr == mc;
+        gr[m].flags = live ? (1 | ((c1 && !diag) ? 2 : 0) | (r1 ? 4 : 0) | ((r1 && c1) ? 8 : 0)) : 0;
     }
 }
 
-// accumulate the Gram of the k-pairs [u_lo, u_hi) of the shared tile into the warp's macro tiles
+// accumulate the Gram of the k-pairs [u_lo, u_hi) of the shared tile into the warp's macro tiles.  Loads are
+// unconditional (the tile is padded with zero rows to full macro tiles), DMMAs are predicated.
 template <int MAXM, int S>
-__device__ __forceinline__ void gram_accumulate(const double* __restrict__ Ys, const GramRegs (&gr)[MAXM], int nmac,
-                                                int u_lo, int u_hi, double (&acc)[MAXM][4][2]) {
+__device__ __forceinline__ void gram_accumulate(const GramRegs (&gr)[MAXM], int u_lo, int u_hi,
+                                                double (&acc)[MAXM][4][2]) {
+#pragma unroll 2
     for (int u = u_lo; u < u_hi; ++u) {
 #pragma unroll
         for (int m = 0; m < MAXM; ++m) {
-            if (m < nmac) {
-                const int f = gr[m].flags;
-                const double2 a0 = *reinterpret_cast<const double2*>(Ys + gr[m].offR + 8 * u);
-                double2 a1 = make_double2(0.0, 0.0), b0 = a0, b1 = make_double2(0.0, 0.0);
-                if (f & 1) a1 = *reinterpret_cast<const double2*>(Ys + gr[m].offR + 8 * S + 8 * u);
-                if (f & 4) {
-                    b1 = a1;
-                } else {
-                    b0 = *reinterpret_cast<const double2*>(Ys + gr[m].offC + 8 * u);
-                    if (f & 2) b1 = *reinterpret_cast<const double2*>(Ys + gr[m].offC + 8 * S + 8 * u);
-                }
-                dmma(acc[m][0][0], acc[m][0][1], a0.x, b0.x);
-                dmma(acc[m][0][0], acc[m][0][1], a0.y, b0.y);
-                if ((f & 2) && !(f & 4)) {  // (2mr, 2mc+1): upper triangle for a diagonal macro tile
-                    dmma(acc[m][1][0], acc[m][1][1], a0.x, b1.x);
-                    dmma(acc[m][1][0], acc[m][1][1], a0.y, b1.y);
-                }
-                if (f & 1) {
-                    dmma(acc[m][2][0], acc[m][2][1], a1.x, b0.x);
-                    dmma(acc[m][2][0], acc[m][2][1], a1.y, b0.y);
-                    if (f & 2) {
-                        dmma(acc[m][3][0], acc[m][3][1], a1.x, b1.x);
-                        dmma(acc[m][3][0], acc[m][3][1], a1.y, b1.y);
-                    }
-                }
-            }
+            const int f = gr[m].flags;
+            const uint32_t ra = gr[m].addrR + (uint32_t)u * 64u, ca = gr[m].addrC + (uint32_t)u * 64u;
+            const double2 a0 = lds128(ra), a1 = lds128(ra + 8 * S * 8);
+            const double2 b0 = lds128(ca), b1 = lds128(ca + 8 * S * 8);
+            dmma_if(acc[m][0][0], acc[m][0][1], a0.x, b0.x, f & 1);
+            dmma_if(acc[m][0][0], acc[m][0][1], a0.y, b0.y, f & 1);
+            dmma_if(acc[m][1][0], acc[m][1][1], a0.x, b1.x, f & 2);
+            dmma_if(acc[m][1][0], acc[m][1][1], a0.y, b1.y, f & 2);
+            dmma_if(acc[m][2][0], acc[m][2][1], a1.x, b0.x, f & 4);
+            dmma_if(acc[m][2][0], acc[m][2][1], a1.y, b0.y, f & 4);
+            dmma_if(acc[m][3][0], acc[m][3][1], a1.x, b1.x, f & 8);
+            dmma_if(acc[m][3][0], acc[m][3][1], a1.y, b1.y, f & 8);
         }
     }
 }
@@ -161,37 +216,70 @@ __device__ __forceinline__ void gram_store(double* __restrict__ part /* [T][64] 
     }
 }
 
+// B-fragment sources ------------------------------------------------------------------------
+template <int NPT>
+struct GenPhilox {  // z ~ N(0,1): counter (global particle, dim pair 4q+lc, draw)
+    uint64_t seed, draw, particle[NPT];
+    uint32_t lc;
+    __device__ __forceinline__ void operator()(int q, double (&b0)[NPT], double (&b1)[NPT]) const {
+#pragma unroll
+        for (int pt = 0; pt < NPT; ++pt)
+            philox_normal_pair(seed, particle[pt], (uint32_t)(4 * q) + lc, draw, b0[pt], b1[pt]);
+    }
+};
+
+template <int NPT>
+struct GenGlobal {  // rows 8q+lc and 8q+4+lc of an SoA array at this lane's particle, minus an optional per-row mean
+    const double* base[NPT];  // &x[lc*ld + particle] (NULL if the particle is out of range)
+    const double* mean;       // shared-memory vector or NULL
+    int64_t ld;
+    int d, lc;
+    __device__ __forceinline__ void operator()(int q, double (&b0)[NPT], double (&b1)[NPT]) const {
+        const int j0 = 8 * q + lc, j1 = j0 + 4;
+#pragma unroll
+        for (int pt = 0; pt < NPT; ++pt) {
+            double v0 = 0.0, v1 = 0.0;
+            if (base[pt] && j0 < d) v0 = __ldg(base[pt] + (int64_t)(8 * q) * ld) - (mean ? mean[j0] : 0.0);
+            if (base[pt] && j1 < d) v1 = __ldg(base[pt] + (int64_t)(8 * q + 4) * ld) - (mean ? mean[j1] : 0.0);
+            b0[pt] = v0;
+            b1[pt] = v1;
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------------------
 // sweep 1
 // ---------------------------------------------------------------------------------------
 template <int NTB, int NPT, int MAXM, int KS>
 __global__ void __launch_bounds__(MT, 1) k_step_mma(const MmaArgs a) {
-    constexpr int P = 8 * NPT * 8;  // particles per CTA tile
-    constexpr int S = P + 8;        // row stride of the shared tile (8 mod 16 doubles)
+    constexpr int P = 8 * NPT * 8;                // particles per CTA tile
+    constexpr int S = P + 8;                      // row stride of the shared tile (8 mod 16 doubles)
+    constexpr int ROWS = 16 * ((NTB + 1) / 2);    // tile rows padded to full macro tiles
     extern __shared__ double sm[];
-    const int d = a.d, ntd = (d + 7) >> 3, nta = (d + 8) >> 3, KT2 = 2 * ntd;
-    const int rows = 16 * ((nta + 1) >> 1);  // tile rows padded to full macro tiles
+    const int d = a.d, ntd = (d + 7) >> 3, nta = (d + 8) >> 3;
     double* Lf = sm;
-    double* Ys = Lf + ntd * KT2 * 32;
-    double* vm = Ys + rows * S;
+    double* Ys = Lf + NTB * 2 * NTB * 32;
+    double* vm = Ys + ROWS * S;
     double* vs = vm + 8 * NTB;
     double* vc = vs + 8 * NTB;
     __shared__ double red[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lc = lane & 3;
 
-    pack_matrix<S>(Lf, a.A, d, ntd, KT2);
+    pack_matrix<NTB>(Lf, a.A, d);
     for (int j = tid; j < 8 * NTB; j += MT) {
         vm[j] = (j < d) ? a.m_noise[j] : 0.0;
         vs[j] = (j < d && a.shift) ? a.shift[j] : 0.0;
         vc[j] = (j < d) ? (a.lsf_mode == 1 ? a.coef[j] : 1.0) : 0.0;
     }
-    for (int idx = tid; idx < rows * S; idx += MT) Ys[idx] = 0.0;
+    for (int idx = tid; idx < ROWS * S; idx += MT) Ys[idx] = 0.0;
 
     constexpr int WG = 8 / KS;
     const int grp = warp / WG, wi = warp % WG;
+    const uint32_t ys_addr = smem_u32(Ys);
+    const uint32_t lf_lane = smem_u32(Lf) + lane * 8;
     GramRegs gr[MAXM];
     int nmac;
-    gram_setup<MAXM, S>(a.plan, wi, nta, lr, lc, gr, nmac);
+    gram_setup<MAXM, S>(a.plan, wi, nta, lr, lc, ys_addr, gr, nmac);
     double acc[MAXM][4][2];
 #pragma unroll
     for (int m = 0; m < MAXM; ++m)
@@ -203,6 +291,23 @@ __global__ void __launch_bounds__(MT, 1) k_step_mma(const MmaArgs a) {
     const int pw = warp * 8 * NPT;  // first tile column of this warp
     const double e_const = (double)d * REE_LOG_2PI;
     const int64_t ntiles = (a.n + P - 1) / P;
+    // this lane's element of tile row block mt, particle tile pt: row 8mt+lr, columns pw+8pt+2lc (+1)
+    const uint32_t own_addr = ys_addr + (uint32_t)((lr * S + pw + 2 * lc) * 8);
+
+    auto prefetch = [&](int64_t i0) {  // x tile -> shared tile, every lane fetches exactly the elements it consumes
+#pragma unroll
+        for (int mt = 0; mt < NTB; ++mt) {
+            const int row = 8 * mt + lr;
+#pragma unroll
+            for (int pt = 0; pt < NPT; ++pt) {
+                const int64_t ip = i0 + pw + 8 * pt + 2 * lc;
+                if (row < d && ip < a.ld)
+                    cp_async16(own_addr + (uint32_t)((8 * mt * S + 8 * pt) * 8), a.x + (int64_t)row * a.ld + ip);
+            }
+        }
+    };
+    if ((int64_t)blockIdx.x < ntiles) prefetch((int64_t)blockIdx.x * P);
+
     for (int64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
         const int64_t i0 = tix * P;
         // ---- F z on the tensor pipe: c[mt][pt] = rows 8mt.., particles pw+8pt.. ------------------
@@ -211,33 +316,23 @@ __global__ void __launch_bounds__(MT, 1) k_step_mma(const MmaArgs a) {
         for (int mt = 0; mt < NTB; ++mt)
 #pragma unroll
             for (int pt = 0; pt < NPT; ++pt) c[mt][pt][0] = c[mt][pt][1] = 0.0;
-        for (int q = 0; q < ntd; ++q) {
-            double b0[NPT], b1[NPT];
+        if (a.z) {
+            GenGlobal<NPT> gen;
 #pragma unroll
             for (int pt = 0; pt < NPT; ++pt) {
                 const int64_t ip = i0 + pw + 8 * pt + lr;
-                if (a.z) {
-                    const int j0 = 8 * q + lc, j1 = j0 + 4;
-                    b0[pt] = (j0 < d && ip < a.n) ? a.z[(int64_t)j0 * a.ld + ip] : 0.0;
-                    b1[pt] = (j1 < d && ip < a.n) ? a.z[(int64_t)j1 * a.ld + ip] : 0.0;
-                } else {
-                    philox_normal_pair(a.seed, (uint64_t)(a.first + ip), (uint32_t)(4 * q + lc), a.draw, b0[pt],
-                                       b1[pt]);
-                }
+                gen.base[pt] = (ip < a.n) ? a.z + (int64_t)lc * a.ld + ip : nullptr;
             }
+            gen.mean = nullptr; gen.ld = a.ld; gen.d = d; gen.lc = lc;
+            transform_tiles<NTB, NPT>(lf_lane, ntd, a.tri, gen, c);
+        } else {
+            GenPhilox<NPT> gen;
+            gen.seed = a.seed; gen.draw = a.draw; gen.lc = (uint32_t)lc;
 #pragma unroll
-            for (int mt = 0; mt < NTB; ++mt) {
-                if (mt < ntd && (!a.tri || mt >= q)) {
-                    const double a0 = Lf[((mt * KT2 + 2 * q) << 5) + lane];
-                    const double a1 = Lf[((mt * KT2 + 2 * q + 1) << 5) + lane];
-#pragma unroll
-                    for (int pt = 0; pt < NPT; ++pt) {
-                        dmma(c[mt][pt][0], c[mt][pt][1], a0, b0[pt]);
-                        dmma(c[mt][pt][0], c[mt][pt][1], a1, b1[pt]);
-                    }
-                }
-            }
+            for (int pt = 0; pt < NPT; ++pt) gen.particle[pt] = (uint64_t)(a.first + i0 + pw + 8 * pt + lr);
+            transform_tiles<NTB, NPT>(lf_lane, ntd, a.tri, gen, c);
         }
+        cp_async_wait_all();
         // ---- epilogue: x' = t x + (m + F z), store, energy / affine LSF partials, y -> shared tile ----
         double se[NPT][2], sg[NPT][2];
 #pragma unroll
@@ -250,11 +345,11 @@ __global__ void __launch_bounds__(MT, 1) k_step_mma(const MmaArgs a) {
                 const double mrow = vm[row], srow = vs[row], crow = vc[row];
 #pragma unroll
                 for (int pt = 0; pt < NPT; ++pt) {
-                    const int pc = pw + 8 * pt + 2 * lc;
-                    const int64_t ip = i0 + pc;
+                    const int64_t ip = i0 + pw + 8 * pt + 2 * lc;
                     const bool in_buf = rv && ip < a.ld;
-                    double2 xv = make_double2(0.0, 0.0);
-                    if (in_buf) xv = *reinterpret_cast<const double2*>(a.x + (int64_t)row * a.ld + ip);
+                    const uint32_t sa = own_addr + (uint32_t)((8 * mt * S + 8 * pt) * 8);
+                    double2 xv = lds128(sa);
+                    if (!in_buf) xv = make_double2(0.0, 0.0);
                     // t*X + (m_noise + Z F^T): grouping of solver.py:667
                     double2 xn;
                     xn.x = __dadd_rn(__dmul_rn(a.t, xv.x), __dadd_rn(mrow, c[mt][pt][0]));
@@ -268,7 +363,7 @@ __global__ void __launch_bounds__(MT, 1) k_step_mma(const MmaArgs a) {
                         y.x = v0 ? 1.0 : 0.0;
                         y.y = v1 ? 1.0 : 0.0;
                     }
-                    *reinterpret_cast<double2*>(Ys + row * S + pc) = y;
+                    sts128(sa, y);
                     if (rv) {
                         se[pt][0] = fma(xn.x, xn.x, se[pt][0]);
                         se[pt][1] = fma(xn.y, xn.y, se[pt][1]);
@@ -283,7 +378,8 @@ __global__ void __launch_bounds__(MT, 1) k_step_mma(const MmaArgs a) {
             for (int pt = 0; pt < NPT; ++pt) {
                 const int pc = pw + 8 * pt + 2 * lc;
                 const int64_t ip = i0 + pc;
-                *reinterpret_cast<double2*>(Ys + d * S + pc) = make_double2(ip < a.n ? 1.0 : 0.0, ip + 1 < a.n ? 1.0 : 0.0);
+                sts128(ys_addr + (uint32_t)((d * S + pc) * 8),
+                       make_double2(ip < a.n ? 1.0 : 0.0, ip + 1 < a.n ? 1.0 : 0.0));
             }
         }
 #pragma unroll
@@ -310,8 +406,9 @@ __global__ void __launch_bounds__(MT, 1) k_step_mma(const MmaArgs a) {
         }
         __syncthreads();
         // ---- Gram of the tile (k-split across warp groups) ------------------------------------
-        gram_accumulate<MAXM, S>(Ys, gr, nmac, grp * (P / 8 / KS), (grp + 1) * (P / 8 / KS), acc);
+        gram_accumulate<MAXM, S>(gr, grp * (P / 8 / KS), (grp + 1) * (P / 8 / KS), acc);
         __syncthreads();
+        if (tix + gridDim.x < ntiles) prefetch((tix + gridDim.x) * P);  // lands while the next F z runs
     }
     const int T = nta * (nta + 1) / 2;
     gram_store<MAXM>(a.partials + ((size_t)blockIdx.x * KS + grp) * T * 64, a.plan, wi, nmac, nta, lr, lc, acc);
@@ -320,32 +417,34 @@ __global__ void __launch_bounds__(MT, 1) k_step_mma(const MmaArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-// sweep 2
+// sweep 2 (and, with wmax == NULL, the plain shifted moments of an existing ensemble)
 // ---------------------------------------------------------------------------------------
 template <int NTB, int NPT, int MAXM, int KS>
 __global__ void __launch_bounds__(MT, 1) k_maha_mma(const MmaArgs a) {
     constexpr int P = 8 * NPT * 8;
     constexpr int S = P + 8;
+    constexpr int ROWS = 16 * ((NTB + 1) / 2);
     extern __shared__ double sm[];
-    const int d = a.d, ntd = (d + 7) >> 3, nta = (d + 8) >> 3, KT2 = 2 * ntd;
-    const int rows = 16 * ((nta + 1) >> 1);
+    const int d = a.d, ntd = (d + 7) >> 3, nta = (d + 8) >> 3;
     double* Lf = sm;
-    double* Ys = Lf + ntd * KT2 * 32;
-    double* vm = Ys + rows * S;  // mean
-    double* sw = vm + 8 * NTB;   // sqrt(w) of the tile's particles [P]
+    double* Ys = Lf + NTB * 2 * NTB * 32;
+    double* vm = Ys + ROWS * S;  // mean
+    double* sw = vm + 8 * NTB;   // per particle of the tile: |u|^2, then sqrt(w)   [P]
     __shared__ ExpSums sh[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lc = lane & 3;
-    const bool weighted = a.wmax != nullptr;  // false: plain moments of an existing ensemble (no Linv, no IS)
+    const bool weighted = a.wmax != nullptr;  // false: plain moments (no Linv, no IS)
 
-    if (weighted) pack_matrix<S>(Lf, a.A, d, ntd, KT2);
+    pack_matrix<NTB>(Lf, weighted ? a.A : nullptr, d);
     for (int j = tid; j < 8 * NTB; j += MT) vm[j] = (j < d && a.mean) ? a.mean[j] : 0.0;
-    for (int idx = tid; idx < rows * S; idx += MT) Ys[idx] = 0.0;
+    for (int idx = tid; idx < ROWS * S; idx += MT) Ys[idx] = 0.0;
 
     constexpr int WG = 8 / KS;
     const int grp = warp / WG, wi = warp % WG;
+    const uint32_t ys_addr = smem_u32(Ys);
+    const uint32_t lf_lane = smem_u32(Lf) + lane * 8;
     GramRegs gr[MAXM];
     int nmac;
-    gram_setup<MAXM, S>(a.plan, wi, nta, lr, lc, gr, nmac);
+    gram_setup<MAXM, S>(a.plan, wi, nta, lr, lc, ys_addr, gr, nmac);
     double acc[MAXM][4][2];
 #pragma unroll
     for (int m = 0; m < MAXM; ++m)
@@ -358,102 +457,88 @@ __global__ void __launch_bounds__(MT, 1) k_maha_mma(const MmaArgs a) {
     const int pw = warp * 8 * NPT;
     const double logdet = weighted ? a.logdet[0] : 0.0;
     const double wmax = weighted ? a.wmax[0] : 0.0;
+    const double lq_const = (double)d * REE_LOG_2PI + logdet;
     const int64_t ntiles = (a.n + P - 1) / P;
     for (int64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
         const int64_t i0 = tix * P;
-        // ---- stage y = x - mean (coalesced 16-byte loads along the particle axis) -----------------
+        // ---- raw tile -> shared memory with cp.async (16-byte chunks along the particle axis) ------
         for (int idx = tid; idx < d * (P / 2); idx += MT) {
             const int j = idx / (P / 2), p2 = (idx - j * (P / 2)) * 2;
             const int64_t ip = i0 + p2;
-            double2 v = make_double2(0.0, 0.0);
-            if (ip < a.ld) v = *reinterpret_cast<const double2*>(a.x + (int64_t)j * a.ld + ip);
-            const double mj = vm[j];
-            v.x = (ip < a.n) ? v.x - mj : 0.0;
-            v.y = (ip + 1 < a.n) ? v.y - mj : 0.0;
-            *reinterpret_cast<double2*>(Ys + j * S + p2) = v;
+            if (ip < a.ld) cp_async16(ys_addr + (uint32_t)((j * S + p2) * 8), a.x + (int64_t)j * a.ld + ip);
         }
-        if (!weighted) {
-            for (int p = tid; p < P; p += MT) {
-                const int64_t ip = i0 + p;
-                Ys[d * S + p] = (ip < a.n) ? 1.0 : 0.0;
-                if (a.g && ip < a.n) n_fail += (a.g[ip] <= 0.0) ? 1.0 : 0.0;
-            }
-        }
-        __syncthreads();
         if (weighted) {
-            // ---- u = Linv y on the tensor pipe; B fragments come from the shared tile ----------
+            // ---- u = Linv (x - mean) on the tensor pipe; B fragments straight from global / L2 ----------
             double c[NTB][NPT][2];
 #pragma unroll
             for (int mt = 0; mt < NTB; ++mt)
 #pragma unroll
                 for (int pt = 0; pt < NPT; ++pt) c[mt][pt][0] = c[mt][pt][1] = 0.0;
-            for (int q = 0; q < ntd; ++q) {
-                double b0[NPT], b1[NPT];
+            GenGlobal<NPT> gen;
 #pragma unroll
-                for (int pt = 0; pt < NPT; ++pt) {
-                    const int col = pw + 8 * pt + lr;
-                    b0[pt] = Ys[(8 * q + lc) * S + col];
-                    b1[pt] = Ys[(8 * q + 4 + lc) * S + col];
-                }
-#pragma unroll
-                for (int mt = 0; mt < NTB; ++mt) {
-                    if (mt < ntd && (!a.tri || mt >= q)) {
-                        const double a0 = Lf[((mt * KT2 + 2 * q) << 5) + lane];
-                        const double a1 = Lf[((mt * KT2 + 2 * q + 1) << 5) + lane];
-#pragma unroll
-                        for (int pt = 0; pt < NPT; ++pt) {
-                            dmma(c[mt][pt][0], c[mt][pt][1], a0, b0[pt]);
-                            dmma(c[mt][pt][0], c[mt][pt][1], a1, b1[pt]);
-                        }
-                    }
-                }
+            for (int pt = 0; pt < NPT; ++pt) {
+                const int64_t ip = i0 + pw + 8 * pt + lr;
+                gen.base[pt] = (ip < a.n) ? a.x + (int64_t)lc * a.ld + ip : nullptr;
             }
-            // ---- q = |u|^2 per particle, log q, IS statistics, weights ---------------------------
+            gen.mean = vm; gen.ld = a.ld; gen.d = d; gen.lc = lc;
+            transform_tiles<NTB, NPT>(lf_lane, ntd, a.tri, gen, c);
+            // ---- q = |u|^2 per particle -> this warp's slice of sw ----------------------------------
 #pragma unroll
             for (int pt = 0; pt < NPT; ++pt) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     double qq = 0.0;
 #pragma unroll
-                    for (int mt = 0; mt < NTB; ++mt)
-                        if (mt < ntd) qq = fma(c[mt][pt][h], c[mt][pt][h], qq);
+                    for (int mt = 0; mt < NTB; ++mt) qq = fma(c[mt][pt][h], c[mt][pt][h], qq);
 #pragma unroll
                     for (int o = 4; o < 32; o <<= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
-                    const int p = pw + 8 * pt + 2 * lc + h;
-                    const int64_t ip = i0 + p;
-                    if (lr == 0) {
-                        double swv = 0.0;
-                        if (ip < a.n) {
-                            const double lq = -0.5 * ((double)d * REE_LOG_2PI + logdet + qq);
-                            if (a.logq) a.logq[ip] = lq;
-                            const double gi = a.g[ip], ei = a.e[ip];
-                            const double r = __dsub_rn(-ei, lq);  // -e_fun - log_pdf  (solver.py:684)
-                            if (isfinite(r)) expsums_add(is_acc, r, gi <= 0.0 ? 1.0 : 0.0);
-                            const double al = __dmul_rn(ree_logtgt(gi, ei, a.sigma, a.tgt_kind), a.beta);
-                            const double wv = isfinite(al) ? exp(al - wmax) : 0.0;
-                            if (a.w_out) a.w_out[ip] = wv;
-                            swv = sqrt(wv);
-                        }
-                        sw[p] = swv;
-                    }
+                    if (lr == 0) sw[pw + 8 * pt + 2 * lc + h] = qq;
                 }
             }
-            __syncthreads();
-            // ---- rescale the tile by sqrt(w); augmented row = sqrt(w) => sum w y and sum w -------
-            for (int idx = tid; idx < (d + 1) * (P / 2); idx += MT) {
-                const int j = idx / (P / 2), p2 = (idx - j * (P / 2)) * 2;
-                const double2 s2 = *reinterpret_cast<const double2*>(sw + p2);
-                double2 v = s2;
-                if (j < d) {
-                    v = *reinterpret_cast<const double2*>(Ys + j * S + p2);
-                    v.x *= s2.x;
-                    v.y *= s2.y;
+            __syncwarp();
+            // ---- one lane per particle: log q, IS statistics, weight (solver.py:629-632, 683-686) -------
+            if (lane < 8 * NPT) {
+                const int p = pw + lane;
+                const int64_t ip = i0 + p;
+                double swv = 0.0;
+                if (ip < a.n) {
+                    const double lq = -0.5 * (lq_const + sw[p]);
+                    if (a.logq) a.logq[ip] = lq;
+                    const double gi = a.g[ip], ei = a.e[ip];
+                    const double r = __dsub_rn(-ei, lq);  // -e_fun - log_pdf  (solver.py:684)
+                    if (isfinite(r)) expsums_add(is_acc, r, gi <= 0.0 ? 1.0 : 0.0);
+                    const double al = __dmul_rn(ree_logtgt(gi, ei, a.sigma, a.tgt_kind), a.beta);
+                    const double wv = isfinite(al) ? exp(al - wmax) : 0.0;
+                    if (a.w_out) a.w_out[ip] = wv;
+                    swv = sqrt(wv);
                 }
-                *reinterpret_cast<double2*>(Ys + j * S + p2) = v;
+                sw[p] = swv;
             }
-            __syncthreads();
+        } else {
+            for (int p = tid; p < P; p += MT) {
+                const int64_t ip = i0 + p;
+                sw[p] = (ip < a.n) ? 1.0 : 0.0;
+                if (a.g && ip < a.n) n_fail += (a.g[ip] <= 0.0) ? 1.0 : 0.0;
+            }
         }
-        gram_accumulate<MAXM, S>(Ys, gr, nmac, grp * (P / 8 / KS), (grp + 1) * (P / 8 / KS), acc);
+        cp_async_wait_all();
+        __syncthreads();
+        // ---- centre and scale the tile by sqrt(w) in place; augmented row = sqrt(w) => sum w y, sum w ----
+        for (int idx = tid; idx < (d + 1) * (P / 2); idx += MT) {
+            const int j = idx / (P / 2), p2 = (idx - j * (P / 2)) * 2;
+            const uint32_t sa = ys_addr + (uint32_t)((j * S + p2) * 8);
+            const double2 s2 = *reinterpret_cast<const double2*>(sw + p2);
+            double2 v = s2;
+            if (j < d) {
+                const double2 xv = lds128(sa);
+                const double mj = vm[j];
+                v.x = (s2.x != 0.0) ? (xv.x - mj) * s2.x : 0.0;  // select, not multiply: stale/padded lanes
+                v.y = (s2.y != 0.0) ? (xv.y - mj) * s2.y : 0.0;
+            }
+            sts128(sa, v);
+        }
+        __syncthreads();
+        gram_accumulate<MAXM, S>(gr, grp * (P / 8 / KS), (grp + 1) * (P / 8 / KS), acc);
         __syncthreads();
     }
     const int T = nta * (nta + 1) / 2;
@@ -582,9 +667,10 @@ bool ree_mma_supported(int d) {
 extern "C" int ree_fused_path(int d) { return ree_mma_supported(d) ? 1 : 0; }
 
 static size_t mma_smem_bytes(int d, const MmaCfg& c, bool sweep2) {
-    int ntd = (d + 7) / 8, nta = (d + 8) / 8, KT2 = 2 * ntd, P = 8 * c.npt * 8, S = P + 8;
-    int rows = 16 * ((nta + 1) / 2);
-    size_t n = (size_t)ntd * KT2 * 32 + (size_t)rows * S + (sweep2 ? (8 * c.ntb + P) : 3 * 8 * c.ntb);
+    (void)d;
+    int P = 8 * c.npt * 8, S = P + 8;
+    int rows = 16 * ((c.ntb + 1) / 2);
+    size_t n = (size_t)c.ntb * 2 * c.ntb * 32 + (size_t)rows * S + (sweep2 ? (8 * c.ntb + P) : 3 * 8 * c.ntb);
     return n * sizeof(double);
 }
 

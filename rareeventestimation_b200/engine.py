@@ -132,6 +132,7 @@ class Engine:
         self.device = device
         self.comm = Comm(enabled=False)
         self._ws = {}
+        self._pool = {}
         self._staging = None
         with torch.cuda.device(self.device):
             self.num_ctas = self.lib.ree_num_ctas()
@@ -169,11 +170,29 @@ class Engine:
 
     # -- ensemble I/O ---------------------------------------------------------- #
     def alloc_ensemble(self, n: int, d: int, first: int = 0, with_vectors=True) -> Ensemble:
+        """Ensemble buffers come from a free list first: at the headline size one ensemble is 8 GB and a
+        cudaMalloc/cudaFree pair per iteration would cost more than the sweeps."""
+        free = self._pool.get((int(n), int(d)))
+        if free:
+            ens = free.pop()
+            ens.first = int(first)
+            return ens
         ld = _pad(n)
         X = self.empty(d, ld)
         g = self.empty(ld) if with_vectors else None
         e = self.empty(ld) if with_vectors else None
         return Ensemble(X, n, d, ld, first, g, e)
+
+    def release(self, ens: Optional[Ensemble], keep: int = 3):
+        """Return an ensemble nobody references any more to the free list."""
+        if ens is None or ens.g is None or ens.e is None:
+            return
+        free = self._pool.setdefault((ens.n, ens.d), [])
+        if len(free) < keep:
+            free.append(ens)
+
+    def drop_pool(self):
+        self._pool.clear()
 
     def upload(self, host: np.ndarray, first: int = 0) -> Ensemble:
         """Host (n,d) C-order array -> SoA ensemble (chunked H2D + device transpose)."""

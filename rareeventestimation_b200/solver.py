@@ -624,6 +624,8 @@ class CBREE(Solver):
         h1 = np.sqrt(0.01 / np.maximum(d1, d2))
         cache.t_step = np.exp(-np.maximum(100 * h0, h1))
         cache.num_lsf_evals = cache_new.num_lsf_evals
+        dev, cache_new._dev = cache_new._dev, None  # the trial ensemble is discarded (solver.py:804-817)
+        self._eng.release(dev)
 
     # ------------------------------------------------------------------ #
     # final estimates
@@ -687,7 +689,7 @@ class CBREE(Solver):
                 warn(str(e))
             return False
         if not self.save_history and len(cache_list) > self.observation_window:
-            cache_list.pop(0)
+            self._retire(cache_list.pop(0))
         self._convergence_check(cache_list)
         if self.callback is not None:
             try:
@@ -702,6 +704,15 @@ class CBREE(Solver):
         if self.verbose:
             self._print_row(self._table, cache_list)
         return True
+
+    def _retire(self, cache: CBREECache):
+        """A cache left the observation window: its HBM buffers go back to the engine's free list unless somebody
+        else (a callback, the caller) still holds the cache."""
+        import sys
+
+        if sys.getrefcount(cache) <= 3 and not self.callback:  # this frame's arg + local + getrefcount's own
+            dev, cache._dev = cache._dev, None
+            self._eng.release(dev)
 
     def finish(self, cache_list: list) -> Solution:
         """solver.py:468-503: exit message, importance sampling of the retained caches, Solution."""

@@ -192,7 +192,7 @@ def test_philox_normal_matches_restatement_and_is_rank_invariant(eng):
     for j in range(d):
         pair, slot = (j // 8) * 4 + (j % 4), (j // 4) % 2
         z = philox_oracle(seed, np.arange(n), pair, draw)[slot]
-        np.testing.assert_allclose(Z[:, j], z, rtol=0, atol=5e-15)
+        np.testing.assert_allclose(Z[:, j], z, rtol=0, atol=2e-14)
     # shifting the first particle reproduces the same global stream (sharding invariance)
     Zs = eng.download(eng.philox_normal(1000, d, seed, draw, first=3000))
     np.testing.assert_array_equal(Zs, Z[3000:4000])
