@@ -17,7 +17,6 @@
 
 #include "common.cuh"
 
-#define MT 256          // threads per CTA (8 warps), one CTA per SM
 #define MAXM_MAX 8      // macro tiles (2x2 tiles of 8x8) per warp, upper bound of the plan table
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -28,8 +27,8 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 // which macro tiles (mr >= mc) of the lower triangle each warp of a k-split group accumulates
 struct GramPlan {
-    int nmac[8];
-    unsigned short mac[8][MAXM_MAX];  // mr | mc << 8
+    int nmac[16];
+    unsigned short mac[16][MAXM_MAX];  // mr | mc << 8
 };
 
 struct MmaArgs {
@@ -101,7 +100,7 @@ __device__ __forceinline__ void dmma_if(double& c0, double& c1, double a, double
         : "d"(a), "d"(b), "r"(on));
 }
 
-template <int NTB>
+template <int NTB, int MT>
 __device__ __forceinline__ void pack_matrix(double* Lf, const double* __restrict__ A, int d) {
     // fragment order with a compile-time stride: tile (mt, kk) -> 32 consecutive doubles at (mt*2*NTB + kk)*32,
     // lane l holds A[8mt + l/4][4kk + l%4]
@@ -116,31 +115,35 @@ __device__ __forceinline__ void pack_matrix(double* Lf, const double* __restrict
 
 // C[mt][pt] += A(mt, 2q..2q+1) * B(q)[pt] for all k-pairs q; B fragments come from `gen` (Philox / global loads),
 // generated one k-pair ahead so that their instruction stream interleaves with the DMMAs of the current pair.
-template <int NTB, int NPT, class Gen>
-__device__ __forceinline__ void transform_tiles(uint32_t lf_lane_addr, int ntd, int tri, Gen& gen,
-                                                double (&c)[NTB][NPT][2]) {
+// The q loop is fully unrolled: with TRI (lower-triangular A) the zero tiles mt < q vanish at compile time --
+// a predicated-off DMMA still occupies the fp64 tensor pipe, so skipping has to be structural.
+template <int NTB, int NPT, bool TRI, bool EXACT, int LA, class Gen>
+__device__ __forceinline__ void transform_tiles(uint32_t lf_lane_addr, int ntd, Gen& gen, double (&c)[NTB][NPT][2]) {
     constexpr int KT2B = 2 * NTB;
-    double nb0[NPT], nb1[NPT];
-    gen(0, nb0, nb1);
-#pragma unroll 1
-    for (int q = 0; q < ntd; ++q) {
-        double b0[NPT], b1[NPT];
+    double pb0[LA][NPT], pb1[LA][NPT];  // B fragments of the next LA k-pairs (in flight)
 #pragma unroll
-        for (int pt = 0; pt < NPT; ++pt) {
-            b0[pt] = nb0[pt];
-            b1[pt] = nb1[pt];
-        }
-        gen(q + 1, nb0, nb1);
-        const uint32_t col = lf_lane_addr + (uint32_t)q * 512u;  // tile (0, 2q)
+    for (int l = 0; l < LA; ++l) gen(l, pb0[l], pb1[l]);
 #pragma unroll
-        for (int mt = 0; mt < NTB; ++mt) {
-            const int on = (mt < ntd && (!tri || mt >= q)) ? 1 : 0;
-            const double a0 = lds64(col + mt * KT2B * 256);
-            const double a1 = lds64(col + mt * KT2B * 256 + 256);
+    for (int q = 0; q < NTB; ++q) {
+        if (EXACT || q < ntd) {  // EXACT (ntd == NTB): no guards, one straight-line block
+            double b0[NPT], b1[NPT];
 #pragma unroll
             for (int pt = 0; pt < NPT; ++pt) {
-                dmma_if(c[mt][pt][0], c[mt][pt][1], a0, b0[pt], on);
-                dmma_if(c[mt][pt][0], c[mt][pt][1], a1, b1[pt], on);
+                b0[pt] = pb0[q % LA][pt];
+                b1[pt] = pb1[q % LA][pt];
+            }
+            if (q + LA < NTB) gen(q + LA, pb0[q % LA], pb1[q % LA]);
+#pragma unroll
+            for (int mt = (TRI ? q : 0); mt < NTB; ++mt) {
+                if (EXACT || mt < ntd) {
+                    const double a0 = lds64(lf_lane_addr + (mt * KT2B + 2 * q) * 256);
+                    const double a1 = lds64(lf_lane_addr + (mt * KT2B + 2 * q + 1) * 256);
+#pragma unroll
+                    for (int pt = 0; pt < NPT; ++pt) {
+                        dmma(c[mt][pt][0], c[mt][pt][1], a0, b0[pt]);
+                        dmma(c[mt][pt][0], c[mt][pt][1], a1, b1[pt]);
+                    }
+                }
             }
         }
     }
@@ -167,27 +170,51 @@ __device__ __forceinline__ void gram_setup(const GramPlan& plan, int wi, int nta
     }
 }
 
-// accumulate the Gram of the k-pairs [u_lo, u_hi) of the shared tile into the warp's macro tiles.  Loads are
-// unconditional (the tile is padded with zero rows to full macro tiles), DMMAs are predicated.
+// accumulate the Gram of the k-pairs [u_lo, u_hi) of the shared tile into the warp's macro tiles.  The macro type
+// (full 2x2, diagonal, single row, single tile) selects one of four straight-line blocks through warp-uniform
+// branches; no DMMA is issued for tiles outside the lower triangle.
 template <int MAXM, int S>
 __device__ __forceinline__ void gram_accumulate(const GramRegs (&gr)[MAXM], int u_lo, int u_hi,
                                                 double (&acc)[MAXM][4][2]) {
-#pragma unroll 2
+#pragma unroll 1
     for (int u = u_lo; u < u_hi; ++u) {
 #pragma unroll
         for (int m = 0; m < MAXM; ++m) {
             const int f = gr[m].flags;
+            if (f == 0) continue;
             const uint32_t ra = gr[m].addrR + (uint32_t)u * 64u, ca = gr[m].addrC + (uint32_t)u * 64u;
-            const double2 a0 = lds128(ra), a1 = lds128(ra + 8 * S * 8);
-            const double2 b0 = lds128(ca), b1 = lds128(ca + 8 * S * 8);
-            dmma_if(acc[m][0][0], acc[m][0][1], a0.x, b0.x, f & 1);
-            dmma_if(acc[m][0][0], acc[m][0][1], a0.y, b0.y, f & 1);
-            dmma_if(acc[m][1][0], acc[m][1][1], a0.x, b1.x, f & 2);
-            dmma_if(acc[m][1][0], acc[m][1][1], a0.y, b1.y, f & 2);
-            dmma_if(acc[m][2][0], acc[m][2][1], a1.x, b0.x, f & 4);
-            dmma_if(acc[m][2][0], acc[m][2][1], a1.y, b0.y, f & 4);
-            dmma_if(acc[m][3][0], acc[m][3][1], a1.x, b1.x, f & 8);
-            dmma_if(acc[m][3][0], acc[m][3][1], a1.y, b1.y, f & 8);
+            if (f == 15) {  // off-diagonal 2x2
+                const double2 a0 = lds128(ra), a1 = lds128(ra + 8 * S * 8);
+                const double2 b0 = lds128(ca), b1 = lds128(ca + 8 * S * 8);
+                dmma(acc[m][0][0], acc[m][0][1], a0.x, b0.x);
+                dmma(acc[m][1][0], acc[m][1][1], a0.x, b1.x);
+                dmma(acc[m][2][0], acc[m][2][1], a1.x, b0.x);
+                dmma(acc[m][3][0], acc[m][3][1], a1.x, b1.x);
+                dmma(acc[m][0][0], acc[m][0][1], a0.y, b0.y);
+                dmma(acc[m][1][0], acc[m][1][1], a0.y, b1.y);
+                dmma(acc[m][2][0], acc[m][2][1], a1.y, b0.y);
+                dmma(acc[m][3][0], acc[m][3][1], a1.y, b1.y);
+            } else if (f == 13) {  // diagonal 2x2: tiles (0,0), (1,0), (1,1); B fragments are the A fragments
+                const double2 a0 = lds128(ra), a1 = lds128(ra + 8 * S * 8);
+                dmma(acc[m][0][0], acc[m][0][1], a0.x, a0.x);
+                dmma(acc[m][2][0], acc[m][2][1], a1.x, a0.x);
+                dmma(acc[m][3][0], acc[m][3][1], a1.x, a1.x);
+                dmma(acc[m][0][0], acc[m][0][1], a0.y, a0.y);
+                dmma(acc[m][2][0], acc[m][2][1], a1.y, a0.y);
+                dmma(acc[m][3][0], acc[m][3][1], a1.y, a1.y);
+            } else if (f == 3) {  // one row tile, two column tiles
+                const double2 a0 = lds128(ra);
+                const double2 b0 = lds128(ca), b1 = lds128(ca + 8 * S * 8);
+                dmma(acc[m][0][0], acc[m][0][1], a0.x, b0.x);
+                dmma(acc[m][1][0], acc[m][1][1], a0.x, b1.x);
+                dmma(acc[m][0][0], acc[m][0][1], a0.y, b0.y);
+                dmma(acc[m][1][0], acc[m][1][1], a0.y, b1.y);
+            } else {  // f == 1: single tile (last diagonal tile, or a lone off-diagonal tile)
+                const double2 a0 = lds128(ra);
+                const double2 b0 = lds128(ca);
+                dmma(acc[m][0][0], acc[m][0][1], a0.x, b0.x);
+                dmma(acc[m][0][0], acc[m][0][1], a0.y, b0.y);
+            }
         }
     }
 }
@@ -250,9 +277,10 @@ struct GenGlobal {  // rows 8q+lc and 8q+4+lc of an SoA array at this lane's par
 // ---------------------------------------------------------------------------------------
 // sweep 1
 // ---------------------------------------------------------------------------------------
-template <int NTB, int NPT, int MAXM, int KS>
-__global__ void __launch_bounds__(MT, 1) k_step_mma(const MmaArgs a) {
-    constexpr int P = 8 * NPT * 8;                // particles per CTA tile
+template <int NTB, int NW, int NPT, int MAXM, int KS, bool EXACT>
+__global__ void __launch_bounds__(NW * 32, 1) k_step_mma(const MmaArgs a) {
+    constexpr int MT = NW * 32;
+    constexpr int P = NW * NPT * 8;               // particles per CTA tile
     constexpr int S = P + 8;                      // row stride of the shared tile (8 mod 16 doubles)
     constexpr int ROWS = 16 * ((NTB + 1) / 2);    // tile rows padded to full macro tiles
     extern __shared__ double sm[];
@@ -265,7 +293,7 @@ __global__ void __launch_bounds__(MT, 1) k_step_mma(const MmaArgs a) {
     __shared__ double red[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lc = lane & 3;
 
-    pack_matrix<NTB>(Lf, a.A, d);
+    pack_matrix<NTB, MT>(Lf, a.A, d);
     for (int j = tid; j < 8 * NTB; j += MT) {
         vm[j] = (j < d) ? a.m_noise[j] : 0.0;
         vs[j] = (j < d && a.shift) ? a.shift[j] : 0.0;
@@ -273,7 +301,7 @@ __global__ void __launch_bounds__(MT, 1) k_step_mma(const MmaArgs a) {
     }
     for (int idx = tid; idx < ROWS * S; idx += MT) Ys[idx] = 0.0;
 
-    constexpr int WG = 8 / KS;
+    constexpr int WG = NW / KS;
     const int grp = warp / WG, wi = warp % WG;
     const uint32_t ys_addr = smem_u32(Ys);
     const uint32_t lf_lane = smem_u32(Lf) + lane * 8;
@@ -324,13 +352,13 @@ __global__ void __launch_bounds__(MT, 1) k_step_mma(const MmaArgs a) {
                 gen.base[pt] = (ip < a.n) ? a.z + (int64_t)lc * a.ld + ip : nullptr;
             }
             gen.mean = nullptr; gen.ld = a.ld; gen.d = d; gen.lc = lc;
-            transform_tiles<NTB, NPT>(lf_lane, ntd, a.tri, gen, c);
+            transform_tiles<NTB, NPT, false, EXACT, 2>(lf_lane, ntd, gen, c);  // injected noise: dense parity factor
         } else {
             GenPhilox<NPT> gen;
             gen.seed = a.seed; gen.draw = a.draw; gen.lc = (uint32_t)lc;
 #pragma unroll
             for (int pt = 0; pt < NPT; ++pt) gen.particle[pt] = (uint64_t)(a.first + i0 + pw + 8 * pt + lr);
-            transform_tiles<NTB, NPT>(lf_lane, ntd, a.tri, gen, c);
+            transform_tiles<NTB, NPT, true, EXACT, 1>(lf_lane, ntd, gen, c);  // Philox noise: Cholesky factor
         }
         cp_async_wait_all();
         // ---- epilogue: x' = t x + (m + F z), store, energy / affine LSF partials, y -> shared tile ----
@@ -339,7 +367,7 @@ __global__ void __launch_bounds__(MT, 1) k_step_mma(const MmaArgs a) {
         for (int pt = 0; pt < NPT; ++pt) se[pt][0] = se[pt][1] = sg[pt][0] = sg[pt][1] = 0.0;
 #pragma unroll
         for (int mt = 0; mt < NTB; ++mt) {
-            if (mt < ntd) {
+            if (EXACT || mt < ntd) {
                 const int row = 8 * mt + lr;
                 const bool rv = row < d;
                 const double mrow = vm[row], srow = vs[row], crow = vc[row];
@@ -418,10 +446,14 @@ __global__ void __launch_bounds__(MT, 1) k_step_mma(const MmaArgs a) {
 
 // ---------------------------------------------------------------------------------------
 // sweep 2 (and, with wmax == NULL, the plain shifted moments of an existing ensemble)
+// Same tile pipeline as sweep 1: every lane prefetches (cp.async) exactly the elements it will rescale, the
+// transform takes its B fragments straight from global / L2 (two k-pairs ahead), the accumulator fragments give
+// q = |Linv (x - mean)|^2, and the lane rewrites its elements as (x - mean) sqrt(w) for the weighted Gram.
 // ---------------------------------------------------------------------------------------
-template <int NTB, int NPT, int MAXM, int KS>
-__global__ void __launch_bounds__(MT, 1) k_maha_mma(const MmaArgs a) {
-    constexpr int P = 8 * NPT * 8;
+template <int NTB, int NW, int NPT, int MAXM, int KS, bool EXACT>
+__global__ void __launch_bounds__(NW * 32, 1) k_maha_mma(const MmaArgs a) {
+    constexpr int MT = NW * 32;
+    constexpr int P = NW * NPT * 8;
     constexpr int S = P + 8;
     constexpr int ROWS = 16 * ((NTB + 1) / 2);
     extern __shared__ double sm[];
@@ -429,16 +461,15 @@ __global__ void __launch_bounds__(MT, 1) k_maha_mma(const MmaArgs a) {
     double* Lf = sm;
     double* Ys = Lf + NTB * 2 * NTB * 32;
     double* vm = Ys + ROWS * S;  // mean
-    double* sw = vm + 8 * NTB;   // per particle of the tile: |u|^2, then sqrt(w)   [P]
     __shared__ ExpSums sh[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lc = lane & 3;
     const bool weighted = a.wmax != nullptr;  // false: plain moments (no Linv, no IS)
 
-    pack_matrix<NTB>(Lf, weighted ? a.A : nullptr, d);
+    pack_matrix<NTB, MT>(Lf, weighted ? a.A : nullptr, d);
     for (int j = tid; j < 8 * NTB; j += MT) vm[j] = (j < d && a.mean) ? a.mean[j] : 0.0;
     for (int idx = tid; idx < ROWS * S; idx += MT) Ys[idx] = 0.0;
 
-    constexpr int WG = 8 / KS;
+    constexpr int WG = NW / KS;
     const int grp = warp / WG, wi = warp % WG;
     const uint32_t ys_addr = smem_u32(Ys);
     const uint32_t lf_lane = smem_u32(Lf) + lane * 8;
@@ -459,14 +490,25 @@ __global__ void __launch_bounds__(MT, 1) k_maha_mma(const MmaArgs a) {
     const double wmax = weighted ? a.wmax[0] : 0.0;
     const double lq_const = (double)d * REE_LOG_2PI + logdet;
     const int64_t ntiles = (a.n + P - 1) / P;
+    const uint32_t own_addr = ys_addr + (uint32_t)((lr * S + pw + 2 * lc) * 8);
+
+    auto prefetch = [&](int64_t i0) {
+#pragma unroll
+        for (int mt = 0; mt < NTB; ++mt) {
+            const int row = 8 * mt + lr;
+#pragma unroll
+            for (int pt = 0; pt < NPT; ++pt) {
+                const int64_t ip = i0 + pw + 8 * pt + 2 * lc;
+                if (row < d && ip < a.ld)
+                    cp_async16(own_addr + (uint32_t)((8 * mt * S + 8 * pt) * 8), a.x + (int64_t)row * a.ld + ip);
+            }
+        }
+    };
+    if ((int64_t)blockIdx.x < ntiles) prefetch((int64_t)blockIdx.x * P);
+
     for (int64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
         const int64_t i0 = tix * P;
-        // ---- raw tile -> shared memory with cp.async (16-byte chunks along the particle axis) ------
-        for (int idx = tid; idx < d * (P / 2); idx += MT) {
-            const int j = idx / (P / 2), p2 = (idx - j * (P / 2)) * 2;
-            const int64_t ip = i0 + p2;
-            if (ip < a.ld) cp_async16(ys_addr + (uint32_t)((j * S + p2) * 8), a.x + (int64_t)j * a.ld + ip);
-        }
+        double swc[NPT][2];  // sqrt(w) of this lane's particle columns (1 / 0 for plain moments)
         if (weighted) {
             // ---- u = Linv (x - mean) on the tensor pipe; B fragments straight from global / L2 ----------
             double c[NTB][NPT][2];
@@ -481,8 +523,8 @@ __global__ void __launch_bounds__(MT, 1) k_maha_mma(const MmaArgs a) {
                 gen.base[pt] = (ip < a.n) ? a.x + (int64_t)lc * a.ld + ip : nullptr;
             }
             gen.mean = vm; gen.ld = a.ld; gen.d = d; gen.lc = lc;
-            transform_tiles<NTB, NPT>(lf_lane, ntd, a.tri, gen, c);
-            // ---- q = |u|^2 per particle -> this warp's slice of sw ----------------------------------
+            transform_tiles<NTB, NPT, true, EXACT, 2>(lf_lane, ntd, gen, c);  // Linv is lower triangular
+            // ---- q = |u|^2, log q, IS statistics, weight (solver.py:629-632, 683-686) ---------------------
 #pragma unroll
             for (int pt = 0; pt < NPT; ++pt) {
 #pragma unroll
@@ -492,54 +534,64 @@ __global__ void __launch_bounds__(MT, 1) k_maha_mma(const MmaArgs a) {
                     for (int mt = 0; mt < NTB; ++mt) qq = fma(c[mt][pt][h], c[mt][pt][h], qq);
 #pragma unroll
                     for (int o = 4; o < 32; o <<= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
-                    if (lr == 0) sw[pw + 8 * pt + 2 * lc + h] = qq;
+                    const int64_t ip = i0 + pw + 8 * pt + 2 * lc + h;
+                    double swv = 0.0;
+                    if (lr == 0 && ip < a.n) {
+                        const double lq = -0.5 * (lq_const + qq);
+                        if (a.logq) a.logq[ip] = lq;
+                        const double gi = a.g[ip], ei = a.e[ip];
+                        const double r = __dsub_rn(-ei, lq);  // -e_fun - log_pdf  (solver.py:684)
+                        if (isfinite(r)) expsums_add(is_acc, r, gi <= 0.0 ? 1.0 : 0.0);
+                        const double al = __dmul_rn(ree_logtgt(gi, ei, a.sigma, a.tgt_kind), a.beta);
+                        const double wv = isfinite(al) ? exp(al - wmax) : 0.0;
+                        if (a.w_out) a.w_out[ip] = wv;
+                        swv = sqrt(wv);
+                    }
+                    swc[pt][h] = __shfl_sync(0xffffffffu, swv, lc);  // lane lc (lr == 0) owns this column pair
                 }
-            }
-            __syncwarp();
-            // ---- one lane per particle: log q, IS statistics, weight (solver.py:629-632, 683-686) -------
-            if (lane < 8 * NPT) {
-                const int p = pw + lane;
-                const int64_t ip = i0 + p;
-                double swv = 0.0;
-                if (ip < a.n) {
-                    const double lq = -0.5 * (lq_const + sw[p]);
-                    if (a.logq) a.logq[ip] = lq;
-                    const double gi = a.g[ip], ei = a.e[ip];
-                    const double r = __dsub_rn(-ei, lq);  // -e_fun - log_pdf  (solver.py:684)
-                    if (isfinite(r)) expsums_add(is_acc, r, gi <= 0.0 ? 1.0 : 0.0);
-                    const double al = __dmul_rn(ree_logtgt(gi, ei, a.sigma, a.tgt_kind), a.beta);
-                    const double wv = isfinite(al) ? exp(al - wmax) : 0.0;
-                    if (a.w_out) a.w_out[ip] = wv;
-                    swv = sqrt(wv);
-                }
-                sw[p] = swv;
             }
         } else {
-            for (int p = tid; p < P; p += MT) {
-                const int64_t ip = i0 + p;
-                sw[p] = (ip < a.n) ? 1.0 : 0.0;
-                if (a.g && ip < a.n) n_fail += (a.g[ip] <= 0.0) ? 1.0 : 0.0;
+#pragma unroll
+            for (int pt = 0; pt < NPT; ++pt) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t ip = i0 + pw + 8 * pt + 2 * lc + h;
+                    swc[pt][h] = (ip < a.n) ? 1.0 : 0.0;
+                    if (lr == 0 && a.g && ip < a.n) n_fail += (a.g[ip] <= 0.0) ? 1.0 : 0.0;
+                }
             }
         }
         cp_async_wait_all();
-        __syncthreads();
-        // ---- centre and scale the tile by sqrt(w) in place; augmented row = sqrt(w) => sum w y, sum w ----
-        for (int idx = tid; idx < (d + 1) * (P / 2); idx += MT) {
-            const int j = idx / (P / 2), p2 = (idx - j * (P / 2)) * 2;
-            const uint32_t sa = ys_addr + (uint32_t)((j * S + p2) * 8);
-            const double2 s2 = *reinterpret_cast<const double2*>(sw + p2);
-            double2 v = s2;
-            if (j < d) {
-                const double2 xv = lds128(sa);
-                const double mj = vm[j];
-                v.x = (s2.x != 0.0) ? (xv.x - mj) * s2.x : 0.0;  // select, not multiply: stale/padded lanes
-                v.y = (s2.y != 0.0) ? (xv.y - mj) * s2.y : 0.0;
+        // ---- this lane's elements: (x - mean) sqrt(w); augmented row = sqrt(w) => sum w y, sum w ----------
+#pragma unroll
+        for (int mt = 0; mt < NTB; ++mt) {
+            if (EXACT || mt < ntd) {
+                const int row = 8 * mt + lr;
+                const double mrow = vm[row];
+#pragma unroll
+                for (int pt = 0; pt < NPT; ++pt) {
+                    const uint32_t sa = own_addr + (uint32_t)((8 * mt * S + 8 * pt) * 8);
+                    const double2 xv = lds128(sa);
+                    double2 y;  // select, not multiply: padded / stale lanes may hold anything
+                    y.x = (row < d && swc[pt][0] != 0.0) ? (xv.x - mrow) * swc[pt][0] : 0.0;
+                    y.y = (row < d && swc[pt][1] != 0.0) ? (xv.y - mrow) * swc[pt][1] : 0.0;
+                    if (row == d) {
+                        y.x = swc[pt][0];
+                        y.y = swc[pt][1];
+                    }
+                    sts128(sa, y);
+                }
             }
-            sts128(sa, v);
+        }
+        if (nta > ntd && lr == 0) {
+#pragma unroll
+            for (int pt = 0; pt < NPT; ++pt)
+                sts128(ys_addr + (uint32_t)((d * S + pw + 8 * pt + 2 * lc) * 8), make_double2(swc[pt][0], swc[pt][1]));
         }
         __syncthreads();
         gram_accumulate<MAXM, S>(gr, grp * (P / 8 / KS), (grp + 1) * (P / 8 / KS), acc);
         __syncthreads();
+        if (tix + gridDim.x < ntiles) prefetch((tix + gridDim.x) * P);
     }
     const int T = nta * (nta + 1) / 2;
     gram_store<MAXM>(a.partials + ((size_t)blockIdx.x * KS + grp) * T * 64, a.plan, wi, nmac, nta, lr, lc, acc);
@@ -627,8 +679,8 @@ static void make_plan(GramPlan& plan, int nta, int warps_per_group, int maxm) {
         for (int j = i; j > 0 && items[j].w > items[j - 1].w; --j) {
             Item t = items[j]; items[j] = items[j - 1]; items[j - 1] = t;
         }
-    int load[8] = {0};
-    for (int w = 0; w < 8; ++w) plan.nmac[w] = 0;
+    int load[16] = {0};
+    for (int w = 0; w < 16; ++w) plan.nmac[w] = 0;
     for (int i = 0; i < n; ++i) {
         int best = -1;
         for (int w = 0; w < warps_per_group; ++w)
@@ -638,16 +690,26 @@ static void make_plan(GramPlan& plan, int nta, int warps_per_group, int maxm) {
     }
 }
 
+// kernel configuration per dimension bucket: NTB tile rows, NW warps, NPT particle tiles per warp,
+// MAXM Gram macro tiles per warp, KS k-split groups
 struct MmaCfg {
-    int ntb, npt, maxm, ks;
+    int ntb, nw, npt, maxm, ks;
 };
 
+static int g_nw_override = -1;
+
 static bool pick_cfg(int d, MmaCfg& c) {
-    if (d <= 15) c = {2, 2, 1, 8};
-    else if (d <= 31) c = {4, 2, 2, 4};
-    else if (d <= 55) c = {7, 2, 3, 2};
-    else if (d <= 103) c = {13, 2, 4, 1};
-    else return false;
+    if (g_nw_override < 0) {
+        const char* e = getenv("REE_MMA_WARPS");  // tuning hook: 8 or 16 warps per CTA for the d <= 103 bucket
+        g_nw_override = e ? atoi(e) : 0;
+    }
+    if (d <= 15) c = {2, 8, 2, 1, 8};
+    else if (d <= 31) c = {4, 8, 2, 2, 4};
+    else if (d <= 55) c = {7, 8, 2, 3, 2};
+    else if (d <= 103) {
+        c = {13, 16, 1, 2, 1};
+        if (g_nw_override == 8) c = {13, 8, 2, 4, 1};
+    } else return false;
     return true;
 }
 
@@ -666,11 +728,10 @@ bool ree_mma_supported(int d) {
 
 extern "C" int ree_fused_path(int d) { return ree_mma_supported(d) ? 1 : 0; }
 
-static size_t mma_smem_bytes(int d, const MmaCfg& c, bool sweep2) {
-    (void)d;
-    int P = 8 * c.npt * 8, S = P + 8;
+static size_t mma_smem_bytes(const MmaCfg& c, bool sweep2) {
+    int P = c.nw * c.npt * 8, S = P + 8;
     int rows = 16 * ((c.ntb + 1) / 2);
-    size_t n = (size_t)c.ntb * 2 * c.ntb * 32 + (size_t)rows * S + (sweep2 ? (8 * c.ntb + P) : 3 * 8 * c.ntb);
+    size_t n = (size_t)c.ntb * 2 * c.ntb * 32 + (size_t)rows * S + (sweep2 ? 8 * c.ntb : 3 * 8 * c.ntb);
     return n * sizeof(double);
 }
 
@@ -681,16 +742,25 @@ size_t ree_mma_partial_doubles(int d) {
     return (size_t)ree_grid_ctas() * c.ks * T * 64;
 }
 
-template <int NTB, int NPT, int MAXM, int KS>
-static int launch_cfg(bool sweep2, const MmaArgs& a, int grid, size_t smem, cudaStream_t st) {
+template <int NTB, int NW, int NPT, int MAXM, int KS, bool EXACT>
+static int launch_one(bool sweep2, const MmaArgs& a, int grid, size_t smem, cudaStream_t st) {
     if (sweep2) {
-        cudaFuncSetAttribute(k_maha_mma<NTB, NPT, MAXM, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_maha_mma<NTB, NPT, MAXM, KS><<<grid, MT, smem, st>>>(a);
+        cudaFuncSetAttribute(k_maha_mma<NTB, NW, NPT, MAXM, KS, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
+        k_maha_mma<NTB, NW, NPT, MAXM, KS, EXACT><<<grid, NW * 32, smem, st>>>(a);
     } else {
-        cudaFuncSetAttribute(k_step_mma<NTB, NPT, MAXM, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_step_mma<NTB, NPT, MAXM, KS><<<grid, MT, smem, st>>>(a);
+        cudaFuncSetAttribute(k_step_mma<NTB, NW, NPT, MAXM, KS, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
+        k_step_mma<NTB, NW, NPT, MAXM, KS, EXACT><<<grid, NW * 32, smem, st>>>(a);
     }
     return ree_check_launch(sweep2 ? "k_maha_mma" : "k_step_mma");
+}
+
+template <int NTB, int NW, int NPT, int MAXM, int KS>
+static int launch_cfg(bool sweep2, const MmaArgs& a, int grid, size_t smem, cudaStream_t st) {
+    // guard-free instantiation when the dimension fills the bucket (d = 100 -> 13 tiles)
+    if ((a.d + 7) / 8 == NTB) return launch_one<NTB, NW, NPT, MAXM, KS, true>(sweep2, a, grid, smem, st);
+    return launch_one<NTB, NW, NPT, MAXM, KS, false>(sweep2, a, grid, smem, st);
 }
 
 // Runs one sweep and the second-stage reductions.  small_out: sweep 1 -> sums tail [count], sweep 2 -> is4.
@@ -698,19 +768,20 @@ int ree_mma_sweep(bool sweep2, MmaArgs& a, double* workspace_big, double* worksp
                   cudaStream_t st) {
     MmaCfg c;
     if (!pick_cfg(a.d, c)) return ree_set_error(REE_E_UNSUPPORTED, "mma path: d > 103");
-    const int d = a.d, nta = (d + 8) / 8, P = 8 * c.npt * 8;
+    const int d = a.d, nta = (d + 8) / 8, P = c.nw * c.npt * 8;
     int sms = ree_grid_ctas() / 2;  // persistent: one CTA per SM
     int64_t ntiles = (a.n + P - 1) / P;
     int grid = (int)(ntiles < sms ? ntiles : sms);
-    make_plan(a.plan, nta, 8 / c.ks, c.maxm);
+    make_plan(a.plan, nta, c.nw / c.ks, c.maxm);
     a.partials = workspace_big;
     a.small = workspace_small;
-    size_t smem = mma_smem_bytes(d, c, sweep2);
+    size_t smem = mma_smem_bytes(c, sweep2);
     int rc;
-    if (c.ntb == 2) rc = launch_cfg<2, 2, 1, 8>(sweep2, a, grid, smem, st);
-    else if (c.ntb == 4) rc = launch_cfg<4, 2, 2, 4>(sweep2, a, grid, smem, st);
-    else if (c.ntb == 7) rc = launch_cfg<7, 2, 3, 2>(sweep2, a, grid, smem, st);
-    else rc = launch_cfg<13, 2, 4, 1>(sweep2, a, grid, smem, st);
+    if (c.ntb == 2) rc = launch_cfg<2, 8, 2, 1, 8>(sweep2, a, grid, smem, st);
+    else if (c.ntb == 4) rc = launch_cfg<4, 8, 2, 2, 4>(sweep2, a, grid, smem, st);
+    else if (c.ntb == 7) rc = launch_cfg<7, 8, 2, 3, 2>(sweep2, a, grid, smem, st);
+    else if (c.nw == 16) rc = launch_cfg<13, 16, 1, 2, 1>(sweep2, a, grid, smem, st);
+    else rc = launch_cfg<13, 8, 2, 4, 1>(sweep2, a, grid, smem, st);
     if (rc) return rc;
     const int D1 = d + 1;
     k_unpack_gram<<<(D1 * D1 + 255) / 256, 256, 0, st>>>(workspace_big, grid * c.ks, d, nta, (sweep2 && a.wmax) ? 1 : 0, sums);
