@@ -170,42 +170,59 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k
 }
 
 // ---------------------------------------------------------------------------------------
-// Branch-free fp64 Box-Muller.  The uniforms are 53-bit integers, so the arguments of log / sincospi are
-// known to be normal numbers in a fixed range: no special cases, no slow paths -- straight-line code that the
-// scheduler can interleave with DMMA issue.  Accuracy (checked against long double on 2e6 inputs): log <= 3.2 ulp,
-// sqrt <= 1.5 ulp, sin/cos <= 1.8e-16 absolute.
+// Table-driven, branch-free fp64 Box-Muller.
+// DMMA and DFMA share one fp64 pipe on B200 (tools/fp64_pipe_share.cu), so every fp64 instruction spent on noise is
+// taken from the tensor work: the transcendental parts use small tables (bm_tables.cuh, 4 KB) + short polynomials
+// (~38 fp64 instructions per pair instead of ~190 for log/sqrt/sincospi of libdevice).  The uniforms are 53-bit
+// integers, so all arguments are normal numbers in fixed ranges: no special cases, no slow paths.
+// Accuracy (vs long double, 3e6 inputs): ln <= 4.2 ulp, sqrt <= 1.5 ulp, sin/cos <= 1.1e-16 absolute.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double bm_neg2log(uint64_t k53) {
-    // -2*ln(u), u = (k53+1)*2^-53 in (0,1]
+#include "bm_tables.cuh"
+
+struct BmTableGlobal {  // tables read through the read-only path (modular kernels)
+    __device__ __forceinline__ double2 log_entry(int i) const {
+        return make_double2(__ldg(BM_TABLE + 2 * i), __ldg(BM_TABLE + 2 * i + 1));
+    }
+    __device__ __forceinline__ double2 trig_entry(int j) const {
+        return make_double2(__ldg(BM_TABLE + 258 + 2 * j), __ldg(BM_TABLE + 258 + 2 * j + 1));
+    }
+};
+
+struct BmTableShared {  // tables staged in shared memory (fused sweep kernel); addr = 32-bit shared address
+    uint32_t addr;
+    __device__ __forceinline__ double2 log_entry(int i) const {
+        double2 v;
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr + 16u * (uint32_t)i));
+        return v;
+    }
+    __device__ __forceinline__ double2 trig_entry(int j) const {
+        double2 v;
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr + 2064u + 16u * (uint32_t)j));
+        return v;
+    }
+};
+
+template <class Tab>
+__device__ __forceinline__ double bm_neg2log(uint64_t k53, const Tab& tab) {
+    // -2*ln(u), u = (k53+1)*2^-53 in (0,1]:  x = k53+1 = 2^e * m, m in [1,2), i = round((m-1)*128),
+    // m = (1/inv_i)(1 + r) with r = m*inv_i - 1 (one fma, |r| <= 2^-8)  =>  ln m = T_i + log1p(r)
     const double x = (double)(long long)(k53 + 1);  // exact, in [1, 2^53]
     const long long bits = __double_as_longlong(x);
-    int e = (int)(bits >> 52) - (1023 + 53);
-    double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);  // [1,2)
-    const bool big = m > 1.4142135623730951;
-    m = big ? m * 0.5 : m;
-    e = big ? e + 1 : e;
-    const double f = m - 1.0;   // exact
-    const double y = 2.0 + f;   // [1.7, 2.42]
-    double r = (double)__frcp_rn((float)y);
-    r = r * fma(-y, r, 2.0);
-    r = r * fma(-y, r, 2.0);
-    double s = f * r;
-    s = fma(r, fma(-s, y, f), s);  // s = f / y
-    const double s2 = s * s;
-    double p = 2.0 / 21.0;
-    p = fma(p, s2, 2.0 / 19.0);
-    p = fma(p, s2, 2.0 / 17.0);
-    p = fma(p, s2, 2.0 / 15.0);
-    p = fma(p, s2, 2.0 / 13.0);
-    p = fma(p, s2, 2.0 / 11.0);
-    p = fma(p, s2, 2.0 / 9.0);
-    p = fma(p, s2, 2.0 / 7.0);
-    p = fma(p, s2, 2.0 / 5.0);
-    p = fma(p, s2, 2.0 / 3.0);
-    p = p * s2;
-    const double logm = fma(s, p, s + s);  // 2 atanh(s)
+    const long long mant = bits & 0x000fffffffffffffLL;
+    const int i = (int)(((mant >> 44) + 1) >> 1);
+    const int e = (int)(bits >> 52) - (1023 + 53) + (i >= BM_LOG_I0 ? 1 : 0);
+    const double m = __longlong_as_double(mant | 0x3ff0000000000000LL);
+    const double2 t = tab.log_entry(i);
+    const double r = fma(m, t.x, -1.0);
+    double p = -1.0 / 6.0;
+    p = fma(p, r, 0.2);
+    p = fma(p, r, -0.25);
+    p = fma(p, r, 1.0 / 3.0);
+    p = fma(p, r, -0.5);
+    p = fma(p, r, 1.0);
+    p = p * r;
     const double ed = (double)e;
-    const double ln_u = fma(ed, 0.6931471803691238, fma(ed, 1.9082149292705877e-10, logm));
+    const double ln_u = fma(ed, 0.6931471803691238, fma(ed, 1.9082149292705877e-10, t.y + p));
     return -2.0 * ln_u;
 }
 
@@ -220,54 +237,45 @@ __device__ __forceinline__ double bm_sqrt(double w) {
     return r;
 }
 
-__device__ __forceinline__ void bm_sincos2pi(uint64_t b53, double& sn, double& cs) {
-    // sin / cos of 2*pi*u, u = b53*2^-53: octant from the top 3 bits, Taylor polynomials on [0, pi/4]
-    const int o = (int)(b53 >> 50);
-    const long long r50 = (long long)(b53 & ((1ULL << 50) - 1));
-    const long long xi = (o & 1) ? ((1LL << 50) - r50) : r50;
-    const double y = (double)xi * (0.7853981633974483 * 8.8817841970012523e-16);  // * pi/4 * 2^-50
-    const double y2 = y * y;
-    double ps = -1.0 / 1307674368000.0;          // -1/15!
-    ps = fma(ps, y2, 1.0 / 6227020800.0);        // 1/13!
-    ps = fma(ps, y2, -1.0 / 39916800.0);         // -1/11!
-    ps = fma(ps, y2, 1.0 / 362880.0);            // 1/9!
-    ps = fma(ps, y2, -1.0 / 5040.0);             // -1/7!
-    ps = fma(ps, y2, 1.0 / 120.0);               // 1/5!
-    ps = fma(ps, y2, -1.0 / 6.0);                // -1/3!
-    ps = ps * y2;
-    const double S = fma(y, ps, y);
-    double pc = 1.0 / 20922789888000.0;          // 1/16!
-    pc = fma(pc, y2, -1.0 / 87178291200.0);      // -1/14!
-    pc = fma(pc, y2, 1.0 / 479001600.0);         // 1/12!
-    pc = fma(pc, y2, -1.0 / 3628800.0);          // -1/10!
-    pc = fma(pc, y2, 1.0 / 40320.0);             // 1/8!
-    pc = fma(pc, y2, -1.0 / 720.0);              // -1/6!
-    pc = fma(pc, y2, 1.0 / 24.0);                // 1/4!
-    pc = fma(pc, y2, -0.5);
-    const double C = fma(pc, y2, 1.0);
-    const int q = o & 3;
-    const bool keep = (q == 0) || (q == 3);
-    double sv = keep ? S : C;
-    double cv = keep ? C : S;
-    cv = (q >= 2) ? -cv : cv;
-    const bool neg = o >= 4;
-    sn = neg ? -sv : sv;
-    cs = neg ? -cv : cv;
+template <class Tab>
+__device__ __forceinline__ void bm_sincos2pi(uint64_t b53, const Tab& tab, double& sn, double& cs) {
+    // sin / cos of alpha = 2*pi*b53*2^-53: j = nearest 128th of the circle, theta = alpha - 2 pi j/128 in
+    // [-pi/128, pi/128], angle addition with short Taylor polynomials
+    const long long j = (long long)((b53 + (1ULL << 45)) >> 46);
+    const long long rem = (long long)b53 - (j << 46);
+    const double th = (double)rem * (6.283185307179586476925286766559 * 1.1102230246251565e-16);  // 2 pi 2^-53
+    const double t2 = th * th;
+    double ps = fma(t2, -1.0 / 5040.0, 1.0 / 120.0);
+    ps = fma(ps, t2, -1.0 / 6.0);
+    ps = fma(ps, t2, 1.0);
+    ps = ps * th;                       // sin(theta)
+    double pc = fma(t2, -1.0 / 720.0, 1.0 / 24.0);
+    pc = fma(pc, t2, -0.5);
+    pc = pc * t2;                       // cos(theta) - 1
+    const double2 sc = tab.trig_entry((int)(j & 127));
+    sn = sc.x + fma(sc.y, ps, sc.x * pc);
+    cs = sc.y + fma(-sc.x, ps, sc.y * pc);
 }
 
 // two standard normals for (particle, pair, draw)
+template <class Tab>
 __device__ __forceinline__ void philox_normal_pair(uint64_t seed, uint64_t particle, uint32_t pair, uint64_t draw,
-                                                   double& z0, double& z1) {
+                                                   const Tab& tab, double& z0, double& z1) {
     uint32_t c[4] = {(uint32_t)particle, (uint32_t)(particle >> 32), pair, (uint32_t)draw};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     // u1 = (a53+1)*2^-53 in (0,1] ; u2 = b53*2^-53 in [0,1)
     const uint64_t a53 = (((uint64_t)c[0] << 32) | c[1]) >> 11;
     const uint64_t b53 = (((uint64_t)c[2] << 32) | c[3]) >> 11;
-    const double r = bm_sqrt(bm_neg2log(a53));
+    const double r = bm_sqrt(bm_neg2log(a53, tab));
     double sn, cs;
-    bm_sincos2pi(b53, sn, cs);
+    bm_sincos2pi(b53, tab, sn, cs);
     z0 = r * cs;
     z1 = r * sn;
+}
+
+__device__ __forceinline__ void philox_normal_pair(uint64_t seed, uint64_t particle, uint32_t pair, uint64_t draw,
+                                                   double& z0, double& z1) {
+    philox_normal_pair(seed, particle, pair, draw, BmTableGlobal{}, z0, z1);
 }
 
 __host__ __device__ __forceinline__ uint32_t philox_pair_of_dim(int j) { return (uint32_t)((j >> 3) * 4 + (j & 3)); }

@@ -1,23 +1,32 @@
-// Fused DMMA kernels for the two ensemble sweeps of a CBREE iteration (d <= 103).
+// Fused DMMA kernel for the two ensemble sweeps of a CBREE iteration (d <= 103).
 //
-//   sweep 1  k_step_mma : X'^T = t X^T + m 1^T + F Z^T   (F Z^T on the fp64 tensor pipe, Z from Philox in
-//                         registers or injected), g'/e' from the accumulator fragments, X' written once,
-//                         shifted Gram  sum_i y_i y_i^T  (y = x' - shift, augmented with a row of ones so that
-//                         sum y and n fall out of the same contraction) accumulated in registers per CTA.
-//   sweep 2  k_maha_mma : y = x' - mean staged in shared memory, u = Linv y (DMMA), q = |u|^2 -> log q,
-//                         IS statistics, weights w; tile rescaled by sqrt(w) in place, weighted Gram.
+//   SWEEP 1  X'^T = t X^T + m 1^T + F Z^T   (F Z^T on the fp64 tensor pipe; Z from Philox in registers, or injected),
+//            g'/e' from the accumulator fragments, X' written once, shifted Gram  sum_i y_i y_i^T  (y = x' - shift,
+//            augmented with a row of ones so that sum y and n fall out of the same contraction).
+//   SWEEP 2  u = Linv (x' - mean) (DMMA), q = |u|^2 -> log q, IS statistics, weights w; the tile is rewritten as
+//            (x' - mean) sqrt(w) (augmented row sqrt(w)) and its Gram gives sum w y y^T, sum w y, sum w.
+//            With wmax == NULL: plain shifted moments of an existing ensemble (no transform).
 //
 // Fragment conventions of mma.sync.aligned.m8n8k4.row.col.f64 (lane = 4*lr + lc):
 //   A (8x4): a = A[lr][lc]      B (4x8): b = B[lc][lr]      C (8x8): c0,c1 = C[lr][2*lc], C[lr][2*lc+1]
 // Orientation: M = dimension, N = particle for the transforms; for the Grams M = N = dimension and K = particle.
-// Because a Gram sums over all particles, the order of particles inside a k-step is free: the pair of k-steps u
-// uses particles {8u+2*lc} and {8u+2*lc+1}, i.e. exactly the double2 a C-fragment holds -> the shared-memory tile
-// is written (st.shared.v2) and read (ld.shared.v2) with the same conflict-free pattern (row stride = 8 mod 16).
+// A Gram sums over all particles, so the order of particles inside a k-step is free: the pair of k-steps u uses
+// particles {8u+2*lc} and {8u+2*lc+1}, i.e. exactly the double2 a C-fragment holds -> the shared tile is written
+// (st.shared.v2) and read (ld.shared.v2) with the same conflict-free pattern (row stride = 8 mod 16 doubles).
+//
+// Tile pipeline (one persistent CTA per SM, NW warps, 8 particles per warp and tile, two shared tile buffers):
+//   tile k:  [B fragments: Philox | own columns of buf k]  ->  DMMA transform  ->  wait own cp.async  ->
+//            epilogue rewrites the lane's own elements of buf k  ->  __syncthreads  ->
+//            cp.async of tile k+1 into buf k+1 (every lane fetches exactly the elements it will rewrite)  ->
+//            Gram of buf k with register accumulators (2x2 macro tiles of the lower triangle, LPT plan from the host)
+// One barrier per tile; loads of tile k+1 overlap the Gram of tile k and the transform of tile k+1.
+// A predicated-off DMMA still occupies the tensor pipe, so all skipping (triangular factor, macro-tile shapes)
+// is structural: unrolled loops with compile-time bounds and warp-uniform branches.
 #include <stdlib.h>
 
 #include "common.cuh"
 
-#define MAXM_MAX 8      // macro tiles (2x2 tiles of 8x8) per warp, upper bound of the plan table
+#define MAXM_MAX 8  // macro tiles (2x2 tiles of 8x8) per warp, upper bound of the plan table
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -33,14 +42,13 @@ struct GramPlan {
 
 struct MmaArgs {
     // common
-    const double* x;     // sweep 1: X (input) ; sweep 2: X'
+    const double* x;      // sweep 1: X (input) ; sweep 2: X'
     int64_t n, ld;
     int d;
-    const double* A;     // F (sweep 1) or Linv (sweep 2), row-major d x d
-    int tri;             // A is lower triangular (skip zero tiles)
-    const double* shift; // sweep 1: Gram shift ; sweep 2: unused (the mean is the shift)
-    double* partials;    // [(cta*KS + grp)][T][64] packed Gram tiles
-    double* small;       // per-CTA scalars: sweep 1 count of g<=0 ; sweep 2 ExpSums (4 doubles)
+    const double* A;      // F (sweep 1) or Linv (sweep 2), row-major d x d
+    const double* shift;  // sweep 1: Gram shift ; sweep 2: unused (the mean is the shift)
+    double* partials;     // [(cta*KS + grp)][T][64] packed Gram tiles
+    double* small;        // per-CTA scalars: sweep 1 count of g<=0 ; sweep 2 ExpSums (4 doubles)
     GramPlan plan;
     // sweep 1
     double* x_new;
@@ -49,7 +57,7 @@ struct MmaArgs {
     const double* z;
     uint64_t seed, draw;
     int64_t first;
-    int lsf_mode;        // 0: not fused, 1: affine coef, 2: -sum(x)/sqrt(d) + offset
+    int lsf_mode;  // 0: not fused, 1: affine coef, 2: -sum(x)/sqrt(d) + offset
     const double* coef;
     double offset;
     double* g_new;
@@ -84,65 +92,54 @@ __device__ __forceinline__ double2 lds128(uint32_t a) {
 __device__ __forceinline__ void sts128(uint32_t a, double2 v) {
     asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
 }
-__device__ __forceinline__ void sts64(uint32_t a, double v) {
-    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
-}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// DMMA under a warp-uniform guard (predication instead of a branch keeps the block schedulable)
-__device__ __forceinline__ void dmma_if(double& c0, double& c1, double a, double b, int on) {
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %4, 0;\n\t"
-        "@p mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n\t}"
-        : "+d"(c0), "+d"(c1)
-        : "d"(a), "d"(b), "r"(on));
+// fragment-ordered copy of a d x d matrix: tile (mt, kk) (rows 8mt.., columns 4kk..) -> 32 consecutive doubles,
+// lane l holds A[8mt + l/4][4kk + l%4].  TRI keeps only the tiles of the lower triangle (kk <= 2mt+1).
+template <int NTB, bool TRI>
+__host__ __device__ constexpr int lf_tile(int mt, int kk) {
+    return TRI ? mt * (mt + 1) + kk : mt * 2 * NTB + kk;
+}
+template <int NTB, bool TRI>
+__host__ __device__ constexpr int lf_doubles() {
+    return (TRI ? NTB * (NTB + 1) : 2 * NTB * NTB) * 32;
 }
 
-template <int NTB, int MT>
+template <int NTB, bool TRI, int MT>
 __device__ __forceinline__ void pack_matrix(double* Lf, const double* __restrict__ A, int d) {
-    // fragment order with a compile-time stride: tile (mt, kk) -> 32 consecutive doubles at (mt*2*NTB + kk)*32,
-    // lane l holds A[8mt + l/4][4kk + l%4]
-    constexpr int KT2B = 2 * NTB;
-    for (int idx = threadIdx.x; idx < NTB * KT2B * 32; idx += MT) {
-        int l = idx & 31, tile = idx >> 5;
-        int mt = tile / KT2B, kk = tile - mt * KT2B;
-        int r = 8 * mt + (l >> 2), c = 4 * kk + (l & 3);
-        Lf[idx] = (A && r < d && c < d) ? A[(size_t)r * d + c] : 0.0;
+    for (int mt = 0; mt < NTB; ++mt) {
+        const int nk = TRI ? 2 * mt + 2 : 2 * NTB;
+        for (int idx = threadIdx.x; idx < nk * 32; idx += MT) {
+            const int kk = idx >> 5, l = idx & 31;
+            const int r = 8 * mt + (l >> 2), c = 4 * kk + (l & 3);
+            Lf[lf_tile<NTB, TRI>(mt, kk) * 32 + l] = (A && r < d && c < d) ? A[(size_t)r * d + c] : 0.0;
+        }
     }
 }
 
-// C[mt][pt] += A(mt, 2q..2q+1) * B(q)[pt] for all k-pairs q; B fragments come from `gen` (Philox / global loads),
-// generated one k-pair ahead so that their instruction stream interleaves with the DMMAs of the current pair.
-// The q loop is fully unrolled: with TRI (lower-triangular A) the zero tiles mt < q vanish at compile time --
-// a predicated-off DMMA still occupies the fp64 tensor pipe, so skipping has to be structural.
-template <int NTB, int NPT, bool TRI, bool EXACT, int LA, class Gen>
-__device__ __forceinline__ void transform_tiles(uint32_t lf_lane_addr, int ntd, Gen& gen, double (&c)[NTB][NPT][2]) {
-    constexpr int KT2B = 2 * NTB;
-    double pb0[LA][NPT], pb1[LA][NPT];  // B fragments of the next LA k-pairs (in flight)
+// C[mt] += A(mt, 2q..2q+1) * B(q) for all k-pairs q.  B fragments come from `gen` (Philox / shared tile / global),
+// generated LA k-pairs ahead so that their instruction stream interleaves with the DMMAs of the current pair.
+// Fully unrolled: with TRI the zero tiles mt < q vanish at compile time.
+template <int NTB, bool TRI, bool EXACT, int LA, class Gen>
+__device__ __forceinline__ void transform_tiles(uint32_t lf_lane_addr, int ntd, Gen& gen, double (&c)[NTB][2]) {
+    double pb0[LA], pb1[LA];  // B fragments of the next LA k-pairs (in flight)
 #pragma unroll
     for (int l = 0; l < LA; ++l) gen(l, pb0[l], pb1[l]);
 #pragma unroll
     for (int q = 0; q < NTB; ++q) {
         if (EXACT || q < ntd) {  // EXACT (ntd == NTB): no guards, one straight-line block
-            double b0[NPT], b1[NPT];
-#pragma unroll
-            for (int pt = 0; pt < NPT; ++pt) {
-                b0[pt] = pb0[q % LA][pt];
-                b1[pt] = pb1[q % LA][pt];
-            }
+            const double b0 = pb0[q % LA], b1 = pb1[q % LA];
             if (q + LA < NTB) gen(q + LA, pb0[q % LA], pb1[q % LA]);
 #pragma unroll
             for (int mt = (TRI ? q : 0); mt < NTB; ++mt) {
                 if (EXACT || mt < ntd) {
-                    const double a0 = lds64(lf_lane_addr + (mt * KT2B + 2 * q) * 256);
-                    const double a1 = lds64(lf_lane_addr + (mt * KT2B + 2 * q + 1) * 256);
-#pragma unroll
-                    for (int pt = 0; pt < NPT; ++pt) {
-                        dmma(c[mt][pt][0], c[mt][pt][1], a0, b0[pt]);
-                        dmma(c[mt][pt][0], c[mt][pt][1], a1, b1[pt]);
-                    }
+                    const double a0 = lds64(lf_lane_addr + lf_tile<NTB, TRI>(mt, 2 * q) * 256);
+                    const double a1 = lds64(lf_lane_addr + lf_tile<NTB, TRI>(mt, 2 * q + 1) * 256);
+                    dmma(c[mt][0], c[mt][1], a0, b0);
+                    dmma(c[mt][0], c[mt][1], a1, b1);
                 }
             }
         }
@@ -150,31 +147,30 @@ __device__ __forceinline__ void transform_tiles(uint32_t lf_lane_addr, int ntd, 
 }
 
 struct GramRegs {
-    uint32_t addrR, addrC;  // shared byte addresses of this lane's element of the first row / column tile
-    int flags;              // bit q: tile q of the 2x2 macro tile (q = 2*row + col) is accumulated
+    uint32_t offR, offC;  // byte offsets (inside a tile buffer) of this lane's element of the first row / col tile
+    int flags;            // 15: off-diagonal 2x2, 13: diagonal 2x2, 3: one row x two cols, 1: single tile, 0: none
 };
 
 template <int MAXM, int S>
-__device__ __forceinline__ void gram_setup(const GramPlan& plan, int wi, int nta, int lr, int lc, uint32_t ys_addr,
-                                           GramRegs (&gr)[MAXM], int& nmac) {
+__device__ __forceinline__ void gram_setup(const GramPlan& plan, int wi, int nta, int lr, int lc, GramRegs (&gr)[MAXM],
+                                           int& nmac) {
     nmac = plan.nmac[wi];
 #pragma unroll
     for (int m = 0; m < MAXM; ++m) {
         const bool live = m < nmac;
         int code = live ? plan.mac[wi][m] : 0;
         int mr = code & 0xff, mc = code >> 8;
-        gr[m].addrR = ys_addr + (uint32_t)(((16 * mr + lr) * S + 2 * lc) * 8);
-        gr[m].addrC = ys_addr + (uint32_t)(((16 * mc + lr) * S + 2 * lc) * 8);
+        gr[m].offR = (uint32_t)(((16 * mr + lr) * S + 2 * lc) * 8);
+        gr[m].offC = (uint32_t)(((16 * mc + lr) * S + 2 * lc) * 8);
         const bool r1 = 2 * mr + 1 < nta, c1 = 2 * mc + 1 < nta, diag = mr == mc;
         gr[m].flags = live ? (1 | ((c1 && !diag) ? 2 : 0) | (r1 ? 4 : 0) | ((r1 && c1) ? 8 : 0)) : 0;
     }
 }
 
-// accumulate the Gram of the k-pairs [u_lo, u_hi) of the shared tile into the warp's macro tiles.  The macro type
-// (full 2x2, diagonal, single row, single tile) selects one of four straight-line blocks through warp-uniform
-// branches; no DMMA is issued for tiles outside the lower triangle.
+// accumulate the Gram of the k-pairs [u_lo, u_hi) of a shared tile into the warp's macro tiles.  The macro type
+// selects one of four straight-line blocks through warp-uniform branches.
 template <int MAXM, int S>
-__device__ __forceinline__ void gram_accumulate(const GramRegs (&gr)[MAXM], int u_lo, int u_hi,
+__device__ __forceinline__ void gram_accumulate(uint32_t buf, const GramRegs (&gr)[MAXM], int u_lo, int u_hi,
                                                 double (&acc)[MAXM][4][2]) {
 #pragma unroll 1
     for (int u = u_lo; u < u_hi; ++u) {
@@ -182,7 +178,7 @@ __device__ __forceinline__ void gram_accumulate(const GramRegs (&gr)[MAXM], int 
         for (int m = 0; m < MAXM; ++m) {
             const int f = gr[m].flags;
             if (f == 0) continue;
-            const uint32_t ra = gr[m].addrR + (uint32_t)u * 64u, ca = gr[m].addrC + (uint32_t)u * 64u;
+            const uint32_t ra = buf + gr[m].offR + (uint32_t)u * 64u, ca = buf + gr[m].offC + (uint32_t)u * 64u;
             if (f == 15) {  // off-diagonal 2x2
                 const double2 a0 = lds128(ra), a1 = lds128(ra + 8 * S * 8);
                 const double2 b0 = lds128(ca), b1 = lds128(ca + 8 * S * 8);
@@ -209,7 +205,7 @@ __device__ __forceinline__ void gram_accumulate(const GramRegs (&gr)[MAXM], int 
                 dmma(acc[m][1][0], acc[m][1][1], a0.x, b1.x);
                 dmma(acc[m][0][0], acc[m][0][1], a0.y, b0.y);
                 dmma(acc[m][1][0], acc[m][1][1], a0.y, b1.y);
-            } else {  // f == 1: single tile (last diagonal tile, or a lone off-diagonal tile)
+            } else {  // f == 1: single tile
                 const double2 a0 = lds128(ra);
                 const double2 b0 = lds128(ca);
                 dmma(acc[m][0][0], acc[m][0][1], a0.x, b0.x);
@@ -244,238 +240,83 @@ __device__ __forceinline__ void gram_store(double* __restrict__ part /* [T][64] 
 }
 
 // B-fragment sources ------------------------------------------------------------------------
-template <int NPT>
 struct GenPhilox {  // z ~ N(0,1): counter (global particle, dim pair 4q+lc, draw)
-    uint64_t seed, draw, particle[NPT];
+    uint64_t seed, draw, particle;
     uint32_t lc;
-    __device__ __forceinline__ void operator()(int q, double (&b0)[NPT], double (&b1)[NPT]) const {
-#pragma unroll
-        for (int pt = 0; pt < NPT; ++pt)
-            philox_normal_pair(seed, particle[pt], (uint32_t)(4 * q) + lc, draw, b0[pt], b1[pt]);
+    BmTableShared tab;
+    __device__ __forceinline__ void operator()(int q, double& b0, double& b1) const {
+        philox_normal_pair(seed, particle, (uint32_t)(4 * q) + lc, draw, tab, b0, b1);
     }
 };
 
-template <int NPT>
-struct GenGlobal {  // rows 8q+lc and 8q+4+lc of an SoA array at this lane's particle, minus an optional per-row mean
-    const double* base[NPT];  // &x[lc*ld + particle] (NULL if the particle is out of range)
-    const double* mean;       // shared-memory vector or NULL
+struct GenGlobal {  // rows 8q+lc and 8q+4+lc of an SoA array at this lane's particle (injected noise)
+    const double* base;  // &z[lc*ld + particle] (NULL if the particle is out of range)
     int64_t ld;
     int d, lc;
-    __device__ __forceinline__ void operator()(int q, double (&b0)[NPT], double (&b1)[NPT]) const {
+    __device__ __forceinline__ void operator()(int q, double& b0, double& b1) const {
         const int j0 = 8 * q + lc, j1 = j0 + 4;
-#pragma unroll
-        for (int pt = 0; pt < NPT; ++pt) {
-            double v0 = 0.0, v1 = 0.0;
-            if (base[pt] && j0 < d) v0 = __ldg(base[pt] + (int64_t)(8 * q) * ld) - (mean ? mean[j0] : 0.0);
-            if (base[pt] && j1 < d) v1 = __ldg(base[pt] + (int64_t)(8 * q + 4) * ld) - (mean ? mean[j1] : 0.0);
-            b0[pt] = v0;
-            b1[pt] = v1;
-        }
+        b0 = (base && j0 < d) ? __ldg(base + (int64_t)(8 * q) * ld) : 0.0;
+        b1 = (base && j1 < d) ? __ldg(base + (int64_t)(8 * q + 4) * ld) : 0.0;
+    }
+};
+
+template <int S>
+struct GenShared {  // rows 8q+lc and 8q+4+lc of the shared tile at this lane's particle column, minus the row mean
+    uint32_t addr;       // &buf[lc*S + column]
+    uint32_t mean_addr;  // &mean[lc]
+    bool valid;
+    __device__ __forceinline__ void operator()(int q, double& b0, double& b1) const {
+        const double x0 = lds64(addr + (uint32_t)(8 * q * S * 8)), x1 = lds64(addr + (uint32_t)((8 * q + 4) * S * 8));
+        const double m0 = lds64(mean_addr + 64 * q), m1 = lds64(mean_addr + 64 * q + 32);
+        b0 = valid ? x0 - m0 : 0.0;  // rows >= d pair with zero columns of Linv, so no row guard is needed
+        b1 = valid ? x1 - m1 : 0.0;
     }
 };
 
 // ---------------------------------------------------------------------------------------
-// sweep 1
+// the sweep kernel
 // ---------------------------------------------------------------------------------------
-template <int NTB, int NW, int NPT, int MAXM, int KS, bool EXACT>
-__global__ void __launch_bounds__(NW * 32, 1) k_step_mma(const MmaArgs a) {
+template <int SWEEP, int NTB, int NW, int MAXM, int KS, bool EXACT, bool TRI>
+__global__ void __launch_bounds__(NW * 32, 1) k_sweep(const MmaArgs a) {
     constexpr int MT = NW * 32;
-    constexpr int P = NW * NPT * 8;               // particles per CTA tile
+    constexpr int P = NW * 8;                     // particles per CTA tile (8 per warp)
     constexpr int S = P + 8;                      // row stride of the shared tile (8 mod 16 doubles)
-    constexpr int ROWS = 16 * ((NTB + 1) / 2);    // tile rows padded to full macro tiles
+    constexpr int ROWS = 8 * NTB;                 // tile rows (second rows of edge macro tiles are never read)
+    constexpr uint32_t BUF_BYTES = ROWS * S * 8;
     extern __shared__ double sm[];
     const int d = a.d, ntd = (d + 7) >> 3, nta = (d + 8) >> 3;
     double* Lf = sm;
-    double* Ys = Lf + NTB * 2 * NTB * 32;
-    double* vm = Ys + ROWS * S;
-    double* vs = vm + 8 * NTB;
-    double* vc = vs + 8 * NTB;
-    __shared__ double red[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lc = lane & 3;
-
-    pack_matrix<NTB, MT>(Lf, a.A, d);
-    for (int j = tid; j < 8 * NTB; j += MT) {
-        vm[j] = (j < d) ? a.m_noise[j] : 0.0;
-        vs[j] = (j < d && a.shift) ? a.shift[j] : 0.0;
-        vc[j] = (j < d) ? (a.lsf_mode == 1 ? a.coef[j] : 1.0) : 0.0;
-    }
-    for (int idx = tid; idx < ROWS * S; idx += MT) Ys[idx] = 0.0;
-
-    constexpr int WG = NW / KS;
-    const int grp = warp / WG, wi = warp % WG;
-    const uint32_t ys_addr = smem_u32(Ys);
-    const uint32_t lf_lane = smem_u32(Lf) + lane * 8;
-    GramRegs gr[MAXM];
-    int nmac;
-    gram_setup<MAXM, S>(a.plan, wi, nta, lr, lc, ys_addr, gr, nmac);
-    double acc[MAXM][4][2];
-#pragma unroll
-    for (int m = 0; m < MAXM; ++m)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[m][q][0] = acc[m][q][1] = 0.0;
-    __syncthreads();
-
-    double n_fail = 0.0;
-    const int pw = warp * 8 * NPT;  // first tile column of this warp
-    const double e_const = (double)d * REE_LOG_2PI;
-    const int64_t ntiles = (a.n + P - 1) / P;
-    // this lane's element of tile row block mt, particle tile pt: row 8mt+lr, columns pw+8pt+2lc (+1)
-    const uint32_t own_addr = ys_addr + (uint32_t)((lr * S + pw + 2 * lc) * 8);
-
-    auto prefetch = [&](int64_t i0) {  // x tile -> shared tile, every lane fetches exactly the elements it consumes
-#pragma unroll
-        for (int mt = 0; mt < NTB; ++mt) {
-            const int row = 8 * mt + lr;
-#pragma unroll
-            for (int pt = 0; pt < NPT; ++pt) {
-                const int64_t ip = i0 + pw + 8 * pt + 2 * lc;
-                if (row < d && ip < a.ld)
-                    cp_async16(own_addr + (uint32_t)((8 * mt * S + 8 * pt) * 8), a.x + (int64_t)row * a.ld + ip);
-            }
-        }
-    };
-    if ((int64_t)blockIdx.x < ntiles) prefetch((int64_t)blockIdx.x * P);
-
-    for (int64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
-        const int64_t i0 = tix * P;
-        // ---- F z on the tensor pipe: c[mt][pt] = rows 8mt.., particles pw+8pt.. ------------------
-        double c[NTB][NPT][2];
-#pragma unroll
-        for (int mt = 0; mt < NTB; ++mt)
-#pragma unroll
-            for (int pt = 0; pt < NPT; ++pt) c[mt][pt][0] = c[mt][pt][1] = 0.0;
-        if (a.z) {
-            GenGlobal<NPT> gen;
-#pragma unroll
-            for (int pt = 0; pt < NPT; ++pt) {
-                const int64_t ip = i0 + pw + 8 * pt + lr;
-                gen.base[pt] = (ip < a.n) ? a.z + (int64_t)lc * a.ld + ip : nullptr;
-            }
-            gen.mean = nullptr; gen.ld = a.ld; gen.d = d; gen.lc = lc;
-            transform_tiles<NTB, NPT, false, EXACT, 2>(lf_lane, ntd, gen, c);  // injected noise: dense parity factor
-        } else {
-            GenPhilox<NPT> gen;
-            gen.seed = a.seed; gen.draw = a.draw; gen.lc = (uint32_t)lc;
-#pragma unroll
-            for (int pt = 0; pt < NPT; ++pt) gen.particle[pt] = (uint64_t)(a.first + i0 + pw + 8 * pt + lr);
-            transform_tiles<NTB, NPT, true, EXACT, 1>(lf_lane, ntd, gen, c);  // Philox noise: Cholesky factor
-        }
-        cp_async_wait_all();
-        // ---- epilogue: x' = t x + (m + F z), store, energy / affine LSF partials, y -> shared tile ----
-        double se[NPT][2], sg[NPT][2];
-#pragma unroll
-        for (int pt = 0; pt < NPT; ++pt) se[pt][0] = se[pt][1] = sg[pt][0] = sg[pt][1] = 0.0;
-#pragma unroll
-        for (int mt = 0; mt < NTB; ++mt) {
-            if (EXACT || mt < ntd) {
-                const int row = 8 * mt + lr;
-                const bool rv = row < d;
-                const double mrow = vm[row], srow = vs[row], crow = vc[row];
-#pragma unroll
-                for (int pt = 0; pt < NPT; ++pt) {
-                    const int64_t ip = i0 + pw + 8 * pt + 2 * lc;
-                    const bool in_buf = rv && ip < a.ld;
-                    const uint32_t sa = own_addr + (uint32_t)((8 * mt * S + 8 * pt) * 8);
-                    double2 xv = lds128(sa);
-                    if (!in_buf) xv = make_double2(0.0, 0.0);
-                    // t*X + (m_noise + Z F^T): grouping of solver.py:667
-                    double2 xn;
-                    xn.x = __dadd_rn(__dmul_rn(a.t, xv.x), __dadd_rn(mrow, c[mt][pt][0]));
-                    xn.y = __dadd_rn(__dmul_rn(a.t, xv.y), __dadd_rn(mrow, c[mt][pt][1]));
-                    if (in_buf) *reinterpret_cast<double2*>(a.x_new + (int64_t)row * a.ld + ip) = xn;
-                    const bool v0 = ip < a.n, v1 = ip + 1 < a.n;
-                    double2 y;
-                    y.x = (rv && v0) ? xn.x - srow : 0.0;
-                    y.y = (rv && v1) ? xn.y - srow : 0.0;
-                    if (row == d) {  // augmented row of ones: sum y and n come out of the Gram
-                        y.x = v0 ? 1.0 : 0.0;
-                        y.y = v1 ? 1.0 : 0.0;
-                    }
-                    sts128(sa, y);
-                    if (rv) {
-                        se[pt][0] = fma(xn.x, xn.x, se[pt][0]);
-                        se[pt][1] = fma(xn.y, xn.y, se[pt][1]);
-                        sg[pt][0] = fma(crow, xn.x, sg[pt][0]);
-                        sg[pt][1] = fma(crow, xn.y, sg[pt][1]);
-                    }
-                }
-            }
-        }
-        if (nta > ntd && lr == 0) {  // d % 8 == 0: the augmented row lives in a tile of its own
-#pragma unroll
-            for (int pt = 0; pt < NPT; ++pt) {
-                const int pc = pw + 8 * pt + 2 * lc;
-                const int64_t ip = i0 + pc;
-                sts128(ys_addr + (uint32_t)((d * S + pc) * 8),
-                       make_double2(ip < a.n ? 1.0 : 0.0, ip + 1 < a.n ? 1.0 : 0.0));
-            }
-        }
-#pragma unroll
-        for (int pt = 0; pt < NPT; ++pt) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                double s = se[pt][h], gsum = sg[pt][h];
-#pragma unroll
-                for (int o = 4; o < 32; o <<= 1) {
-                    s += __shfl_xor_sync(0xffffffffu, s, o);
-                    gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
-                }
-                const int64_t ip = i0 + pw + 8 * pt + 2 * lc + h;
-                if (lr == 0 && ip < a.n) {
-                    if (a.e_new) a.e_new[ip] = 0.5 * (e_const + s);
-                    if (a.lsf_mode) {
-                        double gv = (a.lsf_mode == 1) ? __dadd_rn(gsum, a.offset)
-                                                      : __dadd_rn(__ddiv_rn(-gsum, __dsqrt_rn((double)d)), a.offset);
-                        a.g_new[ip] = gv;
-                        n_fail += (gv <= 0.0) ? 1.0 : 0.0;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // ---- Gram of the tile (k-split across warp groups) ------------------------------------
-        gram_accumulate<MAXM, S>(gr, grp * (P / 8 / KS), (grp + 1) * (P / 8 / KS), acc);
-        __syncthreads();
-        if (tix + gridDim.x < ntiles) prefetch((tix + gridDim.x) * P);  // lands while the next F z runs
-    }
-    const int T = nta * (nta + 1) / 2;
-    gram_store<MAXM>(a.partials + ((size_t)blockIdx.x * KS + grp) * T * 64, a.plan, wi, nmac, nta, lr, lc, acc);
-    n_fail = block_sum(n_fail, red);
-    if (tid == 0) a.small[blockIdx.x] = n_fail;
-}
-
-// ---------------------------------------------------------------------------------------
-// sweep 2 (and, with wmax == NULL, the plain shifted moments of an existing ensemble)
-// Same tile pipeline as sweep 1: every lane prefetches (cp.async) exactly the elements it will rescale, the
-// transform takes its B fragments straight from global / L2 (two k-pairs ahead), the accumulator fragments give
-// q = |Linv (x - mean)|^2, and the lane rewrites its elements as (x - mean) sqrt(w) for the weighted Gram.
-// ---------------------------------------------------------------------------------------
-template <int NTB, int NW, int NPT, int MAXM, int KS, bool EXACT>
-__global__ void __launch_bounds__(NW * 32, 1) k_maha_mma(const MmaArgs a) {
-    constexpr int MT = NW * 32;
-    constexpr int P = NW * NPT * 8;
-    constexpr int S = P + 8;
-    constexpr int ROWS = 16 * ((NTB + 1) / 2);
-    extern __shared__ double sm[];
-    const int d = a.d, ntd = (d + 7) >> 3, nta = (d + 8) >> 3;
-    double* Lf = sm;
-    double* Ys = Lf + NTB * 2 * NTB * 32;
-    double* vm = Ys + ROWS * S;  // mean
+    double* Ys = Lf + lf_doubles<NTB, TRI>();     // two tile buffers
+    double* vm = Ys + 2 * ROWS * S;               // m_noise (sweep 1) / mean (sweep 2)
+    double* vs = vm + 8 * NTB;                    // Gram shift (sweep 1)
+    double* vc = vs + 8 * NTB;                    // LSF coefficients (sweep 1)
+    double* bm = vc + 8 * NTB;                    // Box-Muller tables (sweep 1, Philox noise)
     __shared__ ExpSums sh[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lc = lane & 3;
-    const bool weighted = a.wmax != nullptr;  // false: plain moments (no Linv, no IS)
+    const bool weighted = (SWEEP == 2) && a.wmax != nullptr;
 
-    pack_matrix<NTB, MT>(Lf, weighted ? a.A : nullptr, d);
-    for (int j = tid; j < 8 * NTB; j += MT) vm[j] = (j < d && a.mean) ? a.mean[j] : 0.0;
-    for (int idx = tid; idx < ROWS * S; idx += MT) Ys[idx] = 0.0;
+    pack_matrix<NTB, TRI, MT>(Lf, (SWEEP == 1 || weighted) ? a.A : nullptr, d);
+    for (int j = tid; j < 8 * NTB; j += MT) {
+        if (SWEEP == 1) {
+            vm[j] = (j < d) ? a.m_noise[j] : 0.0;
+            vs[j] = (j < d && a.shift) ? a.shift[j] : 0.0;
+            vc[j] = (j < d) ? (a.lsf_mode == 1 ? a.coef[j] : 1.0) : 0.0;
+        } else {
+            vm[j] = (j < d && a.mean) ? a.mean[j] : 0.0;
+        }
+    }
+    for (int idx = tid; idx < 2 * ROWS * S; idx += MT) Ys[idx] = 0.0;
+    if (SWEEP == 1)
+        for (int idx = tid; idx < BM_TABLE_DOUBLES; idx += MT) bm[idx] = BM_TABLE[idx];
 
     constexpr int WG = NW / KS;
     const int grp = warp / WG, wi = warp % WG;
     const uint32_t ys_addr = smem_u32(Ys);
     const uint32_t lf_lane = smem_u32(Lf) + lane * 8;
+    const uint32_t vm_addr = smem_u32(vm);
     GramRegs gr[MAXM];
     int nmac;
-    gram_setup<MAXM, S>(a.plan, wi, nta, lr, lc, ys_addr, gr, nmac);
+    gram_setup<MAXM, S>(a.plan, wi, nta, lr, lc, gr, nmac);
     double acc[MAXM][4][2];
 #pragma unroll
     for (int m = 0; m < MAXM; ++m)
@@ -485,113 +326,163 @@ __global__ void __launch_bounds__(NW * 32, 1) k_maha_mma(const MmaArgs a) {
 
     ExpSums is_acc = expsums_empty();
     double n_fail = 0.0;
-    const int pw = warp * 8 * NPT;
+    const int pw = warp * 8;  // first tile column of this warp
+    const double e_const = (double)d * REE_LOG_2PI;
     const double logdet = weighted ? a.logdet[0] : 0.0;
     const double wmax = weighted ? a.wmax[0] : 0.0;
-    const double lq_const = (double)d * REE_LOG_2PI + logdet;
+    const double lq_const = e_const + logdet;
     const int64_t ntiles = (a.n + P - 1) / P;
-    const uint32_t own_addr = ys_addr + (uint32_t)((lr * S + pw + 2 * lc) * 8);
+    // this lane's elements of a tile: rows 8mt+lr, columns pw+2lc, pw+2lc+1
+    const uint32_t own_off = (uint32_t)((lr * S + pw + 2 * lc) * 8);
 
-    auto prefetch = [&](int64_t i0) {
+    auto prefetch = [&](int64_t i0, uint32_t buf) {  // every lane fetches exactly the elements it will rewrite
+        const int64_t ip = i0 + pw + 2 * lc;
+        if (ip < a.ld) {
 #pragma unroll
-        for (int mt = 0; mt < NTB; ++mt) {
-            const int row = 8 * mt + lr;
-#pragma unroll
-            for (int pt = 0; pt < NPT; ++pt) {
-                const int64_t ip = i0 + pw + 8 * pt + 2 * lc;
-                if (row < d && ip < a.ld)
-                    cp_async16(own_addr + (uint32_t)((8 * mt * S + 8 * pt) * 8), a.x + (int64_t)row * a.ld + ip);
+            for (int mt = 0; mt < NTB; ++mt) {
+                const int row = 8 * mt + lr;
+                if (row < d) cp_async16(buf + own_off + (uint32_t)(8 * mt * S * 8), a.x + (int64_t)row * a.ld + ip);
             }
         }
     };
-    if ((int64_t)blockIdx.x < ntiles) prefetch((int64_t)blockIdx.x * P);
+    if ((int64_t)blockIdx.x < ntiles) prefetch((int64_t)blockIdx.x * P, ys_addr);
 
-    for (int64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
+    int parity = 0;
+    for (int64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x, parity ^= 1) {
         const int64_t i0 = tix * P;
-        double swc[NPT][2];  // sqrt(w) of this lane's particle columns (1 / 0 for plain moments)
-        if (weighted) {
-            // ---- u = Linv (x - mean) on the tensor pipe; B fragments straight from global / L2 ----------
-            double c[NTB][NPT][2];
+        const uint32_t buf = ys_addr + (parity ? BUF_BYTES : 0u);
+        const int64_t ip = i0 + pw + 2 * lc;  // first of this lane's two particle columns
+        const bool v0 = ip < a.n, v1 = ip + 1 < a.n;
+        double c[NTB][2];
 #pragma unroll
-            for (int mt = 0; mt < NTB; ++mt)
-#pragma unroll
-                for (int pt = 0; pt < NPT; ++pt) c[mt][pt][0] = c[mt][pt][1] = 0.0;
-            GenGlobal<NPT> gen;
-#pragma unroll
-            for (int pt = 0; pt < NPT; ++pt) {
-                const int64_t ip = i0 + pw + 8 * pt + lr;
-                gen.base[pt] = (ip < a.n) ? a.x + (int64_t)lc * a.ld + ip : nullptr;
+        for (int mt = 0; mt < NTB; ++mt) c[mt][0] = c[mt][1] = 0.0;
+        double sw0 = v0 ? 1.0 : 0.0, sw1 = v1 ? 1.0 : 0.0;  // sweep 2: sqrt(w) of the lane's columns
+
+        if (SWEEP == 1) {
+            // ---- F z on the tensor pipe: c[mt] = rows 8mt.., particles pw.. ----------------------------
+            if (a.z) {
+                GenGlobal gen;
+                const int64_t ipb = i0 + pw + lr;
+                gen.base = (ipb < a.n) ? a.z + (int64_t)lc * a.ld + ipb : nullptr;
+                gen.ld = a.ld; gen.d = d; gen.lc = lc;
+                transform_tiles<NTB, TRI, EXACT, 3>(lf_lane, ntd, gen, c);
+            } else {
+                GenPhilox gen;
+                gen.seed = a.seed; gen.draw = a.draw; gen.lc = (uint32_t)lc; gen.tab.addr = smem_u32(bm);
+                gen.particle = (uint64_t)(a.first + i0 + pw + lr);
+                transform_tiles<NTB, TRI, EXACT, 1>(lf_lane, ntd, gen, c);
             }
-            gen.mean = vm; gen.ld = a.ld; gen.d = d; gen.lc = lc;
-            transform_tiles<NTB, NPT, true, EXACT, 2>(lf_lane, ntd, gen, c);  // Linv is lower triangular
-            // ---- q = |u|^2, log q, IS statistics, weight (solver.py:629-632, 683-686) ---------------------
-#pragma unroll
-            for (int pt = 0; pt < NPT; ++pt) {
+            cp_async_wait_all();
+        } else {
+            cp_async_wait_all();
+            __syncwarp();  // the warp's own columns of tile k have landed
+            if (weighted) {
+                // ---- u = Linv (x - mean); B fragments from the warp's own columns of the shared tile -----
+                GenShared<S> gen;
+                gen.addr = buf + (uint32_t)((lc * S + pw + lr) * 8);
+                gen.mean_addr = vm_addr + lc * 8;
+                gen.valid = (i0 + pw + lr) < a.n;
+                transform_tiles<NTB, TRI, EXACT, 1>(lf_lane, ntd, gen, c);
+                // ---- q = |u|^2, log q, IS statistics, weight (solver.py:629-632, 683-686) -----------------
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     double qq = 0.0;
 #pragma unroll
-                    for (int mt = 0; mt < NTB; ++mt) qq = fma(c[mt][pt][h], c[mt][pt][h], qq);
+                    for (int mt = 0; mt < NTB; ++mt) qq = fma(c[mt][h], c[mt][h], qq);
 #pragma unroll
                     for (int o = 4; o < 32; o <<= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
-                    const int64_t ip = i0 + pw + 8 * pt + 2 * lc + h;
                     double swv = 0.0;
-                    if (lr == 0 && ip < a.n) {
+                    if (lr == 0 && ip + h < a.n) {
                         const double lq = -0.5 * (lq_const + qq);
-                        if (a.logq) a.logq[ip] = lq;
-                        const double gi = a.g[ip], ei = a.e[ip];
+                        if (a.logq) a.logq[ip + h] = lq;
+                        const double gi = a.g[ip + h], ei = a.e[ip + h];
                         const double r = __dsub_rn(-ei, lq);  // -e_fun - log_pdf  (solver.py:684)
                         if (isfinite(r)) expsums_add(is_acc, r, gi <= 0.0 ? 1.0 : 0.0);
                         const double al = __dmul_rn(ree_logtgt(gi, ei, a.sigma, a.tgt_kind), a.beta);
                         const double wv = isfinite(al) ? exp(al - wmax) : 0.0;
-                        if (a.w_out) a.w_out[ip] = wv;
+                        if (a.w_out) a.w_out[ip + h] = wv;
                         swv = sqrt(wv);
                     }
-                    swc[pt][h] = __shfl_sync(0xffffffffu, swv, lc);  // lane lc (lr == 0) owns this column pair
+                    swv = __shfl_sync(0xffffffffu, swv, lc);  // lane lc (lr == 0) owns this column pair
+                    if (h == 0) sw0 = swv; else sw1 = swv;
                 }
-            }
-        } else {
-#pragma unroll
-            for (int pt = 0; pt < NPT; ++pt) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int64_t ip = i0 + pw + 8 * pt + 2 * lc + h;
-                    swc[pt][h] = (ip < a.n) ? 1.0 : 0.0;
-                    if (lr == 0 && a.g && ip < a.n) n_fail += (a.g[ip] <= 0.0) ? 1.0 : 0.0;
-                }
+                __syncwarp();  // all B-fragment reads of the raw tile precede the in-place rewrite below
+            } else if (lr == 0 && a.g) {
+                if (v0) n_fail += (a.g[ip] <= 0.0) ? 1.0 : 0.0;
+                if (v1) n_fail += (a.g[ip + 1] <= 0.0) ? 1.0 : 0.0;
             }
         }
-        cp_async_wait_all();
-        // ---- this lane's elements: (x - mean) sqrt(w); augmented row = sqrt(w) => sum w y, sum w ----------
+
+        // ---- epilogue: rewrite this lane's elements of the tile -----------------------------------------
+        double se0 = 0.0, se1 = 0.0, sg0 = 0.0, sg1 = 0.0;
 #pragma unroll
         for (int mt = 0; mt < NTB; ++mt) {
             if (EXACT || mt < ntd) {
                 const int row = 8 * mt + lr;
-                const double mrow = vm[row];
-#pragma unroll
-                for (int pt = 0; pt < NPT; ++pt) {
-                    const uint32_t sa = own_addr + (uint32_t)((8 * mt * S + 8 * pt) * 8);
-                    const double2 xv = lds128(sa);
-                    double2 y;  // select, not multiply: padded / stale lanes may hold anything
-                    y.x = (row < d && swc[pt][0] != 0.0) ? (xv.x - mrow) * swc[pt][0] : 0.0;
-                    y.y = (row < d && swc[pt][1] != 0.0) ? (xv.y - mrow) * swc[pt][1] : 0.0;
-                    if (row == d) {
-                        y.x = swc[pt][0];
-                        y.y = swc[pt][1];
+                const bool rv = row < d;
+                const uint32_t sa = buf + own_off + (uint32_t)(8 * mt * S * 8);
+                double2 xv = lds128(sa);
+                double2 y;
+                if (SWEEP == 1) {
+                    const bool in_buf = rv && ip < a.ld;
+                    if (!in_buf) xv = make_double2(0.0, 0.0);
+                    const double mrow = vm[row], srow = vs[row], crow = vc[row];
+                    // t*X + (m_noise + Z F^T): grouping of solver.py:667
+                    double2 xn;
+                    xn.x = __dadd_rn(__dmul_rn(a.t, xv.x), __dadd_rn(mrow, c[mt][0]));
+                    xn.y = __dadd_rn(__dmul_rn(a.t, xv.y), __dadd_rn(mrow, c[mt][1]));
+                    if (in_buf) *reinterpret_cast<double2*>(a.x_new + (int64_t)row * a.ld + ip) = xn;
+                    y.x = (rv && v0) ? xn.x - srow : 0.0;
+                    y.y = (rv && v1) ? xn.y - srow : 0.0;
+                    if (rv) {
+                        se0 = fma(xn.x, xn.x, se0);
+                        se1 = fma(xn.y, xn.y, se1);
+                        sg0 = fma(crow, xn.x, sg0);
+                        sg1 = fma(crow, xn.y, sg1);
                     }
-                    sts128(sa, y);
+                } else {
+                    const double mrow = vm[row];  // select, not multiply: padded / stale lanes may hold anything
+                    y.x = (rv && sw0 != 0.0) ? (xv.x - mrow) * sw0 : 0.0;
+                    y.y = (rv && sw1 != 0.0) ? (xv.y - mrow) * sw1 : 0.0;
+                }
+                if (row == d) {  // augmented row: ones (or sqrt(w)) => sum y and n (sum w y and sum w)
+                    y.x = sw0;
+                    y.y = sw1;
+                }
+                sts128(sa, y);
+            }
+        }
+        if (nta > ntd && lr == 0)  // d % 8 == 0: the augmented row lives in a tile of its own
+            sts128(buf + (uint32_t)((d * S + pw + 2 * lc) * 8), make_double2(sw0, sw1));
+        if (SWEEP == 1) {
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                se0 += __shfl_xor_sync(0xffffffffu, se0, o);
+                se1 += __shfl_xor_sync(0xffffffffu, se1, o);
+                sg0 += __shfl_xor_sync(0xffffffffu, sg0, o);
+                sg1 += __shfl_xor_sync(0xffffffffu, sg1, o);
+            }
+            if (lr == 0) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (ip + h < a.n) {
+                        const double s = h ? se1 : se0, gsum = h ? sg1 : sg0;
+                        if (a.e_new) a.e_new[ip + h] = 0.5 * (e_const + s);
+                        if (a.lsf_mode) {
+                            double gv = (a.lsf_mode == 1)
+                                            ? __dadd_rn(gsum, a.offset)
+                                            : __dadd_rn(__ddiv_rn(-gsum, __dsqrt_rn((double)d)), a.offset);
+                            a.g_new[ip + h] = gv;
+                            n_fail += (gv <= 0.0) ? 1.0 : 0.0;
+                        }
+                    }
                 }
             }
         }
-        if (nta > ntd && lr == 0) {
-#pragma unroll
-            for (int pt = 0; pt < NPT; ++pt)
-                sts128(ys_addr + (uint32_t)((d * S + pw + 8 * pt + 2 * lc) * 8), make_double2(swc[pt][0], swc[pt][1]));
-        }
-        __syncthreads();
-        gram_accumulate<MAXM, S>(gr, grp * (P / 8 / KS), (grp + 1) * (P / 8 / KS), acc);
-        __syncthreads();
-        if (tix + gridDim.x < ntiles) prefetch((tix + gridDim.x) * P);
+        __syncthreads();  // the one barrier of the tile: buf k complete; everybody is done with buf k+1 (Gram k-1)
+        if (tix + gridDim.x < ntiles) prefetch((tix + gridDim.x) * P, ys_addr + (parity ? 0u : BUF_BYTES));
+        // ---- Gram of the tile (k-split across warp groups) ------------------------------------------------
+        gram_accumulate<MAXM, S>(buf, gr, grp * (P / 8 / KS), (grp + 1) * (P / 8 / KS), acc);
     }
     const int T = nta * (nta + 1) / 2;
     gram_store<MAXM>(a.partials + ((size_t)blockIdx.x * KS + grp) * T * 64, a.plan, wi, nmac, nta, lr, lc, acc);
@@ -609,7 +500,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_maha_mma(const MmaArgs a) {
 
 // ---------------------------------------------------------------------------------------
 // second stage: fixed-order sum over (cta, group) partials, unpack tiles into sums = [S1 | S2 | a | b]
-//   S2[j][k] = G[j][k], S1[j] = G[d][j], b = G[d][d] (n or sum w); a = tail scalar (count / unused)
+//   S2[j][k] = G[j][k], S1[j] = G[d][j], G[d][d] = n (tail slot b) or sum w (tail slot a)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_unpack_gram(const double* __restrict__ partials, int nparts, int d, int nta,
                                                      int weighted, double* __restrict__ sums) {
@@ -690,26 +581,19 @@ static void make_plan(GramPlan& plan, int nta, int warps_per_group, int maxm) {
     }
 }
 
-// kernel configuration per dimension bucket: NTB tile rows, NW warps, NPT particle tiles per warp,
-// MAXM Gram macro tiles per warp, KS k-split groups
+// kernel configuration per dimension bucket: NTB tile rows, NW warps (8 particles each), MAXM Gram macro tiles per
+// warp, KS k-split groups.  `dense` (injected noise with the parity-mode factor U sqrt(S)) keeps the full F in shared
+// memory and therefore uses fewer warps in the d <= 103 bucket.
 struct MmaCfg {
-    int ntb, nw, npt, maxm, ks;
+    int ntb, nw, maxm, ks;
 };
 
-static int g_nw_override = -1;
-
-static bool pick_cfg(int d, MmaCfg& c) {
-    if (g_nw_override < 0) {
-        const char* e = getenv("REE_MMA_WARPS");  // tuning hook: 8 or 16 warps per CTA for the d <= 103 bucket
-        g_nw_override = e ? atoi(e) : 0;
-    }
-    if (d <= 15) c = {2, 8, 2, 1, 8};
-    else if (d <= 31) c = {4, 8, 2, 2, 4};
-    else if (d <= 55) c = {7, 8, 2, 3, 2};
-    else if (d <= 103) {
-        c = {13, 16, 1, 2, 1};
-        if (g_nw_override == 8) c = {13, 8, 2, 4, 1};
-    } else return false;
+static bool pick_cfg(int d, bool dense, MmaCfg& c) {
+    if (d <= 15) c = {2, 8, 1, 8};
+    else if (d <= 31) c = {4, 8, 2, 4};
+    else if (d <= 55) c = {7, 8, 3, 2};
+    else if (d <= 103) c = dense ? MmaCfg{13, 6, 5, 1} : MmaCfg{13, 12, 3, 1};
+    else return false;
     return true;
 }
 
@@ -723,71 +607,68 @@ bool ree_mma_supported(int d) {
     }
     if (forced) return false;
     MmaCfg c;
-    return pick_cfg(d, c);
+    return pick_cfg(d, false, c);
 }
 
 extern "C" int ree_fused_path(int d) { return ree_mma_supported(d) ? 1 : 0; }
 
-static size_t mma_smem_bytes(const MmaCfg& c, bool sweep2) {
-    int P = c.nw * c.npt * 8, S = P + 8;
-    int rows = 16 * ((c.ntb + 1) / 2);
-    size_t n = (size_t)c.ntb * 2 * c.ntb * 32 + (size_t)rows * S + (sweep2 ? 8 * c.ntb : 3 * 8 * c.ntb);
-    return n * sizeof(double);
-}
-
 size_t ree_mma_partial_doubles(int d) {
     MmaCfg c;
-    if (!pick_cfg(d, c)) return 0;
+    if (!pick_cfg(d, false, c)) return 0;
     int nta = (d + 8) / 8, T = nta * (nta + 1) / 2;
-    return (size_t)ree_grid_ctas() * c.ks * T * 64;
+    return (size_t)ree_grid_ctas() * 8 * T * 64;  // 8 >= any KS
 }
 
-template <int NTB, int NW, int NPT, int MAXM, int KS, bool EXACT>
-static int launch_one(bool sweep2, const MmaArgs& a, int grid, size_t smem, cudaStream_t st) {
-    if (sweep2) {
-        cudaFuncSetAttribute(k_maha_mma<NTB, NW, NPT, MAXM, KS, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem);
-        k_maha_mma<NTB, NW, NPT, MAXM, KS, EXACT><<<grid, NW * 32, smem, st>>>(a);
-    } else {
-        cudaFuncSetAttribute(k_step_mma<NTB, NW, NPT, MAXM, KS, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem);
-        k_step_mma<NTB, NW, NPT, MAXM, KS, EXACT><<<grid, NW * 32, smem, st>>>(a);
-    }
-    return ree_check_launch(sweep2 ? "k_maha_mma" : "k_step_mma");
+template <int SWEEP, int NTB, int NW, int MAXM, int KS, bool EXACT, bool TRI>
+static int launch_k(const MmaArgs& a, int grid, cudaStream_t st) {
+    constexpr int P = NW * 8, S = P + 8, ROWS = 8 * NTB;
+    constexpr size_t smem = ((size_t)lf_doubles<NTB, TRI>() + 2 * ROWS * S + 3 * 8 * NTB +
+                             (SWEEP == 1 ? BM_TABLE_DOUBLES + 2 : 0)) * sizeof(double);
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    auto kern = k_sweep<SWEEP, NTB, NW, MAXM, KS, EXACT, TRI>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, NW * 32, smem, st>>>(a);
+    return ree_check_launch(SWEEP == 1 ? "k_sweep<1>" : "k_sweep<2>");
 }
 
-template <int NTB, int NW, int NPT, int MAXM, int KS>
-static int launch_cfg(bool sweep2, const MmaArgs& a, int grid, size_t smem, cudaStream_t st) {
+template <int SWEEP, int NTB, int NW, int MAXM, int KS, bool TRI>
+static int launch_exact(const MmaArgs& a, int grid, cudaStream_t st) {
     // guard-free instantiation when the dimension fills the bucket (d = 100 -> 13 tiles)
-    if ((a.d + 7) / 8 == NTB) return launch_one<NTB, NW, NPT, MAXM, KS, true>(sweep2, a, grid, smem, st);
-    return launch_one<NTB, NW, NPT, MAXM, KS, false>(sweep2, a, grid, smem, st);
+    if ((a.d + 7) / 8 == NTB) return launch_k<SWEEP, NTB, NW, MAXM, KS, true, TRI>(a, grid, st);
+    return launch_k<SWEEP, NTB, NW, MAXM, KS, false, TRI>(a, grid, st);
 }
 
-// Runs one sweep and the second-stage reductions.  small_out: sweep 1 -> sums tail [count], sweep 2 -> is4.
-int ree_mma_sweep(bool sweep2, MmaArgs& a, double* workspace_big, double* workspace_small, double* sums, double* is4,
-                  cudaStream_t st) {
+template <int SWEEP, bool TRI>
+static int launch_bucket(const MmaCfg& c, const MmaArgs& a, int grid, cudaStream_t st) {
+    if (c.ntb == 2) return launch_exact<SWEEP, 2, 8, 1, 8, TRI>(a, grid, st);
+    if (c.ntb == 4) return launch_exact<SWEEP, 4, 8, 2, 4, TRI>(a, grid, st);
+    if (c.ntb == 7) return launch_exact<SWEEP, 7, 8, 3, 2, TRI>(a, grid, st);
+    if constexpr (TRI) return launch_exact<SWEEP, 13, 12, 3, 1, TRI>(a, grid, st);
+    else return launch_exact<SWEEP, 13, 6, 5, 1, TRI>(a, grid, st);
+}
+
+// Runs one sweep and the second-stage reductions.  sweep 1 -> sums tail [count], sweep 2 -> is4.
+static int ree_mma_sweep(int sweep, bool dense, MmaArgs& a, double* workspace_big, double* workspace_small, double* sums,
+                         double* is4, cudaStream_t st) {
     MmaCfg c;
-    if (!pick_cfg(a.d, c)) return ree_set_error(REE_E_UNSUPPORTED, "mma path: d > 103");
-    const int d = a.d, nta = (d + 8) / 8, P = c.nw * c.npt * 8;
+    if (!pick_cfg(a.d, dense, c)) return ree_set_error(REE_E_UNSUPPORTED, "mma path: d > 103");
+    const int d = a.d, nta = (d + 8) / 8, P = c.nw * 8;
     int sms = ree_grid_ctas() / 2;  // persistent: one CTA per SM
     int64_t ntiles = (a.n + P - 1) / P;
     int grid = (int)(ntiles < sms ? ntiles : sms);
     make_plan(a.plan, nta, c.nw / c.ks, c.maxm);
     a.partials = workspace_big;
     a.small = workspace_small;
-    size_t smem = mma_smem_bytes(c, sweep2);
     int rc;
-    if (c.ntb == 2) rc = launch_cfg<2, 8, 2, 1, 8>(sweep2, a, grid, smem, st);
-    else if (c.ntb == 4) rc = launch_cfg<4, 8, 2, 2, 4>(sweep2, a, grid, smem, st);
-    else if (c.ntb == 7) rc = launch_cfg<7, 8, 2, 3, 2>(sweep2, a, grid, smem, st);
-    else if (c.nw == 16) rc = launch_cfg<13, 16, 1, 2, 1>(sweep2, a, grid, smem, st);
-    else rc = launch_cfg<13, 8, 2, 4, 1>(sweep2, a, grid, smem, st);
+    if (sweep == 1) rc = dense ? launch_bucket<1, false>(c, a, grid, st) : launch_bucket<1, true>(c, a, grid, st);
+    else rc = launch_bucket<2, true>(c, a, grid, st);
     if (rc) return rc;
     const int D1 = d + 1;
-    k_unpack_gram<<<(D1 * D1 + 255) / 256, 256, 0, st>>>(workspace_big, grid * c.ks, d, nta, (sweep2 && a.wmax) ? 1 : 0, sums);
+    const bool weighted = sweep == 2 && a.wmax;
+    k_unpack_gram<<<(D1 * D1 + 255) / 256, 256, 0, st>>>(workspace_big, grid * c.ks, d, nta, weighted ? 1 : 0, sums);
     rc = ree_check_launch("k_unpack_gram");
     if (rc) return rc;
-    if (sweep2 && a.wmax) {
+    if (weighted) {
         k_merge_expsums<<<1, 256, 0, st>>>(workspace_small, grid, is4);
         return ree_check_launch("k_merge_expsums");
     }
@@ -803,24 +684,24 @@ int ree_mma_step(const double* x, double* x_new, int64_t n, int d, int64_t ld, d
                  const double* coef, double offset, const double* shift, double* g_new, double* e_new, double* ws_big,
                  double* ws_small, double* sums, cudaStream_t st) {
     MmaArgs a{};
-    a.x = x; a.n = n; a.ld = ld; a.d = d; a.A = F; a.tri = tri; a.shift = shift; a.x_new = x_new; a.t = t;
+    a.x = x; a.n = n; a.ld = ld; a.d = d; a.A = F; a.shift = shift; a.x_new = x_new; a.t = t;
     a.m_noise = m_noise; a.z = z; a.seed = seed; a.draw = draw; a.first = first; a.lsf_mode = lsf_mode; a.coef = coef;
     a.offset = offset; a.g_new = g_new; a.e_new = e_new;
-    return ree_mma_sweep(false, a, ws_big, ws_small, sums, nullptr, st);
+    return ree_mma_sweep(1, tri == 0, a, ws_big, ws_small, sums, nullptr, st);
 }
 
 int ree_mma_maha(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* e, const double* mean,
                  const double* Linv, const double* logdet, double sigma, double beta, int tgt_kind, const double* wmax,
                  double* logq, double* w, double* ws_big, double* ws_small, double* sums, double* is4, cudaStream_t st) {
     MmaArgs a{};
-    a.x = x; a.n = n; a.ld = ld; a.d = d; a.A = Linv; a.tri = 1; a.g = g; a.e = e; a.mean = mean; a.logdet = logdet;
+    a.x = x; a.n = n; a.ld = ld; a.d = d; a.A = Linv; a.g = g; a.e = e; a.mean = mean; a.logdet = logdet;
     a.wmax = wmax; a.sigma = sigma; a.beta = beta; a.tgt_kind = tgt_kind; a.logq = logq; a.w_out = w;
-    return ree_mma_sweep(true, a, ws_big, ws_small, sums, is4, st);
+    return ree_mma_sweep(2, false, a, ws_big, ws_small, sums, is4, st);
 }
 
 int ree_mma_sums(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* shift, double* ws_big,
                  double* ws_small, double* sums, cudaStream_t st) {
     MmaArgs a{};
     a.x = x; a.n = n; a.ld = ld; a.d = d; a.g = g; a.mean = shift;  // plain moments: y = x - shift, no weights
-    return ree_mma_sweep(true, a, ws_big, ws_small, sums, nullptr, st);
+    return ree_mma_sweep(2, false, a, ws_big, ws_small, sums, nullptr, st);
 }
