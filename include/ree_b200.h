@@ -127,6 +127,9 @@ int ree_reduce_ess(const double* g, const double* e, int64_t n, double sigma, do
  * replaces the sigma objective, solver.py:538-545 + my_log_cvar utilities.py:76-102.        */
 int ree_reduce_cvar(const double* g, int64_t n, double sigma_new, double sigma_old, int tgt_kind,
                     double* workspace, double* out4, void* stream);
+/* Same four outputs for a = scale * ell_i with a precomputed log-target vector (ree_logtgt): the beta root find
+ * (solver.py:591-601) evaluates ESS(beta) many times for one sigma.                                            */
+int ree_reduce_scaled(const double* ell, int64_t n, double scale, double* workspace, double* out4, void* stream);
 /* out[0] = #{g_i <= 0} (as double)       replaces sum(lsf_evals <= 0), solver.py:534, 570, 709-712 */
 int ree_count_failed(const double* g, int64_t n, double* workspace, double* out1, void* stream);
 

@@ -61,6 +61,7 @@ PROTOTYPES = {
     "ree_logtgt": (_INT, [_P, _P, _I64, _DBL, _INT, _P, _P]),
     "ree_reduce_ess": (_INT, [_P, _P, _I64, _DBL, _DBL, _INT, _P, _P, _P]),
     "ree_reduce_cvar": (_INT, [_P, _I64, _DBL, _DBL, _INT, _P, _P, _P]),
+    "ree_reduce_scaled": (_INT, [_P, _I64, _DBL, _P, _P, _P]),
     "ree_count_failed": (_INT, [_P, _I64, _P, _P, _P]),
     "ree_cbree_step": (_INT, [_P, _P, _I64, _INT, _I64, _DBL, _P, _P, _INT, _P, _U64, _U64, _I64, _LSFP, _P, _P, _P,
                               _P, _P, _P]),

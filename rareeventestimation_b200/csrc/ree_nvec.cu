@@ -60,6 +60,51 @@ __global__ void __launch_bounds__(REE_THREADS) k_reduce_ess(const double* __rest
     expsums_grid_finalize(blk, ws, out4, sh, &is_last);
 }
 
+// a_i = scale * ell_i for a precomputed log-target vector (the beta root find re-evaluates ESS(beta) ~20 times
+// for a fixed sigma: one exp per particle instead of the whole log-target)
+__global__ void __launch_bounds__(REE_THREADS) k_reduce_scaled(const double* __restrict__ ell, int64_t n, double scale,
+                                                               double* ws, double* out4) {
+    __shared__ ExpSums sh[32];
+    __shared__ bool is_last;
+    ExpSums acc = expsums_empty();
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double a = __dmul_rn(ell[i], scale);
+        if (isfinite(a)) expsums_add(acc, a, 1.0);
+    }
+    ExpSums blk = expsums_block_reduce(acc, sh);
+    expsums_grid_finalize(blk, ws, out4, sh, &is_last);
+}
+
+// algebraic target, sigma_new >= sigma_old: exp(a_i) = I(sigma_new; g_i) / I(sigma_old; g_i) with the smoothed
+// indicator I = (1 - sigma g / sqrt(1 + sigma^2 g^2)) / 2 -- the same rounded 1 - q the reference feeds to log1p, so
+// the ratio equals exp(l_new - l_old) to an ulp, without log / exp.  Entries whose l_new or l_old is -inf (1 - q
+// rounds to 0) are non-finite in the reference and masked there; they are skipped here.  Ratios are <= 2: no shift.
+__global__ void __launch_bounds__(REE_THREADS) k_reduce_cvar_alg(const double* __restrict__ g, int64_t n,
+                                                                 double sigma_new, double sigma_old, double* ws,
+                                                                 double* out4) {
+    __shared__ ExpSums sh[32];
+    __shared__ bool is_last;
+    double s1 = 0.0, s2 = 0.0, cnt = 0.0;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const double sn2 = __dmul_rn(sigma_new, sigma_new), so2 = __dmul_rn(sigma_old, sigma_old);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double gi = g[i], g2 = __dmul_rn(gi, gi);
+        const double qn = __ddiv_rn(__dmul_rn(-sigma_new, gi), __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(sn2, g2))));
+        const double qo = __ddiv_rn(__dmul_rn(-sigma_old, gi), __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(so2, g2))));
+        const double in = __dadd_rn(1.0, qn), io = __dadd_rn(1.0, qo);  // 1 + q as log1p forms it
+        if (in > 0.0 && io > 0.0 && isfinite(in) && isfinite(io)) {
+            const double v = in / io;
+            s1 += v;
+            s2 = fma(v, v, s2);
+            cnt += 1.0;
+        }
+    }
+    ExpSums acc{cnt > 0.0 ? 0.0 : -CUDART_INF, s1, s2, cnt};
+    ExpSums blk = expsums_block_reduce(acc, sh);
+    expsums_grid_finalize(blk, ws, out4, sh, &is_last);
+}
+
 // a_i = logtgt(g_i,0;sigma_new) - logtgt(g_i,0;sigma_old)   (solver.py:538-545)
 __global__ void __launch_bounds__(REE_THREADS) k_reduce_cvar(const double* __restrict__ g, int64_t n,
                                                              double sigma_new, double sigma_old, int kind,
@@ -127,6 +172,11 @@ extern "C" int ree_reduce_ess(const double* g, const double* e, int64_t n, doubl
 extern "C" int ree_reduce_cvar(const double* g, int64_t n, double sigma_new, double sigma_old, int tgt_kind,
                                double* workspace, double* out4, void* stream) {
     if (!g || !workspace || !out4 || n < 0) return ree_set_error(REE_E_BADARG, "ree_reduce_cvar: bad argument");
+    if (tgt_kind == REE_TGT_ALGEBRAIC && sigma_new >= sigma_old && sigma_old >= 0.0) {
+        k_reduce_cvar_alg<<<nvec_grid(n), REE_THREADS, 0, ree_stream(stream)>>>(g, n, sigma_new, sigma_old, workspace,
+                                                                                out4);
+        return ree_check_launch("ree_reduce_cvar(algebraic)");
+    }
     k_reduce_cvar<<<nvec_grid(n), REE_THREADS, 0, ree_stream(stream)>>>(g, n, sigma_new, sigma_old, tgt_kind, workspace,
                                                                         out4);
     return ree_check_launch("ree_reduce_cvar");
@@ -136,4 +186,11 @@ extern "C" int ree_count_failed(const double* g, int64_t n, double* workspace, d
     if (!g || !workspace || !out1 || n < 0) return ree_set_error(REE_E_BADARG, "ree_count_failed: bad argument");
     k_count_failed<<<nvec_grid(n), REE_THREADS, 0, ree_stream(stream)>>>(g, n, workspace, out1);
     return ree_check_launch("ree_count_failed");
+}
+
+extern "C" int ree_reduce_scaled(const double* ell, int64_t n, double scale, double* workspace, double* out4,
+                                 void* stream) {
+    if (!ell || !workspace || !out4 || n < 0) return ree_set_error(REE_E_BADARG, "ree_reduce_scaled: bad argument");
+    k_reduce_scaled<<<nvec_grid(n), REE_THREADS, 0, ree_stream(stream)>>>(ell, n, scale, workspace, out4);
+    return ree_check_launch("ree_reduce_scaled");
 }

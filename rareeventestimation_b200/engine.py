@@ -133,6 +133,7 @@ class Engine:
         self.comm = Comm(enabled=False)
         self._ws = {}
         self._pool = {}
+        self._scratch = {}
         self._staging = None
         with torch.cuda.device(self.device):
             self.num_ctas = self.lib.ree_num_ctas()
@@ -183,7 +184,7 @@ class Engine:
         e = self.empty(ld) if with_vectors else None
         return Ensemble(X, n, d, ld, first, g, e)
 
-    def release(self, ens: Optional[Ensemble], keep: int = 3):
+    def release(self, ens: Optional[Ensemble], keep: int = 8):
         """Return an ensemble nobody references any more to the free list."""
         if ens is None or ens.g is None or ens.e is None:
             return
@@ -193,6 +194,23 @@ class Engine:
 
     def drop_pool(self):
         self._pool.clear()
+        self._scratch.clear()
+
+    def reserve(self, n: int, d: int, count: int):
+        """Make sure `count` ensembles of this shape sit in the free list (one cudaMalloc each, outside the
+        iteration loop); the allocations of a solve are then reused by the next one."""
+        free = self._pool.setdefault((int(n), int(d)), [])
+        while len(free) < count:
+            ld = _pad(n)
+            free.append(Ensemble(self.empty(d, ld), n, d, ld, 0, self.empty(ld), self.empty(ld)))
+
+    def scratch(self, name: str, numel: int) -> torch.Tensor:
+        """Named N-sized scratch vector that persists across iterations (torch's caching allocator would otherwise
+        carve it out of a freed 8 GB ensemble block and force a fresh cudaMalloc for the next ensemble)."""
+        t = self._scratch.get(name)
+        if t is None or t.numel() < numel:
+            t = self._scratch[name] = self.empty(numel)
+        return t
 
     def upload(self, host: np.ndarray, first: int = 0) -> Ensemble:
         """Host (n,d) C-order array -> SoA ensemble (chunked H2D + device transpose)."""
@@ -241,8 +259,8 @@ class Engine:
         check(self.lib.ree_energy(ens.X.data_ptr(), ens.n, ens.d, ens.ld, e.data_ptr(), self.stream), "ree_energy")
         return e
 
-    def logtgt(self, g, e, n, sigma, kind) -> torch.Tensor:
-        out = self.empty(g.numel())
+    def logtgt(self, g, e, n, sigma, kind, out=None) -> torch.Tensor:
+        out = out if out is not None else self.empty(g.numel())
         check(self.lib.ree_logtgt(g.data_ptr(), e.data_ptr() if e is not None else None, n, float(sigma), kind,
                                   out.data_ptr(), self.stream), "ree_logtgt")
         return out
@@ -261,6 +279,14 @@ class Engine:
         ws = self.workspace(ens.d)
         check(self.lib.ree_reduce_cvar(ens.g.data_ptr(), ens.n, float(sigma_new), float(sigma_old), kind,
                                        ws.data_ptr(), out.data_ptr(), self.stream), "ree_reduce_cvar")
+        return self.comm.combine_expsums_(out)
+
+    def reduce_scaled(self, ell: torch.Tensor, n: int, d: int, scale: float, out=None) -> torch.Tensor:
+        """[max, sum exp, sum exp^2, count] of scale*ell (a log-target vector from :meth:`logtgt`)."""
+        out = out if out is not None else self.empty(4)
+        ws = self.workspace(d)
+        check(self.lib.ree_reduce_scaled(ell.data_ptr(), n, float(scale), ws.data_ptr(), out.data_ptr(), self.stream),
+              "ree_reduce_scaled")
         return self.comm.combine_expsums_(out)
 
     def count_failed(self, ens: Ensemble, out=None) -> torch.Tensor:

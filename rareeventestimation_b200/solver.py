@@ -464,8 +464,14 @@ class CBREE(Solver):
             else:
                 _log.info(f"Iteration {cache.iteration}: {msg}")
 
-    def _ess(self, cache: CBREECache, beta, out=None) -> float:
-        t4 = self._eng.reduce_ess(cache._dev, cache.sigma, beta, self._tgt_kind(), out=out).cpu().numpy()
+    def _ess(self, cache: CBREECache, beta, out=None, ell=None) -> float:
+        """ESS of the weights exp(beta*l).  `ell` (the log-target vector for cache.sigma, from ree_logtgt) makes
+        repeated evaluations for different beta cost one exp per particle."""
+        dev = cache._dev
+        if ell is not None:
+            t4 = self._eng.reduce_scaled(ell, dev.n, dev.d, beta, out=out).cpu().numpy()
+        else:
+            t4 = self._eng.reduce_ess(dev, cache.sigma, beta, self._tgt_kind(), out=out).cpu().numpy()
         if t4[3] <= 0:
             raise ValueError("attempt to get argmax of an empty sequence")
         return ess_from(t4)
@@ -474,9 +480,10 @@ class CBREE(Solver):
         """solver.py:582-612: MINPACK hybr root of ESS(beta) - ess_tgt*N; objective = ``ree_reduce_ess``."""
         out = self._eng.empty(4)
         n_tot = cache._n_total
+        ell = self._ell_of(cache)
 
         def obj_fun(temperature):
-            return self._ess(cache, float(np.asarray(temperature).reshape(-1)[0]), out) - self.ess_tgt * n_tot
+            return self._ess(cache, float(np.asarray(temperature).reshape(-1)[0]), out, ell) - self.ess_tgt * n_tot
 
         try:
             sol = root(obj_fun, cache.beta)
@@ -488,6 +495,13 @@ class CBREE(Solver):
                 cache.msg += msg
             else:
                 _log.info(f"Iteration {cache.iteration}: {msg}")
+
+    def _ell_of(self, cache: CBREECache):
+        """Device vector l(g, e; cache.sigma), computed once per sigma (the reference recomputes it inside every
+        objective evaluation, solver.py:592-594)."""
+        dev = cache._dev
+        return self._eng.logtgt(dev.g, dev.e, dev.n, cache.sigma, self._tgt_kind(),
+                                out=self._eng.scratch("ell", dev.ld))
 
     def _update_beta_and_sigma(self, cache: CBREECache) -> None:
         """solver.py:505-523."""
@@ -664,6 +678,8 @@ class CBREE(Solver):
         initial weights, initial step size.  Returns the cache list."""
         self._setup(prob)
         dev = self._initial_ensemble(prob)
+        if not self.save_history:  # the window's HBM buffers, allocated once and recycled by _retire
+            self._eng.reserve(dev.n, dev.d, int(min(self.observation_window, self.num_steps + 1)) + 1)
         cache = CBREECache(self._eng, dev, sigma=self.sigma, beta=self.beta, num_lsf_evals=self.lsf.counter)
         self._post_ensemble(cache)
         self._compute_weights_check(cache)
