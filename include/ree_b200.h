@@ -130,6 +130,9 @@ int ree_reduce_cvar(const double* g, int64_t n, double sigma_new, double sigma_o
 /* Same four outputs for a = scale * ell_i with a precomputed log-target vector (ree_logtgt): the beta root find
  * (solver.py:591-601) evaluates ESS(beta) many times for one sigma.                                            */
 int ree_reduce_scaled(const double* ell, int64_t n, double scale, double* workspace, double* out4, void* stream);
+/* Merge `nparts` 4-tuples [M, S1, S2, cnt] (e.g. all_gather'ed from the ranks) into one, shifted to the global
+ * max; fixed order, so every rank computes identical bits.                                                    */
+int ree_merge_expsums(const double* parts, int nparts, double* out4, void* stream);
 /* out[0] = #{g_i <= 0} (as double)       replaces sum(lsf_evals <= 0), solver.py:534, 570, 709-712 */
 int ree_count_failed(const double* g, int64_t n, double* workspace, double* out1, void* stream);
 
@@ -177,6 +180,32 @@ int ree_cbree_maha(const double* x, int64_t n, int d, int64_t ld, const double* 
                    const double* mean, const double* Linv, const double* logdet, double sigma, double beta,
                    int tgt_kind, const double* wmax, double* logq, double* w, double* workspace, double* sums,
                    double* is4, void* stream);
+
+/* ---- secondary path: SIS with adaptive conditional sampling (sis/SIS_aCS.py:64-306) ------------------------ */
+/* mode 0: v_i = Phi(-g_i/sigma_new) / Phi(-g_i/sigma_old)  (sigma_old <= 0: denominator 1)   SIS_aCS.py:151-183
+ * mode 1: v_i = 1[g_i < 0] / Phi(-g_i/sigma_new)                                            SIS_aCS.py:282-300
+ * out4 = [0, sum v, sum v^2, n]; w_out (optional) receives v.                                               */
+int ree_sis_reduce(const double* g, int64_t n, double sigma_new, double sigma_old, int mode, double* w_out,
+                   double* workspace, double* out4, void* stream);
+/* inclusive prefix sum cdf[i] = w[0] + ... + w[i]; scratch: ree_scan_scratch_doubles(n) doubles */
+int64_t ree_scan_scratch_doubles(int64_t n);
+int ree_scan_inclusive(const double* w, int64_t n, double* cdf, double* scratch, void* stream);
+/* multinomial choice of nchain seeds with probabilities w/sum(w): idx[k] = first i with cdf[i] > u_k cdf[n-1],
+ * u_k from Philox (first + k).  replaces np.random.choice(N, nchain, True, p), SIS_aCS.py:194               */
+int ree_sis_resample(const double* cdf, int64_t n, int64_t nchain, uint64_t seed, uint64_t draw, int64_t first,
+                     int64_t* idx, void* stream);
+/* out[j][k] = x[j][idx[k]], g_out[k] = g[idx[k]]   (seed rows, SIS_aCS.py:195-196) */
+int ree_gather_columns(const double* x, int d, int64_t ld_src, const int64_t* idx, int64_t nchain, double* out,
+                       int64_t ld_out, const double* g, double* g_out, void* stream);
+/* cand = rho*cur + sigma_f*z, z ~ N(0,I)   (SIS_aCS.py:232) */
+int ree_acs_propose(const double* cur, int64_t nchain, int d, int64_t ld, double rho, double sigma_f, uint64_t seed,
+                    uint64_t draw, int64_t first, double* cand, void* stream);
+/* accept with probability min(1, Phi(-g_cand/sigma)/Phi(-g_cur/sigma)); the chain state (cur, g_cur) is updated in
+ * place and appended to the new population at columns out_col0 + k.  out4 = [0, sum alpha, #accepted, nchain]
+ * (SIS_aCS.py:238-254) */
+int ree_acs_accept(double* cur, double* g_cur, const double* cand, const double* g_cand, int64_t nchain, int d,
+                   int64_t ld, double sigma, uint64_t seed, uint64_t draw, int64_t first, double* out_x, int64_t ld_out,
+                   int64_t out_col0, double* out_g, double* workspace, double* out4, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,7 @@ from .problem import DeviceSample, NormalProblem, Problem, Vectorizer  # noqa: F
 from .lsf import AffineLSF, ConvexLSF, DeviceLSF, DiffusionLSF, FujitaRackwitzLSF, OscillatorLSF  # noqa: F401
 from .solution import Solution  # noqa: F401
 from .solver import CBREE, CBREECache, MixtureModel, Solver, flatten_cache_list, get_slope  # noqa: F401
+from .baselines import CMC, SIS  # noqa: F401
 from .toy_problems import (  # noqa: F401
     lsf_convex, lsf_lin, lsf_nonlin_osc, make_fujita_rackwitz, make_linear_problem, prob_convex, prob_nonlin_osc,
     problems_highdim, problems_lowdim,

@@ -62,6 +62,7 @@ PROTOTYPES = {
     "ree_reduce_ess": (_INT, [_P, _P, _I64, _DBL, _DBL, _INT, _P, _P, _P]),
     "ree_reduce_cvar": (_INT, [_P, _I64, _DBL, _DBL, _INT, _P, _P, _P]),
     "ree_reduce_scaled": (_INT, [_P, _I64, _DBL, _P, _P, _P]),
+    "ree_merge_expsums": (_INT, [_P, _INT, _P, _P]),
     "ree_count_failed": (_INT, [_P, _I64, _P, _P, _P]),
     "ree_cbree_step": (_INT, [_P, _P, _I64, _INT, _I64, _DBL, _P, _P, _INT, _P, _U64, _U64, _I64, _LSFP, _P, _P, _P,
                               _P, _P, _P]),
@@ -70,6 +71,14 @@ PROTOTYPES = {
     "ree_moments_chol": (_INT, [_P, _P, _INT, _INT, _INT, _P, _P, _P, _P, _P, _P]),
     "ree_chol_scaled": (_INT, [_P, _INT, _DBL, _P, _P, _P]),
     "ree_cbree_maha": (_INT, [_P, _I64, _INT, _I64, _P, _P, _P, _P, _P, _DBL, _DBL, _INT, _P, _P, _P, _P, _P, _P,
+                              _P]),
+    "ree_sis_reduce": (_INT, [_P, _I64, _DBL, _DBL, _INT, _P, _P, _P, _P]),
+    "ree_scan_scratch_doubles": (_I64, [_I64]),
+    "ree_scan_inclusive": (_INT, [_P, _I64, _P, _P, _P]),
+    "ree_sis_resample": (_INT, [_P, _I64, _I64, _U64, _U64, _I64, _P, _P]),
+    "ree_gather_columns": (_INT, [_P, _INT, _I64, _P, _I64, _P, _I64, _P, _P, _P]),
+    "ree_acs_propose": (_INT, [_P, _I64, _INT, _I64, _DBL, _DBL, _U64, _U64, _I64, _P, _P]),
+    "ree_acs_accept": (_INT, [_P, _P, _P, _P, _I64, _INT, _I64, _DBL, _U64, _U64, _I64, _P, _I64, _I64, _P, _P, _P,
                               _P]),
 }
 

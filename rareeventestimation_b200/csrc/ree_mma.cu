@@ -705,3 +705,10 @@ int ree_mma_sums(const double* x, int64_t n, int d, int64_t ld, const double* g,
     a.x = x; a.n = n; a.ld = ld; a.d = d; a.g = g; a.mean = shift;  // plain moments: y = x - shift, no weights
     return ree_mma_sweep(2, false, a, ws_big, ws_small, sums, nullptr, st);
 }
+
+// rank-order merge of R gathered 4-tuples [M, S1, S2, cnt] (multi-GPU combine of ESS / CVAR / IS statistics)
+extern "C" int ree_merge_expsums(const double* parts, int nparts, double* out4, void* stream) {
+    if (!parts || !out4 || nparts < 1) return ree_set_error(REE_E_BADARG, "ree_merge_expsums: bad argument");
+    k_merge_expsums<<<1, 256, 0, ree_stream(stream)>>>(parts, nparts, out4);
+    return ree_check_launch("ree_merge_expsums");
+}

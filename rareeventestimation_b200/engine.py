@@ -66,7 +66,12 @@ class Comm:
         if self.enabled:
             gathered = torch.empty(self.world * 4, dtype=out4.dtype, device=out4.device)
             self.dist.all_gather_into_tensor(gathered, out4.contiguous(), group=self.group)
-            out4.copy_(merge_expsums(gathered.view(self.world, 4)))
+            if out4.is_cuda:  # one small kernel instead of a dozen elementwise launches
+                stream = C.c_void_p(torch.cuda.current_stream(out4.device).cuda_stream)
+                check(_lib.load().ree_merge_expsums(gathered.data_ptr(), self.world, out4.data_ptr(), stream),
+                      "ree_merge_expsums")
+            else:
+                out4.copy_(merge_expsums(gathered.view(self.world, 4)))
         return out4
 
     def shard(self, n_global: int):
@@ -289,12 +294,12 @@ class Engine:
               "ree_reduce_scaled")
         return self.comm.combine_expsums_(out)
 
-    def count_failed(self, ens: Ensemble, out=None) -> torch.Tensor:
+    def count_failed(self, ens: Ensemble, out=None, reduce=True) -> torch.Tensor:
         out = out if out is not None else self.empty(1)
         ws = self.workspace(ens.d)
         check(self.lib.ree_count_failed(ens.g.data_ptr(), ens.n, ws.data_ptr(), out.data_ptr(), self.stream),
               "ree_count_failed")
-        return self.comm.allreduce_sum_(out)
+        return self.comm.allreduce_sum_(out) if reduce else out
 
     # -- sweeps ------------------------------------------------------------------- #
     def ensemble_sums(self, ens: Ensemble, shift: Optional[torch.Tensor], sums: torch.Tensor, with_g=True):

@@ -67,16 +67,17 @@ class DeviceSample:
     """An initial sample that was drawn on the device (Philox) and never visited the host.
     Quacks like the (N,d) ndarray the reference stores in ``prob.sample``."""
 
-    def __init__(self, n: int, d: int, seed: int):
+    def __init__(self, n: int, d: int, seed: int, draw: int = _STREAM_SAMPLE):
         self.shape = (int(n), int(d))
         self.seed = int(seed)
+        self.draw = int(draw)  # Philox draw index of the stream this sample is a window of
         self.ndim = 2
         self.dtype = np.dtype(np.float64)
 
     def materialise(self, engine: Engine, lo: int = 0, hi: Optional[int] = None):
         """Ensemble for the global particle range [lo, hi) (rank-invariant counters)."""
         hi = self.shape[0] if hi is None else hi
-        return engine.philox_normal(hi - lo, self.shape[1], self.seed, _STREAM_SAMPLE, first=lo)
+        return engine.philox_normal(hi - lo, self.shape[1], self.seed, self.draw, first=lo)
 
     def __array__(self, dtype=None, copy=None):
         eng = Engine.get()
