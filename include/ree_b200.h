@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define REE_ABI_VERSION 1
+#define REE_ABI_VERSION 2
 
 /* argument errors */
 #define REE_E_BADARG (-1)
@@ -81,8 +81,12 @@ int ree_abi_version(void);
 const char* ree_last_error(void);
 /* kernels launched by this library in this process so far (bench.py reports the delta as gpu_launches) */
 int64_t ree_launch_count(void);
-/* 1 if dimension d is served by the fused DMMA sweep kernels (d <= 103), 0 if by the modular kernels
- * (which need the optional `w` scratch vector of ree_cbree_maha) */
+/* Which kernels serve dimension d:
+ *   1  fused DMMA sweeps (ree_cbree_step and ree_cbree_maha each produce their Gram)      -- HBM-bound d
+ *   2  split DMMA path: ree_cbree_step(sums = NULL) -> ree_reduce_ess(a_out) -> ree_cbree_moments ->
+ *      ree_moments_chol -> ree_cbree_maha(sums = NULL)                                    -- fp64-bound d (56..103)
+ *   0  modular kernels (need the optional `w` scratch vector of ree_cbree_maha)           -- d > 103
+ * Path 2 dimensions are also served by the path 1 calling sequence.                                    */
 int ree_fused_path(int d);
 /* number of CTAs every reduction kernel uses on the current device (partials per launch) */
 int ree_num_ctas(void);
@@ -119,9 +123,10 @@ int ree_logtgt(const double* g, const double* e, int64_t n, double sigma, int tg
 /* One pass over (g,e): a = beta*logtgt(g,e;sigma), masked to finite a.
  *   out[0] = M = max a, out[1] = sum exp(a-M), out[2] = sum exp(2(a-M)), out[3] = #finite
  * ESS = out[1]^2/out[2].   replaces my_softmax + ESS, utilities.py:105-142, solver.py:523, 591-597.
- * `e` may be NULL (treated as 0).                                                            */
+ * `e` may be NULL (treated as 0).  `a_out` (optional, n doubles) receives a_i = beta*logtgt_i, the log-weights
+ * ree_cbree_moments turns into w_i = exp(a_i - M).                                                */
 int ree_reduce_ess(const double* g, const double* e, int64_t n, double sigma, double beta, int tgt_kind,
-                   double* workspace, double* out4, void* stream);
+                   double* a_out, double* workspace, double* out4, void* stream);
 /* One pass over g: a = logtgt(g,0;sigma_new) - logtgt(g,0;sigma_old), masked to finite a; same
  * four outputs.  cvar = sqrt(out[2]/nf - (out[1]/nf)^2)/(out[1]/nf).
  * replaces the sigma objective, solver.py:538-545 + my_log_cvar utilities.py:76-102.        */
@@ -149,12 +154,23 @@ int ree_cbree_step(const double* x, double* x_new, int64_t n, int d, int64_t ld,
                    uint64_t seed, uint64_t draw, int64_t first_particle, const ree_lsf* lsf,
                    const double* shift, double* g_new, double* e_new, double* workspace, double* sums,
                    void* stream);
+/* (sums may be NULL on path 2 dimensions: transform only, the moments come from ree_cbree_moments.) */
 /* number of doubles in `sums` of ree_cbree_step / ree_cbree_maha / ree_ensemble_sums: d + d*d + 2 */
 int64_t ree_sums_len(int d);
 /* The same unweighted sums for an existing ensemble (initial sample, or after a callback replaced it);
  * g may be NULL (count = 0).  replaces average/cov in solver.py:790-791, 840-841.                 */
 int ree_ensemble_sums(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* shift,
                       double* workspace, double* sums, void* stream);
+
+/* Path 2: both Grams of an ensemble in one pass over X.  With y = x - shift (shift: d device doubles or NULL) and
+ * w_i = exp(a_i - wmax[0]) (0 where a_i is not finite):
+ *   sums_u = [sum y | sum y y^T | #{g_i <= 0} | n]          (np.average / np.cov, solver.py:670-671)
+ *   sums_w = [sum w y | sum w y y^T | sum w | 0]             (weighted mean / cov, solver.py:629-636)
+ * a: log-weights from ree_reduce_ess(a_out); wmax: DEVICE scalar, out4[0] of the same call; g may be NULL (count 0).
+ * sums_w == NULL computes the unweighted sums only (a, wmax unused).                                  */
+int ree_cbree_moments(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* a,
+                      const double* wmax, const double* shift, double* workspace, double* sums_u, double* sums_w,
+                      void* stream);
 
 /* ---- small dense algebra (single CTA) ---------------------------------------------------- */
 /* From raw shifted sums (after any cross-rank allreduce) compute
@@ -175,7 +191,8 @@ int ree_chol_scaled(const double* C, int d, double scale, double* L, double* sta
  * and, with w_i = exp(beta*logtgt(g_i,e_i;sigma) - wmax[0]) (0 where non-finite):
  *     sums as in ree_cbree_step but weighted and shifted by `mean`; sums[d+d*d] = sum w
  *   (weighted mean/cov, solver.py:629-636).  wmax is a DEVICE scalar (out[0] of ree_reduce_ess).
- * logq and w (n doubles each, optional) receive log q_i and the unnormalised weights w_i.       */
+ * logq and w (n doubles each, optional) receive log q_i and the unnormalised weights w_i.
+ * Path 2: sums == NULL skips the weights and the weighted sums (wmax may then be NULL as well).   */
 int ree_cbree_maha(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* e,
                    const double* mean, const double* Linv, const double* logdet, double sigma, double beta,
                    int tgt_kind, const double* wmax, double* logq, double* w, double* workspace, double* sums,

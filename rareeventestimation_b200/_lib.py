@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libree_b200.so")
 TGT_KINDS = {"algebraic": 0, "tanh": 1, "arctan": 2, "erf": 3, "relu": 4, "sigmoid": 5}
 LSF_EXTERNAL, LSF_AFFINE, LSF_CONVEX, LSF_FUJITA_RACKWITZ, LSF_OSCILLATOR, LSF_DIFFUSION = range(6)
 NOISE_INJECT, NOISE_PHILOX = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class ReeError(RuntimeError):
@@ -59,7 +59,7 @@ PROTOTYPES = {
     "ree_lsf_eval": (_INT, [_LSFP, _P, _I64, _I64, _P, _P]),
     "ree_energy": (_INT, [_P, _I64, _INT, _I64, _P, _P]),
     "ree_logtgt": (_INT, [_P, _P, _I64, _DBL, _INT, _P, _P]),
-    "ree_reduce_ess": (_INT, [_P, _P, _I64, _DBL, _DBL, _INT, _P, _P, _P]),
+    "ree_reduce_ess": (_INT, [_P, _P, _I64, _DBL, _DBL, _INT, _P, _P, _P, _P]),
     "ree_reduce_cvar": (_INT, [_P, _I64, _DBL, _DBL, _INT, _P, _P, _P]),
     "ree_reduce_scaled": (_INT, [_P, _I64, _DBL, _P, _P, _P]),
     "ree_merge_expsums": (_INT, [_P, _INT, _P, _P]),
@@ -67,6 +67,7 @@ PROTOTYPES = {
     "ree_cbree_step": (_INT, [_P, _P, _I64, _INT, _I64, _DBL, _P, _P, _INT, _P, _U64, _U64, _I64, _LSFP, _P, _P, _P,
                               _P, _P, _P]),
     "ree_sums_len": (_I64, [_INT]),
+    "ree_cbree_moments": (_INT, [_P, _I64, _INT, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ree_ensemble_sums": (_INT, [_P, _I64, _INT, _I64, _P, _P, _P, _P, _P]),
     "ree_moments_chol": (_INT, [_P, _P, _INT, _INT, _INT, _P, _P, _P, _P, _P, _P]),
     "ree_chol_scaled": (_INT, [_P, _INT, _DBL, _P, _P, _P]),

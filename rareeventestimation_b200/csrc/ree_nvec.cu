@@ -47,13 +47,14 @@ __global__ void __launch_bounds__(REE_THREADS) k_logtgt(const double* __restrict
 // a_i = beta * logtgt(g_i, e_i; sigma)   (my_softmax(log_tgt_evals * beta), solver.py:522, 595)
 __global__ void __launch_bounds__(REE_THREADS) k_reduce_ess(const double* __restrict__ g, const double* __restrict__ e,
                                                             int64_t n, double sigma, double beta, int kind,
-                                                            double* ws, double* out4) {
+                                                            double* __restrict__ a_out, double* ws, double* out4) {
     __shared__ ExpSums sh[32];
     __shared__ bool is_last;
     ExpSums acc = expsums_empty();
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         double a = __dmul_rn(ree_logtgt(g[i], e ? e[i] : 0.0, sigma, kind), beta);
+        if (a_out) a_out[i] = a;
         if (isfinite(a)) expsums_add(acc, a, 1.0);
     }
     ExpSums blk = expsums_block_reduce(acc, sh);
@@ -163,9 +164,10 @@ extern "C" int ree_logtgt(const double* g, const double* e, int64_t n, double si
 }
 
 extern "C" int ree_reduce_ess(const double* g, const double* e, int64_t n, double sigma, double beta, int tgt_kind,
-                              double* workspace, double* out4, void* stream) {
+                              double* a_out, double* workspace, double* out4, void* stream) {
     if (!g || !workspace || !out4 || n < 0) return ree_set_error(REE_E_BADARG, "ree_reduce_ess: bad argument");
-    k_reduce_ess<<<nvec_grid(n), REE_THREADS, 0, ree_stream(stream)>>>(g, e, n, sigma, beta, tgt_kind, workspace, out4);
+    k_reduce_ess<<<nvec_grid(n), REE_THREADS, 0, ree_stream(stream)>>>(g, e, n, sigma, beta, tgt_kind, a_out, workspace,
+                                                                      out4);
     return ree_check_launch("ree_reduce_ess");
 }
 

@@ -1,0 +1,597 @@
+// Split DMMA path of a CBREE iteration for the fp64-bound dimensions (56 <= d <= 103): three homogeneous kernels
+// instead of the two fused sweeps of ree_mma.cu.
+//
+//   k_xform<1>   X' = t X + m 1^T + F Z^T, g', e'        (transform only: no tile buffer, no CTA barrier; every warp
+//                                                          owns 8 particles and runs on its own; Z from Philox)
+//   k_gram2      both Grams of X' in one pass: sum y y^T, sum y, n  and  sum w y y^T, sum w y, sum w  (y = x' - shift,
+//                w = exp(a - wmax) from the a = beta*l vector of ree_reduce_ess): pure LDS + DMMA stream
+//   k_xform<2>   u = Linv (x' - mean), q = |u|^2 -> log q, IS statistics   (transform only)
+//
+// Why split: in the fused sweeps all warps of a CTA walk through the same phases (Philox-heavy transform, epilogue,
+// barrier, Gram) in lock step, so the fp64 pipe idles whenever the phase is not DMMA-dense (49 % / 65 % tensor-active,
+// profiles/r1_a1_*).  Here the integer-heavy Philox work of one warp overlaps the DMMAs of the 15 others, and the
+// Gram kernel feeds the pipe from 16 independent accumulator chains per warp.  Price: X' is read three times instead
+// of twice (32 GB instead of 24 GB of HBM traffic per iteration at N=1e7, d=100 -- 4.9 ms of a >= 12.5 ms DMMA bound).
+#include "mma_common.cuh"
+
+struct XfArgs {
+    const double* x;  // MODE 1: X (input) ; MODE 2: X'
+    int64_t n, ld;
+    int d;
+    const double* A;  // F (MODE 1) or Linv (MODE 2), row-major d x d
+    // MODE 1
+    double* x_new;
+    double t;
+    const double* m_noise;
+    const double* z;
+    uint64_t seed, draw;
+    int64_t first;
+    int lsf_mode;  // 0: not fused, 1: affine coef, 2: -sum(x)/sqrt(d) + offset
+    const double* coef;
+    double offset;
+    double* g_new;
+    double* e_new;
+    // MODE 2
+    const double* g;
+    const double* e;
+    const double* mean;
+    const double* logdet;
+    double* logq;
+    double* small;  // per-CTA ExpSums
+};
+
+struct GenStage {  // rows 8q+lc and 8q+4+lc of the warp's staging block at particle column lr, minus the row mean
+    uint32_t addr;       // &stg[lc*8 + lr]
+    uint32_t mean_addr;  // &mean[lc]
+    bool valid;
+    __device__ __forceinline__ void operator()(int q, double& b0, double& b1) const {
+        const double x0 = lds64(addr + (uint32_t)(8 * q * 64)), x1 = lds64(addr + (uint32_t)((8 * q + 4) * 64));
+        const double m0 = lds64(mean_addr + 64 * q), m1 = lds64(mean_addr + 64 * q + 32);
+        b0 = valid ? x0 - m0 : 0.0;  // rows >= d pair with zero columns of Linv (staging rows >= d stay zero)
+        b1 = valid ? x1 - m1 : 0.0;
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// transform kernel: one warp = 8 particles x all dimensions, persistent over warp tiles
+// ---------------------------------------------------------------------------------------
+template <int MODE, int NTB, int NW, bool EXACT, bool TRI>
+__global__ void __launch_bounds__(NW * 32, 1) k_xform(const XfArgs a) {
+    constexpr int MT = NW * 32;
+    constexpr int ROWS = 8 * NTB;
+    constexpr int STG = ROWS * 8;  // doubles of one warp's staging block: [row][8 particles]
+    extern __shared__ double sm[];
+    const int d = a.d, ntd = (d + 7) >> 3;
+    double* Lf = sm;
+    double* stg = Lf + lf_doubles<NTB, TRI>();
+    double* vm = stg + NW * STG;  // m_noise (MODE 1) / mean (MODE 2)
+    double* vc = vm + 8 * NTB;    // LSF coefficients (MODE 1)
+    double* bm = vc + 8 * NTB;    // Box-Muller tables (MODE 1, Philox noise)
+    __shared__ ExpSums sh[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lc = lane & 3;
+
+    pack_matrix<NTB, TRI, MT>(Lf, a.A, d);
+    for (int j = tid; j < 8 * NTB; j += MT) {
+        if (MODE == 1) {
+            vm[j] = (j < d) ? a.m_noise[j] : 0.0;
+            vc[j] = (j < d) ? (a.lsf_mode == 1 ? a.coef[j] : 1.0) : 0.0;
+        } else {
+            vm[j] = (j < d) ? a.mean[j] : 0.0;
+        }
+    }
+    for (int idx = tid; idx < NW * STG; idx += MT) stg[idx] = 0.0;
+    if (MODE == 1 && !a.z)
+        for (int idx = tid; idx < BM_TABLE_DOUBLES; idx += MT) bm[idx] = BM_TABLE[idx];
+    __syncthreads();
+
+    const uint32_t lf_lane = smem_u32(Lf) + lane * 8;
+    const uint32_t stg_w = smem_u32(stg + warp * STG);
+    const uint32_t own = stg_w + (uint32_t)(lr * 64 + lc * 16);  // rows 8mt+lr, columns 2lc, 2lc+1
+    const uint32_t vm_addr = smem_u32(vm);
+    const double e_const = (double)d * REE_LOG_2PI;
+    const double lq_const = (MODE == 2) ? e_const + a.logdet[0] : 0.0;
+    ExpSums is_acc = expsums_empty();
+    const int64_t nwt = (a.n + 7) >> 3;
+    const int64_t stride = (int64_t)gridDim.x * NW;
+
+    auto prefetch = [&](int64_t wt) {  // every lane fetches the 16-byte chunks (row 8mt+lr, columns 2lc..2lc+1)
+        const double* src = a.x + wt * 8 + 2 * lc;  // wt*8 + 7 < ld (ld is a multiple of 8, ld >= n)
+#pragma unroll
+        for (int mt = 0; mt < NTB; ++mt) {
+            const int row = 8 * mt + lr;
+            if (row < d) cp_async16(own + (uint32_t)(mt * 512), src + (int64_t)row * a.ld);
+        }
+    };
+    int64_t wt = (int64_t)blockIdx.x * NW + warp;
+    if (wt < nwt) prefetch(wt);
+
+    for (; wt < nwt; wt += stride) {
+        const int64_t i0 = wt * 8;
+        const int64_t ip = i0 + 2 * lc;  // first of this lane's two particle columns
+        double c[NTB][2];
+#pragma unroll
+        for (int mt = 0; mt < NTB; ++mt) c[mt][0] = c[mt][1] = 0.0;
+
+        if (MODE == 1) {
+            // ---- F z on the tensor pipe: c[mt] = rows 8mt.., particles i0.. ------------------------------
+            if (a.z) {
+                GenGlobal gen;
+                const int64_t ipb = i0 + lr;
+                gen.base = (ipb < a.n) ? a.z + (int64_t)lc * a.ld + ipb : nullptr;
+                gen.ld = a.ld; gen.d = d; gen.lc = lc;
+                transform_tiles<NTB, TRI, EXACT, 3>(lf_lane, ntd, gen, c);
+            } else {
+                GenPhilox gen;
+                gen.seed = a.seed; gen.draw = a.draw; gen.lc = (uint32_t)lc; gen.tab.addr = smem_u32(bm);
+                gen.particle = (uint64_t)(a.first + i0 + lr);
+                transform_tiles<NTB, TRI, EXACT, 1>(lf_lane, ntd, gen, c);
+            }
+            cp_async_wait_all();  // own elements only: no warp barrier needed
+            double se0 = 0.0, se1 = 0.0, sg0 = 0.0, sg1 = 0.0;
+#pragma unroll
+            for (int mt = 0; mt < NTB; ++mt) {
+                if (EXACT || mt < ntd) {
+                    const int row = 8 * mt + lr;
+                    if (row < d) {
+                        const double2 xv = lds128(own + (uint32_t)(mt * 512));
+                        const double mrow = vm[row], crow = vc[row];
+                        // t*X + (m_noise + Z F^T): grouping of solver.py:667
+                        double2 xn;
+                        xn.x = __dadd_rn(__dmul_rn(a.t, xv.x), __dadd_rn(mrow, c[mt][0]));
+                        xn.y = __dadd_rn(__dmul_rn(a.t, xv.y), __dadd_rn(mrow, c[mt][1]));
+                        *reinterpret_cast<double2*>(a.x_new + (int64_t)row * a.ld + ip) = xn;
+                        se0 = fma(xn.x, xn.x, se0);
+                        se1 = fma(xn.y, xn.y, se1);
+                        sg0 = fma(crow, xn.x, sg0);
+                        sg1 = fma(crow, xn.y, sg1);
+                    }
+                }
+            }
+            if (wt + stride < nwt) prefetch(wt + stride);  // consumed after the next transform
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                se0 += __shfl_xor_sync(0xffffffffu, se0, o);
+                se1 += __shfl_xor_sync(0xffffffffu, se1, o);
+                sg0 += __shfl_xor_sync(0xffffffffu, sg0, o);
+                sg1 += __shfl_xor_sync(0xffffffffu, sg1, o);
+            }
+            if (lr == 0) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (ip + h < a.n) {
+                        const double s = h ? se1 : se0, gsum = h ? sg1 : sg0;
+                        if (a.e_new) a.e_new[ip + h] = 0.5 * (e_const + s);
+                        if (a.lsf_mode)
+                            a.g_new[ip + h] = (a.lsf_mode == 1)
+                                                  ? __dadd_rn(gsum, a.offset)
+                                                  : __dadd_rn(__ddiv_rn(-gsum, __dsqrt_rn((double)d)), a.offset);
+                    }
+                }
+            }
+        } else {
+            cp_async_wait_all();
+            __syncwarp();  // the warp's block has landed (every lane waited for its own copies)
+            GenStage gen;
+            gen.addr = stg_w + (uint32_t)((lc * 8 + lr) * 8);
+            gen.mean_addr = vm_addr + lc * 8;
+            gen.valid = (i0 + lr) < a.n;
+            transform_tiles<NTB, TRI, EXACT, 2>(lf_lane, ntd, gen, c);
+            __syncwarp();  // all B-fragment reads precede the refill of the block
+            if (wt + stride < nwt) prefetch(wt + stride);
+            // ---- q = |u|^2, log q, IS statistics (solver.py:672-674, 683-686, 843-846) -------------------
+            double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+            for (int mt = 0; mt < NTB; ++mt) {
+                q0 = fma(c[mt][0], c[mt][0], q0);
+                q1 = fma(c[mt][1], c[mt][1], q1);
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+                q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+            }
+            // one lane per particle: particle p = 2*lc' + h lives in the lanes with lc == lc'
+            const int srcl = (lane >> 1) & 3;
+            const double qa = __shfl_sync(0xffffffffu, q0, srcl), qb = __shfl_sync(0xffffffffu, q1, srcl);
+            const int64_t i = i0 + lane;
+            if (lane < 8 && i < a.n) {
+                const double qq = (lane & 1) ? qb : qa;
+                const double lq = -0.5 * (lq_const + qq);
+                if (a.logq) a.logq[i] = lq;
+                const double gi = a.g[i], ei = a.e[i];
+                const double r = __dsub_rn(-ei, lq);  // -e_fun - log_pdf  (solver.py:684)
+                if (isfinite(r)) expsums_add(is_acc, r, gi <= 0.0 ? 1.0 : 0.0);
+            }
+        }
+    }
+    if (MODE == 2) {
+        ExpSums blk = expsums_block_reduce(is_acc, sh);
+        if (tid == 0) {
+            double* p = a.small + 4 * (size_t)blockIdx.x;
+            p[0] = blk.m; p[1] = blk.s1; p[2] = blk.s2; p[3] = blk.cnt;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Gram kernel: unweighted and weighted shifted Grams of an ensemble in one pass
+// ---------------------------------------------------------------------------------------
+struct GramArgs {
+    const double* x;
+    int64_t n, ld;
+    int d;
+    const double* shift;  // d doubles or NULL (0)
+    const double* g;      // failure count (or NULL)
+    const double* a;      // log-weights beta*l (WEIGHTED)
+    const double* wmax;   // device scalar (WEIGHTED)
+    double* part_u;       // [(cta*KS + grp)][T][64]
+    double* part_w;
+    double* small;        // per-CTA failure count
+    GramPlan plan;
+};
+
+struct GramRegs2 {
+    uint32_t offR, offC;  // byte offsets (inside a tile buffer) of this lane's element of the first row / col tile
+    int flags;            // 15: off-diagonal 2x2, 13: diagonal 2x2, 3: one row x two cols, 1: single tile, 0: none
+};
+
+// one k-pair (8 particles) of one 8x8 output tile: acc += A(:, 2 particles) B(2 particles, :)
+__device__ __forceinline__ void dmma2(double (&acc)[2], const double2& a, const double2& b) {
+    dmma(acc[0], acc[1], a.x, b.x);
+    dmma(acc[0], acc[1], a.y, b.y);
+}
+
+// Gram of UPG k-pairs of a shared tile into the warp's macro tiles; macro-outer / k-inner so that every branch on the
+// macro type is taken once per tile and the k loop is straight-line code with immediate offsets.
+template <int MAXM, int S, int UPG, bool WEIGHTED>
+__device__ __forceinline__ void gram2_accumulate(uint32_t buf, uint32_t wts, const GramRegs2 (&gr)[MAXM],
+                                                 double (&au)[MAXM][4][2], double (&aw)[MAXM][4][2]) {
+    constexpr uint32_t R1 = 8 * S * 8;  // second tile of a macro tile: 8 rows further down
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+        const int f = gr[m].flags;
+        if (f == 0) continue;
+        const uint32_t ra = buf + gr[m].offR, ca = buf + gr[m].offC;
+        if (f == 15) {  // off-diagonal 2x2
+#pragma unroll
+            for (int u = 0; u < UPG; ++u) {
+                const double2 a0 = lds128(ra + u * 64), a1 = lds128(ra + u * 64 + R1);
+                const double2 b0 = lds128(ca + u * 64), b1 = lds128(ca + u * 64 + R1);
+                dmma2(au[m][0], a0, b0);
+                dmma2(au[m][1], a0, b1);
+                dmma2(au[m][2], a1, b0);
+                dmma2(au[m][3], a1, b1);
+                if (WEIGHTED) {
+                    const double2 w = lds128(wts + u * 64);
+                    const double2 a0w = make_double2(a0.x * w.x, a0.y * w.y), a1w = make_double2(a1.x * w.x, a1.y * w.y);
+                    dmma2(aw[m][0], a0w, b0);
+                    dmma2(aw[m][1], a0w, b1);
+                    dmma2(aw[m][2], a1w, b0);
+                    dmma2(aw[m][3], a1w, b1);
+                }
+            }
+        } else if (f == 13) {  // diagonal 2x2: tiles (0,0), (1,0), (1,1); B fragments are the A fragments
+#pragma unroll
+            for (int u = 0; u < UPG; ++u) {
+                const double2 a0 = lds128(ra + u * 64), a1 = lds128(ra + u * 64 + R1);
+                dmma2(au[m][0], a0, a0);
+                dmma2(au[m][2], a1, a0);
+                dmma2(au[m][3], a1, a1);
+                if (WEIGHTED) {
+                    const double2 w = lds128(wts + u * 64);
+                    const double2 a0w = make_double2(a0.x * w.x, a0.y * w.y), a1w = make_double2(a1.x * w.x, a1.y * w.y);
+                    dmma2(aw[m][0], a0w, a0);
+                    dmma2(aw[m][2], a1w, a0);
+                    dmma2(aw[m][3], a1w, a1);
+                }
+            }
+        } else if (f == 3) {  // one row tile, two column tiles
+#pragma unroll
+            for (int u = 0; u < UPG; ++u) {
+                const double2 a0 = lds128(ra + u * 64);
+                const double2 b0 = lds128(ca + u * 64), b1 = lds128(ca + u * 64 + R1);
+                dmma2(au[m][0], a0, b0);
+                dmma2(au[m][1], a0, b1);
+                if (WEIGHTED) {
+                    const double2 w = lds128(wts + u * 64);
+                    const double2 a0w = make_double2(a0.x * w.x, a0.y * w.y);
+                    dmma2(aw[m][0], a0w, b0);
+                    dmma2(aw[m][1], a0w, b1);
+                }
+            }
+        } else {  // f == 1: single tile
+#pragma unroll
+            for (int u = 0; u < UPG; ++u) {
+                const double2 a0 = lds128(ra + u * 64);
+                const double2 b0 = lds128(ca + u * 64);
+                dmma2(au[m][0], a0, b0);
+                if (WEIGHTED) {
+                    const double2 w = lds128(wts + u * 64);
+                    dmma2(aw[m][0], make_double2(a0.x * w.x, a0.y * w.y), b0);
+                }
+            }
+        }
+    }
+}
+
+template <int MAXM>
+__device__ __forceinline__ void gram2_store(double* __restrict__ part, const GramPlan& plan, int wi, int nmac, int nta,
+                                            int lr, int lc, const double (&acc)[MAXM][4][2]) {
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+        if (m < nmac) {
+            const int code = plan.mac[wi][m];
+            const int mr = code & 0xff, mc = code >> 8;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int mt = 2 * mr + (q >> 1), nt = 2 * mc + (q & 1);
+                if (mt < nta && nt <= mt)
+                    *reinterpret_cast<double2*>(part + (size_t)tri_index(mt, nt) * 64 + lr * 8 + 2 * lc) =
+                        make_double2(acc[m][q][0], acc[m][q][1]);
+            }
+        }
+    }
+}
+
+template <int NTB, int NW, int MAXM, int KS, bool EXACT, bool WEIGHTED>
+__global__ void __launch_bounds__(NW * 32, 1) k_gram2(const GramArgs a) {
+    constexpr int MT = NW * 32;
+    constexpr int P = NW * 8;   // particles per CTA tile
+    constexpr int S = P + 8;    // row stride of the shared tile (8 mod 16 doubles)
+    constexpr int ROWS = 8 * NTB;
+    constexpr uint32_t BUF_BYTES = ROWS * S * 8;
+    constexpr int WG = NW / KS, UPG = P / 8 / KS;
+    extern __shared__ double sm[];
+    const int d = a.d, ntd = (d + 7) >> 3, nta = (d + 8) >> 3;
+    double* Ys = sm;                 // two tile buffers
+    double* wt = Ys + 2 * ROWS * S;  // two weight vectors
+    double* vs = wt + 2 * P;         // shift
+    __shared__ double red[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lc = lane & 3;
+    const int grp = warp / WG, wi = warp % WG;
+
+    for (int j = tid; j < 8 * NTB; j += MT) vs[j] = (j < d && a.shift) ? a.shift[j] : 0.0;
+    for (int idx = tid; idx < 2 * ROWS * S + 2 * P; idx += MT) Ys[idx] = 0.0;
+    const uint32_t ys_addr = smem_u32(Ys), wt_addr = smem_u32(wt);
+    GramRegs2 gr[MAXM];
+    const int nmac = a.plan.nmac[wi];
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+        const bool live = m < nmac;
+        const int code = live ? a.plan.mac[wi][m] : 0;
+        const int mr = code & 0xff, mc = code >> 8;
+        // the k-split group's first k-pair is folded into the offsets
+        gr[m].offR = (uint32_t)(((16 * mr + lr) * S + 2 * lc) * 8 + grp * UPG * 64);
+        gr[m].offC = (uint32_t)(((16 * mc + lr) * S + 2 * lc) * 8 + grp * UPG * 64);
+        const bool r1 = 2 * mr + 1 < nta, c1 = 2 * mc + 1 < nta, diag = mr == mc;
+        gr[m].flags = live ? (1 | ((c1 && !diag) ? 2 : 0) | (r1 ? 4 : 0) | ((r1 && c1) ? 8 : 0)) : 0;
+    }
+    double au[MAXM][4][2], aw[MAXM][4][2];
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) au[m][q][0] = au[m][q][1] = aw[m][q][0] = aw[m][q][1] = 0.0;
+    __syncthreads();
+
+    const double wmax = WEIGHTED ? a.wmax[0] : 0.0;
+    double n_fail = 0.0;
+    const int pw = warp * 8;
+    const int64_t ntiles = (a.n + P - 1) / P;
+    const uint32_t own_off = (uint32_t)((lr * S + pw + 2 * lc) * 8);
+
+    auto prefetch = [&](int64_t i0, uint32_t buf) {  // every lane fetches exactly the elements it will rewrite
+        const int64_t ip = i0 + pw + 2 * lc;
+        if (ip < a.ld) {
+#pragma unroll
+            for (int mt = 0; mt < NTB; ++mt) {
+                const int row = 8 * mt + lr;
+                if (row < d) cp_async16(buf + own_off + (uint32_t)(8 * mt * S * 8), a.x + (int64_t)row * a.ld + ip);
+            }
+        }
+    };
+    // per-particle scalars of the next tile travel in registers (threads 0..P-1 own one particle each)
+    double a_nxt = 0.0, g_nxt = 1.0;
+    auto fetch_scalars = [&](int64_t i0) {
+        const int64_t i = i0 + tid;
+        const bool v = tid < P && i < a.n;
+        a_nxt = (WEIGHTED && v) ? a.a[i] : 0.0;
+        g_nxt = (v && a.g) ? a.g[i] : 1.0;
+    };
+    if ((int64_t)blockIdx.x < ntiles) {
+        prefetch((int64_t)blockIdx.x * P, ys_addr);
+        fetch_scalars((int64_t)blockIdx.x * P);
+    }
+
+    int parity = 0;
+    for (int64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x, parity ^= 1) {
+        const int64_t i0 = tix * P;
+        const uint32_t buf = ys_addr + (parity ? BUF_BYTES : 0u);
+        const uint32_t wbuf = wt_addr + (parity ? (uint32_t)(P * 8) : 0u);
+        const int64_t ip = i0 + pw + 2 * lc;
+        const bool v0 = ip < a.n, v1 = ip + 1 < a.n;
+        cp_async_wait_all();
+        // ---- rewrite this lane's elements: y = x - shift, zero padding, augmented row of ones --------------
+#pragma unroll
+        for (int mt = 0; mt < NTB; ++mt) {
+            if (EXACT || mt < ntd) {
+                const int row = 8 * mt + lr;
+                const bool rv = row < d;
+                const uint32_t sa = buf + own_off + (uint32_t)(8 * mt * S * 8);
+                const double2 xv = lds128(sa);
+                const double srow = vs[row];
+                double2 y;
+                y.x = (rv && v0) ? xv.x - srow : 0.0;  // select, not multiply: padded lanes may hold anything
+                y.y = (rv && v1) ? xv.y - srow : 0.0;
+                if (row == d) {
+                    y.x = v0 ? 1.0 : 0.0;
+                    y.y = v1 ? 1.0 : 0.0;
+                }
+                sts128(sa, y);
+            }
+        }
+        if (nta > ntd && lr == 0)  // d % 8 == 0: the augmented row lives in a tile of its own
+            sts128(buf + (uint32_t)((d * S + pw + 2 * lc) * 8), make_double2(v0 ? 1.0 : 0.0, v1 ? 1.0 : 0.0));
+        if (tid < P) {
+            const bool v = i0 + tid < a.n;
+            if (WEIGHTED) {
+                const double wv = (v && isfinite(a_nxt)) ? exp(a_nxt - wmax) : 0.0;
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"(wbuf + (uint32_t)tid * 8u), "d"(wv) : "memory");
+            }
+            n_fail += (v && g_nxt <= 0.0) ? 1.0 : 0.0;
+        }
+        __syncthreads();  // tile k complete; everybody is done with the other buffer (Gram k-1)
+        if (tix + gridDim.x < ntiles) {
+            prefetch((tix + gridDim.x) * P, ys_addr + (parity ? 0u : BUF_BYTES));
+            fetch_scalars((tix + gridDim.x) * P);
+        }
+        gram2_accumulate<MAXM, S, UPG, WEIGHTED>(buf, wbuf + (uint32_t)((grp * UPG * 8 + 2 * lc) * 8), gr, au, aw);
+    }
+    const int T = nta * (nta + 1) / 2;
+    const size_t poff = ((size_t)blockIdx.x * KS + grp) * T * 64;
+    gram2_store<MAXM>(a.part_u + poff, a.plan, wi, nmac, nta, lr, lc, au);
+    if (WEIGHTED) gram2_store<MAXM>(a.part_w + poff, a.plan, wi, nmac, nta, lr, lc, aw);
+    n_fail = block_sum(n_fail, red);
+    if (tid == 0) a.small[blockIdx.x] = n_fail;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct SplitCfg {
+    int ntb;
+    int xf_nw;                 // warps of the transform kernels
+    int g_nw, g_maxm, g_ks;    // Gram kernel
+};
+
+static int split_min_d() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("REE_SPLIT_MIN_D");  // tuning / test hook: dimensions below run the fused sweeps
+        v = e ? atoi(e) : 56;
+        if (v < 32) v = 32;
+    }
+    return v;
+}
+
+static bool pick_split(int d, SplitCfg& c) {
+    if (d < split_min_d()) return false;
+    if (d <= 55) c = {7, 16, 8, 3, 2};
+    else if (d <= 103) c = {13, 16, 12, 3, 1};
+    else return false;
+    return true;
+}
+
+bool ree_split_supported(int d) {
+    SplitCfg c;
+    return pick_split(d, c);
+}
+
+template <int MODE, int NTB, int NW, bool EXACT, bool TRI>
+static int launch_xf(const XfArgs& a, int grid, cudaStream_t st) {
+    constexpr size_t smem = ((size_t)lf_doubles<NTB, TRI>() + (size_t)NW * 8 * NTB * 8 + 2 * 8 * NTB +
+                             (MODE == 1 ? BM_TABLE_DOUBLES + 2 : 0)) * sizeof(double);
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    auto kern = k_xform<MODE, NTB, NW, EXACT, TRI>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, NW * 32, smem, st>>>(a);
+    return ree_check_launch(MODE == 1 ? "k_xform<1>" : "k_xform<2>");
+}
+
+template <int MODE, int NTB, int NW, bool TRI>
+static int launch_xf_exact(const XfArgs& a, int grid, cudaStream_t st) {
+    if ((a.d + 7) / 8 == NTB) return launch_xf<MODE, NTB, NW, true, TRI>(a, grid, st);
+    return launch_xf<MODE, NTB, NW, false, TRI>(a, grid, st);
+}
+
+template <int MODE, bool TRI>
+static int launch_xf_bucket(const SplitCfg& c, const XfArgs& a, cudaStream_t st) {
+    const int sms = ree_grid_ctas() / 2;  // persistent: one CTA per SM
+    const int64_t nwt = (a.n + 7) / 8;
+    if (c.ntb == 7) {
+        const int64_t want = (nwt + 15) / 16;
+        return launch_xf_exact<MODE, 7, 16, TRI>(a, (int)(want < sms ? want : sms), st);
+    }
+    if constexpr (TRI) {
+        const int64_t want = (nwt + 15) / 16;
+        return launch_xf_exact<MODE, 13, 16, TRI>(a, (int)(want < sms ? want : sms), st);
+    } else {  // dense parity-mode factor: 86 KB of fragments, fewer warps
+        const int64_t want = (nwt + 11) / 12;
+        return launch_xf_exact<MODE, 13, 12, TRI>(a, (int)(want < sms ? want : sms), st);
+    }
+}
+
+template <int NTB, int NW, int MAXM, int KS, bool EXACT, bool WEIGHTED>
+static int launch_g2(const GramArgs& a, int grid, cudaStream_t st) {
+    constexpr int P = NW * 8, S = P + 8, ROWS = 8 * NTB;
+    constexpr size_t smem = ((size_t)2 * ROWS * S + 2 * P + 8 * NTB) * sizeof(double);
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    auto kern = k_gram2<NTB, NW, MAXM, KS, EXACT, WEIGHTED>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, NW * 32, smem, st>>>(a);
+    return ree_check_launch("k_gram2");
+}
+
+template <int NTB, int NW, int MAXM, int KS>
+static int launch_g2_variants(const GramArgs& a, int grid, bool weighted, cudaStream_t st) {
+    const bool exact = (a.d + 7) / 8 == NTB;
+    if (weighted) return exact ? launch_g2<NTB, NW, MAXM, KS, true, true>(a, grid, st)
+                               : launch_g2<NTB, NW, MAXM, KS, false, true>(a, grid, st);
+    return exact ? launch_g2<NTB, NW, MAXM, KS, true, false>(a, grid, st)
+                 : launch_g2<NTB, NW, MAXM, KS, false, false>(a, grid, st);
+}
+
+// ---- entry points used by ree_step.cu -----------------------------------------------------------
+int ree_split_step(const double* x, double* x_new, int64_t n, int d, int64_t ld, double t, const double* m_noise,
+                   const double* F, int tri, const double* z, uint64_t seed, uint64_t draw, int64_t first, int lsf_mode,
+                   const double* coef, double offset, double* g_new, double* e_new, cudaStream_t st) {
+    SplitCfg c;
+    if (!pick_split(d, c)) return ree_set_error(REE_E_UNSUPPORTED, "split path: unsupported dimension");
+    XfArgs a{};
+    a.x = x; a.n = n; a.ld = ld; a.d = d; a.A = F; a.x_new = x_new; a.t = t; a.m_noise = m_noise; a.z = z;
+    a.seed = seed; a.draw = draw; a.first = first; a.lsf_mode = lsf_mode; a.coef = coef; a.offset = offset;
+    a.g_new = g_new; a.e_new = e_new;
+    return tri ? launch_xf_bucket<1, true>(c, a, st) : launch_xf_bucket<1, false>(c, a, st);
+}
+
+int ree_split_maha(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* e, const double* mean,
+                   const double* Linv, const double* logdet, double* logq, double* ws_small, double* is4,
+                   cudaStream_t st) {
+    SplitCfg c;
+    if (!pick_split(d, c)) return ree_set_error(REE_E_UNSUPPORTED, "split path: unsupported dimension");
+    XfArgs a{};
+    a.x = x; a.n = n; a.ld = ld; a.d = d; a.A = Linv; a.g = g; a.e = e; a.mean = mean; a.logdet = logdet;
+    a.logq = logq; a.small = ws_small;
+    const int sms = ree_grid_ctas() / 2;
+    const int64_t want = ((n + 7) / 8 + 15) / 16;
+    const int grid = (int)(want < sms ? want : sms);
+    int rc = launch_xf_bucket<2, true>(c, a, st);
+    if (rc) return rc;
+    return ree_mma_merge_small(ws_small, grid, is4, st);
+}
+
+// sums_u = [sum y | sum y y^T | #{g <= 0} | n], sums_w = [sum w y | sum w y y^T | sum w | 0]   (y = x - shift)
+int ree_split_moments(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* a_vec,
+                      const double* wmax, const double* shift, double* ws_big, double* ws_small, double* sums_u,
+                      double* sums_w, cudaStream_t st) {
+    SplitCfg c;
+    if (!pick_split(d, c)) return ree_set_error(REE_E_UNSUPPORTED, "split path: unsupported dimension");
+    const bool weighted = sums_w != nullptr;
+    const int nta = (d + 8) / 8, T = nta * (nta + 1) / 2, P = c.g_nw * 8;
+    const int sms = ree_grid_ctas() / 2;
+    const int64_t ntiles = (n + P - 1) / P;
+    const int grid = (int)(ntiles < sms ? ntiles : sms);
+    GramArgs a{};
+    a.x = x; a.n = n; a.ld = ld; a.d = d; a.shift = shift; a.g = g; a.a = a_vec; a.wmax = wmax;
+    a.part_u = ws_big;
+    a.part_w = ws_big + (size_t)grid * c.g_ks * T * 64;
+    a.small = ws_small;
+    make_plan(a.plan, nta, c.g_nw / c.g_ks, c.g_maxm);
+    int rc = (c.ntb == 7) ? launch_g2_variants<7, 8, 3, 2>(a, grid, weighted, st)
+                          : launch_g2_variants<13, 12, 3, 1>(a, grid, weighted, st);
+    if (rc) return rc;
+    rc = ree_mma_unpack(a.part_u, grid * c.g_ks, d, 0, sums_u, st);
+    if (rc) return rc;
+    rc = ree_mma_sum_small(ws_small, grid, sums_u + d + (size_t)d * d, st);
+    if (rc || !weighted) return rc;
+    return ree_mma_unpack(a.part_w, grid * c.g_ks, d, 1, sums_w, st);
+}

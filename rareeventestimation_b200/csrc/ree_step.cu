@@ -21,6 +21,17 @@ int ree_mma_maha(const double* x, int64_t n, int d, int64_t ld, const double* g,
 int ree_mma_sums(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* shift, double* ws_big,
                  double* ws_small, double* sums, cudaStream_t st);
 
+bool ree_split_supported(int d);
+int ree_split_step(const double* x, double* x_new, int64_t n, int d, int64_t ld, double t, const double* m_noise,
+                   const double* F, int tri, const double* z, uint64_t seed, uint64_t draw, int64_t first, int lsf_mode,
+                   const double* coef, double offset, double* g_new, double* e_new, cudaStream_t st);
+int ree_split_maha(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* e, const double* mean,
+                   const double* Linv, const double* logdet, double* logq, double* ws_small, double* is4,
+                   cudaStream_t st);
+int ree_split_moments(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* a_vec,
+                      const double* wmax, const double* shift, double* ws_big, double* ws_small, double* sums_u,
+                      double* sums_w, cudaStream_t st);
+
 #define TP 128  // particles per CTA tile in the contraction kernels
 #define JB 4    // output dims per register block
 
@@ -304,16 +315,39 @@ extern "C" int ree_ensemble_sums(const double* x, int64_t n, int d, int64_t ld, 
     return launch_gram(x, n, d, ld, shift, nullptr, g, workspace, sums, ree_stream(stream));
 }
 
+extern "C" int ree_cbree_moments(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* a,
+                                 const double* wmax, const double* shift, double* workspace, double* sums_u,
+                                 double* sums_w, void* stream) {
+    if (!x || !workspace || !sums_u || d < 1 || n < 1 || ld < n || (sums_w && (!a || !wmax)))
+        return ree_set_error(REE_E_BADARG, "ree_cbree_moments: bad argument");
+    if (!ree_split_supported(d))
+        return ree_set_error(REE_E_UNSUPPORTED, "ree_cbree_moments: only where ree_fused_path(d) == 2");
+    return ree_split_moments(x, n, d, ld, g, a, wmax, shift, workspace + ws_big_offset(), workspace + REE_WS_HEADER,
+                             sums_u, sums_w, ree_stream(stream));
+}
+
 extern "C" int ree_cbree_step(const double* x, double* x_new, int64_t n, int d, int64_t ld, double t,
                               const double* m_noise, const double* F, int noise_mode, const double* z, uint64_t seed,
                               uint64_t draw, int64_t first_particle, const ree_lsf* lsf, const double* shift,
                               double* g_new, double* e_new, double* workspace, double* sums, void* stream) {
-    if (!x || !x_new || !m_noise || !F || !workspace || !sums || d < 1 || n < 1 || ld < n)
+    if (!x || !x_new || !m_noise || !F || !workspace || d < 1 || n < 1 || ld < n)
         return ree_set_error(REE_E_BADARG, "ree_cbree_step: bad argument");
+    if (!sums && !ree_split_supported(d))
+        return ree_set_error(REE_E_BADARG, "ree_cbree_step: sums may be NULL only where ree_fused_path(d) == 2");
     if (noise_mode == REE_NOISE_INJECT && !z) return ree_set_error(REE_E_BADARG, "ree_cbree_step: INJECT needs z");
     cudaStream_t st = ree_stream(stream);
     const bool fused_lsf = lsf && lsf->kind == REE_LSF_AFFINE;
     if (lsf && lsf->kind != REE_LSF_EXTERNAL && !g_new) return ree_set_error(REE_E_BADARG, "ree_cbree_step: g_new is NULL");
+    if (!sums) {  // split path: transform only
+        const int tri = (noise_mode == REE_NOISE_PHILOX) ? 1 : 0;
+        int lsf_mode = fused_lsf ? (lsf->coef ? 1 : 2) : 0;
+        int rc = ree_split_step(x, x_new, n, d, ld, t, m_noise, F, tri, noise_mode == REE_NOISE_INJECT ? z : nullptr, seed,
+                                draw, first_particle, lsf_mode, fused_lsf ? lsf->coef : nullptr,
+                                fused_lsf ? lsf->offset : 0.0, g_new, e_new, st);
+        if (rc) return rc;
+        if (lsf && lsf->kind != REE_LSF_EXTERNAL && !fused_lsf) return ree_lsf_launch(lsf, x_new, n, ld, g_new, st);
+        return 0;
+    }
     if (ree_mma_supported(d)) {
         // a Cholesky factor is lower triangular; the parity-mode factor U*sqrt(S) is dense
         const int tri = (noise_mode == REE_NOISE_PHILOX) ? 1 : 0;
@@ -354,9 +388,15 @@ extern "C" int ree_cbree_maha(const double* x, int64_t n, int d, int64_t ld, con
                               const double* mean, const double* Linv, const double* logdet, double sigma, double beta,
                               int tgt_kind, const double* wmax, double* logq, double* w, double* workspace,
                               double* sums, double* is4, void* stream) {
-    if (!x || !g || !e || !mean || !Linv || !logdet || !wmax || !workspace || !sums || !is4 || d < 1 || n < 1)
+    if (!x || !g || !e || !mean || !Linv || !logdet || !workspace || !is4 || d < 1 || n < 1)
         return ree_set_error(REE_E_BADARG, "ree_cbree_maha: bad argument");
     cudaStream_t st = ree_stream(stream);
+    if (!sums) {
+        if (!ree_split_supported(d))
+            return ree_set_error(REE_E_BADARG, "ree_cbree_maha: sums may be NULL only where ree_fused_path(d) == 2");
+        return ree_split_maha(x, n, d, ld, g, e, mean, Linv, logdet, logq, workspace + REE_WS_HEADER, is4, st);
+    }
+    if (!wmax) return ree_set_error(REE_E_BADARG, "ree_cbree_maha: wmax is NULL");
     if (ree_mma_supported(d))
         return ree_mma_maha(x, n, d, ld, g, e, mean, Linv, logdet, sigma, beta, tgt_kind, wmax, logq, w,
                             workspace + ws_big_offset(), workspace + REE_WS_HEADER, sums, is4, st);

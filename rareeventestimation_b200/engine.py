@@ -271,12 +271,13 @@ class Engine:
         return out
 
     # -- reductions (return device 4-vectors, already combined across ranks) ----- #
-    def reduce_ess(self, ens: Ensemble, sigma, beta, kind, out=None, use_e=True) -> torch.Tensor:
+    def reduce_ess(self, ens: Ensemble, sigma, beta, kind, out=None, use_e=True, a_out=None) -> torch.Tensor:
+        """`a_out` (ld doubles) receives the log-weights beta*l the split path's moments kernel consumes."""
         out = out if out is not None else self.empty(4)
         ws = self.workspace(ens.d)
         check(self.lib.ree_reduce_ess(ens.g.data_ptr(), ens.e.data_ptr() if use_e else None, ens.n, float(sigma),
-                                      float(beta), kind, ws.data_ptr(), out.data_ptr(), self.stream),
-              "ree_reduce_ess")
+                                      float(beta), kind, a_out.data_ptr() if a_out is not None else None,
+                                      ws.data_ptr(), out.data_ptr(), self.stream), "ree_reduce_ess")
         return self.comm.combine_expsums_(out)
 
     def reduce_cvar(self, ens: Ensemble, sigma_new, sigma_old, kind, out=None) -> torch.Tensor:
@@ -310,8 +311,28 @@ class Engine:
                                          sums.data_ptr(), self.stream), "ree_ensemble_sums")
         return self.comm.allreduce_sum_(sums)
 
+    def path(self, d: int) -> int:
+        """1: fused sweeps, 2: split transform / moments / Mahalanobis kernels, 0: modular kernels."""
+        return int(self.lib.ree_fused_path(int(d)))
+
+    def cbree_moments(self, ens: Ensemble, a: Optional[torch.Tensor], wmax: Optional[torch.Tensor],
+                      shift: Optional[torch.Tensor], sums_uw: torch.Tensor, weighted=True):
+        """Split path: unweighted and weighted shifted sums of one ensemble in one pass.  `sums_uw` holds both
+        (2 x sums_len) so that one all_reduce combines them across ranks."""
+        ws = self.workspace(ens.d)
+        slen = ens.d + ens.d * ens.d + 2
+        su, sw = sums_uw[0:slen], sums_uw[slen:2 * slen]
+        check(self.lib.ree_cbree_moments(ens.X.data_ptr(), ens.n, ens.d, ens.ld,
+                                         ens.g.data_ptr() if ens.g is not None else None,
+                                         a.data_ptr() if weighted else None, wmax.data_ptr() if weighted else None,
+                                         shift.data_ptr() if shift is not None else None, ws.data_ptr(),
+                                         su.data_ptr(), sw.data_ptr() if weighted else None, self.stream),
+              "ree_cbree_moments")
+        self.comm.allreduce_sum_(sums_uw if weighted else su)
+        return su, sw
+
     def cbree_step(self, src: Ensemble, dst: Ensemble, t: float, m_noise: torch.Tensor, F: torch.Tensor,
-                   lsf: Optional[DeviceLsf], shift: Optional[torch.Tensor], sums: torch.Tensor,
+                   lsf: Optional[DeviceLsf], shift: Optional[torch.Tensor], sums: Optional[torch.Tensor],
                    z: Optional[Ensemble] = None, seed: int = 0, draw: int = 0, reduce=True):
         ws = self.workspace(src.d)
         s = lsf.struct() if lsf is not None else None
@@ -323,9 +344,9 @@ class Engine:
                                       z.X.data_ptr() if z is not None else None, seed & (2**64 - 1), draw,
                                       src.first, C.byref(s) if s is not None else None,
                                       shift.data_ptr() if shift is not None else None, dst.g.data_ptr(),
-                                      dst.e.data_ptr(), ws.data_ptr(), sums.data_ptr(), self.stream),
-              "ree_cbree_step")
-        if reduce:
+                                      dst.e.data_ptr(), ws.data_ptr(), sums.data_ptr() if sums is not None else None,
+                                      self.stream), "ree_cbree_step")
+        if reduce and sums is not None:
             self.comm.allreduce_sum_(sums)
         return sums
 
@@ -344,15 +365,17 @@ class Engine:
     def cbree_maha(self, ens: Ensemble, mean, Linv, logdet, sigma, beta, kind, wmax, sums, is4, w=None, logq=None):
         """Sweep 2.  The weighted sums come back shifted by ``mean``."""
         ws = self.workspace(ens.d)
-        if w is None and not self.lib.ree_fused_path(ens.d):
+        if w is None and sums is not None and not self.lib.ree_fused_path(ens.d):
             w = self.empty(ens.ld)
         check(self.lib.ree_cbree_maha(ens.X.data_ptr(), ens.n, ens.d, ens.ld, ens.g.data_ptr(), ens.e.data_ptr(),
                                       mean.data_ptr(), Linv.data_ptr(), logdet.data_ptr(), float(sigma),
-                                      float(beta), kind, wmax.data_ptr(),
+                                      float(beta), kind, wmax.data_ptr() if wmax is not None else None,
                                       logq.data_ptr() if logq is not None else None,
                                       w.data_ptr() if w is not None else None, ws.data_ptr(),
-                                      sums.data_ptr(), is4.data_ptr(), self.stream), "ree_cbree_maha")
-        self.comm.allreduce_sum_(sums)
+                                      sums.data_ptr() if sums is not None else None, is4.data_ptr(), self.stream),
+              "ree_cbree_maha")
+        if sums is not None:  # split path (sums None): only the IS statistics cross ranks
+            self.comm.allreduce_sum_(sums)
         self.comm.combine_expsums_(is4)
 
 

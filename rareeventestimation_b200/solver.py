@@ -370,16 +370,26 @@ class CBREE(Solver):
         stats, is4, ess4 = res[o:o + 4], res[o + 4:o + 8], res[o + 8:o + 12]
         tails = res[o + 12:o + 16]
         L, Linv = eng.empty(d * d), eng.empty(d * d)
-        if sums_ready is None:
-            sums_u = eng.empty(slen)
-            eng.ensemble_sums(dev, shift_u, sums_u)
+        if eng.path(d) == 2 and sums_ready is None:
+            # split path: log-weights + softmax shift, both Grams in one pass, factorisation, Mahalanobis / IS pass
+            a_vec = eng.scratch("logw", dev.ld)
+            eng.reduce_ess(dev, cache.sigma, cache.beta, kind, out=ess4, a_out=a_vec)
+            sums_uw = eng.empty(2 * slen)
+            sums_u, sums_w = eng.cbree_moments(dev, a_vec, ess4[0:1], shift_u, sums_uw)
+            eng.moments_chol(sums_u, shift_u, d, 1, False, mean, cov, L, Linv, stats)
+            eng.cbree_maha(dev, mean, Linv, stats[0:1], cache.sigma, cache.beta, kind, None, None, is4)
+            eng.moments_chol(sums_w, shift_u, d, 0, True, m_w, C_w)
         else:
-            sums_u = sums_ready
-        eng.moments_chol(sums_u, shift_u, d, 1, False, mean, cov, L, Linv, stats)
-        eng.reduce_ess(dev, cache.sigma, cache.beta, kind, out=ess4)
-        sums_w = eng.empty(slen)
-        eng.cbree_maha(dev, mean, Linv, stats[0:1], cache.sigma, cache.beta, kind, ess4[0:1], sums_w, is4)
-        eng.moments_chol(sums_w, mean, d, 0, True, m_w, C_w)  # weighted sums are centred at the unweighted mean
+            if sums_ready is None:
+                sums_u = eng.empty(slen)
+                eng.ensemble_sums(dev, shift_u, sums_u)
+            else:
+                sums_u = sums_ready
+            eng.moments_chol(sums_u, shift_u, d, 1, False, mean, cov, L, Linv, stats)
+            eng.reduce_ess(dev, cache.sigma, cache.beta, kind, out=ess4)
+            sums_w = eng.empty(slen)
+            eng.cbree_maha(dev, mean, Linv, stats[0:1], cache.sigma, cache.beta, kind, ess4[0:1], sums_w, is4)
+            eng.moments_chol(sums_w, mean, d, 0, True, m_w, C_w)  # weighted sums are centred at the unweighted mean
         tails[0:2].copy_(sums_u[d + d * d:])
         tails[2:4].copy_(sums_w[d + d * d:])
         host = res.cpu().numpy()  # the one synchronising D2H of the iteration
@@ -524,7 +534,8 @@ class CBREE(Solver):
         m_noise = (1 - t) * cache.weighted_mean
         scale = (1 - t**2) * (1 + cache.beta)
         dst = eng.alloc_ensemble(n, d, first=src.first)
-        sums = eng.empty(d + d * d + 2)
+        split = eng.path(d) == 2  # transform only; the moments come from the one-pass Gram kernel afterwards
+        sums = None if split else eng.empty(d + d * d + 2)
         # conditioning shifts of the one-pass Grams: predicted unweighted mean, previous weighted mean
         shift_u_h = t * cache.ens_mean + m_noise
         small = eng.to_device(np.concatenate([m_noise, shift_u_h, cache.weighted_mean]))
@@ -549,7 +560,7 @@ class CBREE(Solver):
                            draw=_STREAM_STEP + self._step_draws)
         if desc is None or not self._device_energy:
             self._evaluate_external(dst, desc is None, not self._device_energy)
-            if desc is None:
+            if desc is None and sums is not None:
                 sums[d + d * d: d + d * d + 1].copy_(eng.count_failed(dst))
         self.lsf.counter += self._n_total
         new = CBREECache(eng, dst, mixture_model=MixtureModel(1))

@@ -78,7 +78,7 @@ def test_sis_weight_reduction_and_scan(eng, n):
     gd = eng.to_device(g)
     ws, out4 = eng.workspace(4), eng.empty(4)
     w = eng.empty(n)
-    for s_new, s_old, mode in [(0.7, -1.0, 0), (0.4, 0.7, 0), (0.4, -1.0, 1)]:
+    for s_new, s_old, mode in [(0.4, -1.0, 1), (0.7, -1.0, 0), (0.4, 0.7, 0)]:  # w ends as tempering weights
         assert eng.lib.ree_sis_reduce(gd.data_ptr(), n, s_new, s_old, mode, w.data_ptr(), ws.data_ptr(),
                                       out4.data_ptr(), eng.stream) == 0
         if mode == 0:

@@ -217,7 +217,7 @@ class ReplayRng:
 
 
 CASES = [("affine", 4, 2000), ("oscillator", 6, 3000), ("affine", 100, 1500), ("convex", 2, 1000),
-         ("affine", 37, 1111)]
+         ("affine", 37, 1111), ("affine", 64, 1200), ("affine", 103, 900)]
 
 
 def make_problem(ree, kind, d):

@@ -66,6 +66,18 @@ timeit("ree_cbree_maha", lambda: eng.cbree_maha(X, mean, Linv, stats[0:1], 2.0, 
        n * (8 * d + 16), gram_flops + tri_flops)
 timeit("ree_cbree_step(philox)", lambda: eng.cbree_step(X, Y, 0.6, m_noise, F, lsf, None, sums, seed=7, draw=3),
        n * (16 * d + 16), gram_flops + tri_flops)
+if eng.path(d) == 2:
+    a_vec = eng.empty(X.ld)
+    sums_uw = eng.empty(2 * slen)
+    eng.reduce_ess(X, 2.0, 1.0, 0, out=ess4, a_out=a_vec)
+    timeit("split: ree_cbree_step(philox, transform only)",
+           lambda: eng.cbree_step(X, Y, 0.6, m_noise, F, lsf, None, None, seed=7, draw=3), n * (16 * d + 16), tri_flops)
+    timeit("split: ree_cbree_moments(both Grams)",
+           lambda: eng.cbree_moments(X, a_vec, ess4[0:1], None, sums_uw), n * (8 * d + 16), 2 * gram_flops)
+    timeit("split: ree_cbree_moments(unweighted)",
+           lambda: eng.cbree_moments(X, None, None, None, sums_uw, weighted=False), n * (8 * d + 8), gram_flops)
+    timeit("split: ree_cbree_maha(transform only)",
+           lambda: eng.cbree_maha(X, mean, Linv, stats[0:1], 2.0, 1.0, 0, None, None, is4), n * (8 * d + 16), tri_flops)
 Z = eng.philox_normal(n, d, 2, 2)
 timeit("ree_cbree_step(inject)", lambda: eng.cbree_step(X, Y, 0.6, m_noise, F, lsf, None, sums, z=Z),
        n * (24 * d + 16), gram_flops + 2 * n * d * d)
