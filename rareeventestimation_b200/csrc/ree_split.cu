@@ -14,6 +14,7 @@
 // of twice (32 GB instead of 24 GB of HBM traffic per iteration at N=1e7, d=100 -- 4.9 ms of a >= 12.5 ms DMMA bound).
 #include "mma_common.cuh"
 
+
 struct XfArgs {
     const double* x;  // MODE 1: X (input) ; MODE 2: X'
     int64_t n, ld;
@@ -55,7 +56,8 @@ struct GenStage {  // rows 8q+lc and 8q+4+lc of the warp's staging block at part
 // ---------------------------------------------------------------------------------------
 // transform kernel: one warp = 8 particles x all dimensions, persistent over warp tiles
 // ---------------------------------------------------------------------------------------
-template <int MODE, int NTB, int NW, bool EXACT, bool TRI>
+// PGB: Philox + Box-Muller chains generated together (instruction-level parallelism inside a warp)
+template <int MODE, int NTB, int NW, bool EXACT, bool TRI, int PGB>
 __global__ void __launch_bounds__(NW * 32, 1) k_xform(const XfArgs a) {
     constexpr int MT = NW * 32;
     constexpr int ROWS = 8 * NTB;
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_xform(const XfArgs a) {
                 GenPhilox gen;
                 gen.seed = a.seed; gen.draw = a.draw; gen.lc = (uint32_t)lc; gen.tab.addr = smem_u32(bm);
                 gen.particle = (uint64_t)(a.first + i0 + lr);
-                transform_tiles<NTB, TRI, EXACT, 1>(lf_lane, ntd, gen, c);
+                transform_tiles<NTB, TRI, EXACT, PGB>(lf_lane, ntd, gen, c);
             }
             cp_async_wait_all();  // own elements only: no warp barrier needed
             double se0 = 0.0, se1 = 0.0, sg0 = 0.0, sg1 = 0.0;
@@ -235,11 +237,10 @@ struct GramRegs2 {
     int flags;            // 15: off-diagonal 2x2, 13: diagonal 2x2, 3: one row x two cols, 1: single tile, 0: none
 };
 
-// one k-pair (8 particles) of one 8x8 output tile: acc += A(:, 2 particles) B(2 particles, :)
-__device__ __forceinline__ void dmma2(double (&acc)[2], const double2& a, const double2& b) {
-    dmma(acc[0], acc[1], a.x, b.x);
-    dmma(acc[0], acc[1], a.y, b.y);
-}
+// one k-step (4 particles) of one 8x8 output tile.  A k-pair is issued as all first k-steps of the macro tile, then
+// all second ones: the two DMMAs of one accumulator are 3-7 independent DMMAs apart instead of back to back.
+#define DX(acc, a, b) dmma(acc[0], acc[1], (a).x, (b).x)
+#define DY(acc, a, b) dmma(acc[0], acc[1], (a).y, (b).y)
 
 // Gram of UPG k-pairs of a shared tile into the warp's macro tiles; macro-outer / k-inner so that every branch on the
 // macro type is taken once per tile and the k loop is straight-line code with immediate offsets.
@@ -257,62 +258,67 @@ __device__ __forceinline__ void gram2_accumulate(uint32_t buf, uint32_t wts, con
             for (int u = 0; u < UPG; ++u) {
                 const double2 a0 = lds128(ra + u * 64), a1 = lds128(ra + u * 64 + R1);
                 const double2 b0 = lds128(ca + u * 64), b1 = lds128(ca + u * 64 + R1);
-                dmma2(au[m][0], a0, b0);
-                dmma2(au[m][1], a0, b1);
-                dmma2(au[m][2], a1, b0);
-                dmma2(au[m][3], a1, b1);
+                double2 a0w, a1w;
                 if (WEIGHTED) {
                     const double2 w = lds128(wts + u * 64);
-                    const double2 a0w = make_double2(a0.x * w.x, a0.y * w.y), a1w = make_double2(a1.x * w.x, a1.y * w.y);
-                    dmma2(aw[m][0], a0w, b0);
-                    dmma2(aw[m][1], a0w, b1);
-                    dmma2(aw[m][2], a1w, b0);
-                    dmma2(aw[m][3], a1w, b1);
+                    a0w = make_double2(a0.x * w.x, a0.y * w.y);
+                    a1w = make_double2(a1.x * w.x, a1.y * w.y);
                 }
+                DX(au[m][0], a0, b0); DX(au[m][1], a0, b1); DX(au[m][2], a1, b0); DX(au[m][3], a1, b1);
+                if (WEIGHTED) { DX(aw[m][0], a0w, b0); DX(aw[m][1], a0w, b1); DX(aw[m][2], a1w, b0); DX(aw[m][3], a1w, b1); }
+                DY(au[m][0], a0, b0); DY(au[m][1], a0, b1); DY(au[m][2], a1, b0); DY(au[m][3], a1, b1);
+                if (WEIGHTED) { DY(aw[m][0], a0w, b0); DY(aw[m][1], a0w, b1); DY(aw[m][2], a1w, b0); DY(aw[m][3], a1w, b1); }
             }
         } else if (f == 13) {  // diagonal 2x2: tiles (0,0), (1,0), (1,1); B fragments are the A fragments
 #pragma unroll
             for (int u = 0; u < UPG; ++u) {
                 const double2 a0 = lds128(ra + u * 64), a1 = lds128(ra + u * 64 + R1);
-                dmma2(au[m][0], a0, a0);
-                dmma2(au[m][2], a1, a0);
-                dmma2(au[m][3], a1, a1);
+                double2 a0w, a1w;
                 if (WEIGHTED) {
                     const double2 w = lds128(wts + u * 64);
-                    const double2 a0w = make_double2(a0.x * w.x, a0.y * w.y), a1w = make_double2(a1.x * w.x, a1.y * w.y);
-                    dmma2(aw[m][0], a0w, a0);
-                    dmma2(aw[m][2], a1w, a0);
-                    dmma2(aw[m][3], a1w, a1);
+                    a0w = make_double2(a0.x * w.x, a0.y * w.y);
+                    a1w = make_double2(a1.x * w.x, a1.y * w.y);
                 }
+                DX(au[m][0], a0, a0); DX(au[m][2], a1, a0); DX(au[m][3], a1, a1);
+                if (WEIGHTED) { DX(aw[m][0], a0w, a0); DX(aw[m][2], a1w, a0); DX(aw[m][3], a1w, a1); }
+                DY(au[m][0], a0, a0); DY(au[m][2], a1, a0); DY(au[m][3], a1, a1);
+                if (WEIGHTED) { DY(aw[m][0], a0w, a0); DY(aw[m][2], a1w, a0); DY(aw[m][3], a1w, a1); }
             }
         } else if (f == 3) {  // one row tile, two column tiles
 #pragma unroll
             for (int u = 0; u < UPG; ++u) {
                 const double2 a0 = lds128(ra + u * 64);
                 const double2 b0 = lds128(ca + u * 64), b1 = lds128(ca + u * 64 + R1);
-                dmma2(au[m][0], a0, b0);
-                dmma2(au[m][1], a0, b1);
+                double2 a0w;
                 if (WEIGHTED) {
                     const double2 w = lds128(wts + u * 64);
-                    const double2 a0w = make_double2(a0.x * w.x, a0.y * w.y);
-                    dmma2(aw[m][0], a0w, b0);
-                    dmma2(aw[m][1], a0w, b1);
+                    a0w = make_double2(a0.x * w.x, a0.y * w.y);
                 }
+                DX(au[m][0], a0, b0); DX(au[m][1], a0, b1);
+                if (WEIGHTED) { DX(aw[m][0], a0w, b0); DX(aw[m][1], a0w, b1); }
+                DY(au[m][0], a0, b0); DY(au[m][1], a0, b1);
+                if (WEIGHTED) { DY(aw[m][0], a0w, b0); DY(aw[m][1], a0w, b1); }
             }
-        } else {  // f == 1: single tile
+        } else {  // f == 1: single tile (two k-pairs per round so that the accumulator chain has company)
 #pragma unroll
             for (int u = 0; u < UPG; ++u) {
                 const double2 a0 = lds128(ra + u * 64);
                 const double2 b0 = lds128(ca + u * 64);
-                dmma2(au[m][0], a0, b0);
+                double2 a0w;
                 if (WEIGHTED) {
                     const double2 w = lds128(wts + u * 64);
-                    dmma2(aw[m][0], make_double2(a0.x * w.x, a0.y * w.y), b0);
+                    a0w = make_double2(a0.x * w.x, a0.y * w.y);
                 }
+                DX(au[m][0], a0, b0);
+                if (WEIGHTED) DX(aw[m][0], a0w, b0);
+                DY(au[m][0], a0, b0);
+                if (WEIGHTED) DY(aw[m][0], a0w, b0);
             }
         }
     }
 }
+#undef DX
+#undef DY
 
 template <int MAXM>
 __device__ __forceinline__ void gram2_store(double* __restrict__ part, const GramPlan& plan, int wi, int nmac, int nta,
@@ -334,25 +340,37 @@ __device__ __forceinline__ void gram2_store(double* __restrict__ part, const Gra
 }
 
 template <int NTB, int NW, int MAXM, int KS, bool EXACT, bool WEIGHTED>
-__global__ void __launch_bounds__(NW * 32, 1) k_gram2(const GramArgs a) {
+__global__ void __launch_bounds__(NW * 32, 1) k_gram2(const GramArgs a, const __grid_constant__ CUtensorMap tmap) {
     constexpr int MT = NW * 32;
     constexpr int P = NW * 8;   // particles per CTA tile
     constexpr int S = P + 8;    // row stride of the shared tile (8 mod 16 doubles)
     constexpr int ROWS = 8 * NTB;
     constexpr uint32_t BUF_BYTES = ROWS * S * 8;
     constexpr int WG = NW / KS, UPG = P / 8 / KS;
-    extern __shared__ double sm[];
+    extern __shared__ __align__(1024) double sm[];
     const int d = a.d, ntd = (d + 7) >> 3, nta = (d + 8) >> 3;
-    double* Ys = sm;                 // two tile buffers
+    double* Ys = sm;                 // two tile buffers (TMA destinations: 128-byte aligned)
     double* wt = Ys + 2 * ROWS * S;  // two weight vectors
     double* vs = wt + 2 * P;         // shift
     __shared__ double red[32];
+    __shared__ __align__(8) unsigned long long full_bar[2];   // "the rows of tile buffer b have landed" (bulk copies)
+    __shared__ __align__(8) unsigned long long ready_bar[2];  // "every warp has prepared its part of buffer b"
+    __shared__ unsigned int done_cnt[2];                      // warps that finished the Gram of buffer b
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lc = lane & 3;
     const int grp = warp / WG, wi = warp % WG;
 
     for (int j = tid; j < 8 * NTB; j += MT) vs[j] = (j < d && a.shift) ? a.shift[j] : 0.0;
     for (int idx = tid; idx < 2 * ROWS * S + 2 * P; idx += MT) Ys[idx] = 0.0;
     const uint32_t ys_addr = smem_u32(Ys), wt_addr = smem_u32(wt);
+    const uint32_t bar0 = smem_u32(&full_bar[0]), rdy0 = smem_u32(&ready_bar[0]);
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        mbar_init(rdy0, NW);
+        mbar_init(rdy0 + 8, NW);
+        done_cnt[0] = done_cnt[1] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     GramRegs2 gr[MAXM];
     const int nmac = a.plan.nmac[wi];
 #pragma unroll
@@ -378,73 +396,122 @@ __global__ void __launch_bounds__(NW * 32, 1) k_gram2(const GramArgs a) {
     const int pw = warp * 8;
     const int64_t ntiles = (a.n + P - 1) / P;
     const uint32_t own_off = (uint32_t)((lr * S + pw + 2 * lc) * 8);
+    const uint32_t vs_addr = smem_u32(vs);
 
-    auto prefetch = [&](int64_t i0, uint32_t buf) {  // every lane fetches exactly the elements it will rewrite
-        const int64_t ip = i0 + pw + 2 * lc;
-        if (ip < a.ld) {
-#pragma unroll
-            for (int mt = 0; mt < NTB; ++mt) {
-                const int row = 8 * mt + lr;
-                if (row < d) cp_async16(buf + own_off + (uint32_t)(8 * mt * S * 8), a.x + (int64_t)row * a.ld + ip);
-            }
+    // Tile load = ONE TMA instruction (box S columns x ROWS rows of the ensemble's tensor map; rows >= d and columns
+    // >= ld arrive as zeros), issued by lane 0 of the last warp to finish reading the buffer.  The proxy fence orders the
+    // generic-proxy reads of the previous tile before the async-proxy writes.
+    auto load_tile = [&](int64_t i0, uint32_t buf, uint32_t bar) {
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, BUF_BYTES);
+            tma_load_2d(buf, &tmap, (int)i0, 0, bar);
         }
     };
-    // per-particle scalars of the next tile travel in registers (threads 0..P-1 own one particle each)
+    // per-particle scalars of the next tile travel in registers (lanes 0..7 of every warp own one particle each)
     double a_nxt = 0.0, g_nxt = 1.0;
     auto fetch_scalars = [&](int64_t i0) {
-        const int64_t i = i0 + tid;
-        const bool v = tid < P && i < a.n;
+        const int64_t i = i0 + pw + lane;
+        const bool v = lane < 8 && i < a.n;
         a_nxt = (WEIGHTED && v) ? a.a[i] : 0.0;
         g_nxt = (v && a.g) ? a.g[i] : 1.0;
     };
-    if ((int64_t)blockIdx.x < ntiles) {
-        prefetch((int64_t)blockIdx.x * P, ys_addr);
-        fetch_scalars((int64_t)blockIdx.x * P);
-    }
-
-    int parity = 0;
-    for (int64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x, parity ^= 1) {
-        const int64_t i0 = tix * P;
-        const uint32_t buf = ys_addr + (parity ? BUF_BYTES : 0u);
-        const uint32_t wbuf = wt_addr + (parity ? (uint32_t)(P * 8) : 0u);
+    // Turn the landed tile into Gram operands in place: y = x - shift, zero padding, augmented row of ones; weights.
+    // Every lane rewrites a disjoint set of elements (rows 8mt+lr, its warp's columns 2lc, 2lc+1).
+    auto prepare = [&](int64_t i0, uint32_t buf, uint32_t wbuf, uint32_t bar, uint32_t rdy, uint32_t phase) {
+        mbar_wait(bar, phase);
         const int64_t ip = i0 + pw + 2 * lc;
         const bool v0 = ip < a.n, v1 = ip + 1 < a.n;
-        cp_async_wait_all();
-        // ---- rewrite this lane's elements: y = x - shift, zero padding, augmented row of ones --------------
+        if (i0 + P <= a.n) {  // full tile (all but the last one): no column selects
 #pragma unroll
-        for (int mt = 0; mt < NTB; ++mt) {
-            if (EXACT || mt < ntd) {
-                const int row = 8 * mt + lr;
-                const bool rv = row < d;
-                const uint32_t sa = buf + own_off + (uint32_t)(8 * mt * S * 8);
-                const double2 xv = lds128(sa);
-                const double srow = vs[row];
-                double2 y;
-                y.x = (rv && v0) ? xv.x - srow : 0.0;  // select, not multiply: padded lanes may hold anything
-                y.y = (rv && v1) ? xv.y - srow : 0.0;
-                if (row == d) {
-                    y.x = v0 ? 1.0 : 0.0;
-                    y.y = v1 ? 1.0 : 0.0;
+            for (int mt = 0; mt < NTB; ++mt) {
+                if (EXACT ? (mt < NTB - 1) : (mt < ntd - 1)) {  // all 8 rows of the tile are dimensions
+                    const uint32_t sa = buf + own_off + (uint32_t)(8 * mt * S * 8);
+                    const double2 xv = lds128(sa);
+                    const double srow = lds64(vs_addr + (uint32_t)((8 * mt + lr) * 8));
+                    sts128(sa, make_double2(xv.x - srow, xv.y - srow));
                 }
-                sts128(sa, y);
             }
+        } else {
+#pragma unroll
+            for (int mt = 0; mt < NTB; ++mt) {
+                if (EXACT ? (mt < NTB - 1) : (mt < ntd - 1)) {
+                    const uint32_t sa = buf + own_off + (uint32_t)(8 * mt * S * 8);
+                    const double2 xv = lds128(sa);
+                    const double srow = lds64(vs_addr + (uint32_t)((8 * mt + lr) * 8));
+                    sts128(sa, make_double2(v0 ? xv.x - srow : 0.0, v1 ? xv.y - srow : 0.0));
+                }
+            }
+        }
+        {  // last dimension tile: rows >= d are zero, row d (if it falls into this tile) is the row of ones
+            const int mt = ntd - 1, row = 8 * mt + lr;
+            const uint32_t sa = buf + own_off + (uint32_t)(8 * mt * S * 8);
+            const double2 xv = lds128(sa);
+            const double srow = lds64(vs_addr + (uint32_t)(row * 8));
+            double2 y;
+            y.x = (row < d && v0) ? xv.x - srow : 0.0;  // select, not multiply: padded lanes may hold anything
+            y.y = (row < d && v1) ? xv.y - srow : 0.0;
+            if (row == d) {
+                y.x = v0 ? 1.0 : 0.0;
+                y.y = v1 ? 1.0 : 0.0;
+            }
+            sts128(sa, y);
         }
         if (nta > ntd && lr == 0)  // d % 8 == 0: the augmented row lives in a tile of its own
             sts128(buf + (uint32_t)((d * S + pw + 2 * lc) * 8), make_double2(v0 ? 1.0 : 0.0, v1 ? 1.0 : 0.0));
-        if (tid < P) {
-            const bool v = i0 + tid < a.n;
+        if (lane < 8) {
+            const bool v = i0 + pw + lane < a.n;
             if (WEIGHTED) {
                 const double wv = (v && isfinite(a_nxt)) ? exp(a_nxt - wmax) : 0.0;
-                asm volatile("st.shared.f64 [%0], %1;" ::"r"(wbuf + (uint32_t)tid * 8u), "d"(wv) : "memory");
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"(wbuf + (uint32_t)(pw + lane) * 8u), "d"(wv) : "memory");
             }
             n_fail += (v && g_nxt <= 0.0) ? 1.0 : 0.0;
         }
-        __syncthreads();  // tile k complete; everybody is done with the other buffer (Gram k-1)
-        if (tix + gridDim.x < ntiles) {
-            prefetch((tix + gridDim.x) * P, ys_addr + (parity ? 0u : BUF_BYTES));
-            fetch_scalars((tix + gridDim.x) * P);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rdy);  // release: this warp's part of the buffer is final
+    };
+    // Pipeline without CTA barriers: tile k lives in buffer k & 1.
+    //   full[b]   bulk copies of the tile in buffer b have landed         (armed by the loading warp)
+    //   ready[b]  all warps have prepared their part of buffer b          (count NW)
+    //   done[b]   warps that finished the Gram of buffer b; the last one loads tile k+2 into it
+    // A warp may run ahead of the slowest one by up to a tile.  The Gram of tile k runs in NCH chunks of k-pairs;
+    // the warps of one SM sub-partition (same warp % 4) prepare tile k+1 after different chunks, so that the
+    // sub-partition's tensor pipe always has DMMAs from the others.
+    constexpr int NCH = (UPG % 4 == 0) ? 4 : 1, CH = UPG / NCH;
+    const int slot = (NCH == 1) ? 0 : min(warp >> 2, NCH - 2);
+    const int64_t t0 = blockIdx.x, tstep = gridDim.x;
+    if (t0 < ntiles && warp == 0) load_tile(t0 * P, ys_addr, bar0);
+    if (t0 + tstep < ntiles && warp == 1 % NW) load_tile((t0 + tstep) * P, ys_addr + BUF_BYTES, bar0 + 8);
+    if (t0 < ntiles) {
+        fetch_scalars(t0 * P);
+        prepare(t0 * P, ys_addr, wt_addr, bar0, rdy0, 0);
+    }
+    int k = 0;
+    for (int64_t tix = t0; tix < ntiles; tix += tstep, ++k) {
+        const int b = k & 1;
+        const uint32_t ph = (uint32_t)(k >> 1) & 1u, nph = (uint32_t)((k + 1) >> 1) & 1u;
+        const uint32_t buf = ys_addr + (b ? BUF_BYTES : 0u), nbuf = ys_addr + (b ? 0u : BUF_BYTES);
+        const uint32_t wbuf = wt_addr + (b ? (uint32_t)(P * 8) : 0u), nwbuf = wt_addr + (b ? 0u : (uint32_t)(P * 8));
+        const bool more = tix + tstep < ntiles;
+        const int64_t i0n = (tix + tstep) * P;
+        if (more) fetch_scalars(i0n);
+        mbar_wait(rdy0 + (b ? 8u : 0u), ph);  // acquire: every warp's part of tile k is in place
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+            gram2_accumulate<MAXM, S, CH, WEIGHTED>(buf + (uint32_t)(c * CH * 64),
+                                                    wbuf + (uint32_t)(((grp * UPG + c * CH) * 8 + 2 * lc) * 8), gr, au, aw);
+            if (more && c == slot) prepare(i0n, nbuf, nwbuf, bar0 + (b ? 0u : 8u), rdy0 + (b ? 0u : 8u), nph);
         }
-        gram2_accumulate<MAXM, S, UPG, WEIGHTED>(buf, wbuf + (uint32_t)((grp * UPG * 8 + 2 * lc) * 8), gr, au, aw);
+        // done with buffer b: the last warp to get here refills it with tile k+2
+        __syncwarp();
+        unsigned int last = 0;
+        if (lane == 0) {
+            __threadfence_block();
+            last = (atomicAdd(&done_cnt[b], 1u) == NW - 1) ? 1u : 0u;
+            if (last) done_cnt[b] = 0;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && tix + 2 * tstep < ntiles) load_tile((tix + 2 * tstep) * P, buf, bar0 + (b ? 8u : 0u));
     }
     const int T = nta * (nta + 1) / 2;
     const size_t poff = ((size_t)blockIdx.x * KS + grp) * T * 64;
@@ -473,6 +540,15 @@ static int split_min_d() {
     return v;
 }
 
+static int xf_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("REE_XF_VARIANT");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
 static bool pick_split(int d, SplitCfg& c) {
     if (d < split_min_d()) return false;
     if (d <= 55) c = {7, 16, 8, 3, 2};
@@ -486,12 +562,12 @@ bool ree_split_supported(int d) {
     return pick_split(d, c);
 }
 
-template <int MODE, int NTB, int NW, bool EXACT, bool TRI>
+template <int MODE, int NTB, int NW, bool EXACT, bool TRI, int PGB = 2>
 static int launch_xf(const XfArgs& a, int grid, cudaStream_t st) {
     constexpr size_t smem = ((size_t)lf_doubles<NTB, TRI>() + (size_t)NW * 8 * NTB * 8 + 2 * 8 * NTB +
                              (MODE == 1 ? BM_TABLE_DOUBLES + 2 : 0)) * sizeof(double);
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    auto kern = k_xform<MODE, NTB, NW, EXACT, TRI>;
+    auto kern = k_xform<MODE, NTB, NW, EXACT, TRI, PGB>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, NW * 32, smem, st>>>(a);
     return ree_check_launch(MODE == 1 ? "k_xform<1>" : "k_xform<2>");
@@ -512,6 +588,16 @@ static int launch_xf_bucket(const SplitCfg& c, const XfArgs& a, cudaStream_t st)
         return launch_xf_exact<MODE, 7, 16, TRI>(a, (int)(want < sms ? want : sms), st);
     }
     if constexpr (TRI) {
+        if (MODE == 1 && (a.d + 7) / 8 == 13 && xf_variant() > 0) {  // tuning hook: warps x Philox batch
+            const int v = xf_variant();
+            const int nw = (v == 1 || v == 2) ? 12 : 16;
+            const int64_t want = (nwt + nw - 1) / nw;
+            const int grid = (int)(want < sms ? want : sms);
+            if (v == 1) return launch_xf<MODE, 13, 12, true, TRI, 2>(a, grid, st);
+            if (v == 2) return launch_xf<MODE, 13, 12, true, TRI, 4>(a, grid, st);
+            if (v == 3) return launch_xf<MODE, 13, 16, true, TRI, 1>(a, grid, st);
+            return launch_xf<MODE, 13, 16, true, TRI, 3>(a, grid, st);
+        }
         const int64_t want = (nwt + 15) / 16;
         return launch_xf_exact<MODE, 13, 16, TRI>(a, (int)(want < sms ? want : sms), st);
     } else {  // dense parity-mode factor: 86 KB of fragments, fewer warps
@@ -525,9 +611,12 @@ static int launch_g2(const GramArgs& a, int grid, cudaStream_t st) {
     constexpr int P = NW * 8, S = P + 8, ROWS = 8 * NTB;
     constexpr size_t smem = ((size_t)2 * ROWS * S + 2 * P + 8 * NTB) * sizeof(double);
     static_assert(smem <= 227 * 1024, "shared memory budget");
+    CUtensorMap tmap;
+    int rc = make_ensemble_tmap(&tmap, a.x, a.ld, a.d, S, ROWS);
+    if (rc) return rc;
     auto kern = k_gram2<NTB, NW, MAXM, KS, EXACT, WEIGHTED>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, NW * 32, smem, st>>>(a);
+    kern<<<grid, NW * 32, smem, st>>>(a, tmap);
     return ree_check_launch("k_gram2");
 }
 
