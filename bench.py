@@ -194,7 +194,7 @@ def run_b200(args):
         return float(t.item())
 
     # per-call device timing of the two sweeps (CUDA events on the launching stream)
-    marks = {"step": [], "maha": []}
+    marks = {"step": [], "moments": [], "maha": []}
 
     def timed(name, fn):
         def wrapper(*a, **k):
@@ -207,6 +207,7 @@ def run_b200(args):
         return wrapper
 
     eng.cbree_step = timed("step", eng.cbree_step)
+    eng.cbree_moments = timed("moments", eng.cbree_moments)
     eng.cbree_maha = timed("maha", eng.cbree_maha)
 
     kw = dict(seed=1, convergence_check=False, divergence_check=False, quiet=True)
@@ -251,25 +252,52 @@ def run_b200(args):
         fp64_peak = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))
     except Exception:
         pass
-    # algorithmic bytes per particle (DESIGN.md "Roofline"): sweep 1 reads X, writes X', g', e';
-    # sweep 2 reads X', g', e' and writes the weights.
-    alg = {"step": n_local * (16 * d + 16), "maha": n_local * (8 * d + 24)}
-    # algorithmic flops: triangular noise transform + symmetric Gram (sweep 1), triangular Mahalanobis + symmetric
-    # weighted Gram (sweep 2): 2*d^2 each, plus O(d).
-    flops = {"step": n_local * (2.0 * d * d + 8 * d), "maha": n_local * (2.0 * d * d + 8 * d)}
+    # Algorithmic bytes / flops per particle of the three kernels of an iteration:
+    #   step     read X, write X', g', e'                     | triangular F z: d(d+1) flop
+    #   moments  read X', g', a                               | two symmetric-half Grams of (y, 1): 2 (d+1)(d+2) flop
+    #   maha     read X', g', e'                              | triangular Linv y: d(d+1) flop
+    # (d <= 55 runs the fused two-sweep path: "moments" is empty and the Grams are part of step / maha.)
+    split = bool(marks["moments"])
+    alg = {"step": n_local * (16 * d + 16), "moments": n_local * (8 * d + 16), "maha": n_local * (8 * d + 16)}
+    flops = {"step": n_local * (d * (d + 1.0) + (0 if split else (d + 1.0) * (d + 2))),
+             "moments": n_local * 2.0 * (d + 1) * (d + 2),
+             "maha": n_local * (d * (d + 1.0) + (0 if split else (d + 1.0) * (d + 2)))}
+    sweep_ms = {k: v for k, v in sweep_ms.items() if v > 0}
     dom = max(sweep_ms, key=lambda k: sweep_ms[k])
-    ach = alg[dom] / (sweep_ms[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "ree_cbree_step" if dom == "step" else "ree_cbree_maha",
-                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-                "peak_source": peak_src, "ms_per_launch": sweep_ms[dom],
-                "sweeps_ms": sweep_ms,
-                "hbm_frac_whole_iteration": (n_local * (24 * d + 48)) / (ms / K * 1e-3) / 1e9 / hbm_peak}
-    tfl = flops[dom] / (sweep_ms[dom] * 1e-3) / 1e12
-    roofline["fp64"] = {"achieved_tflops": tfl, "note": "binding pipe at d=100 (SURVEY 8d)"}
-    if fp64_peak:
-        pk = max(fp64_peak.get("dfma_tflops", 0), fp64_peak.get("dmma_m8n8k4_tflops", 0))
-        roofline["fp64"].update({"peak_tflops": pk, "frac": tfl / pk if pk else None,
-                                 "peak_source": "tools/fp64_peak.cu -> profiles/fp64_peak.json"})
+    names = {"step": "ree_cbree_step", "moments": "ree_cbree_moments", "maha": "ree_cbree_maha"}
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if split and int(tr.get("d", -1)) == d:
+            traffic = tr["bytes_per_particle"][names[dom]] * n_local
+    except Exception:
+        pass
+    fp64_pk = max(fp64_peak.get("dfma_tflops", 0), fp64_peak.get("dmma_m8n8k4_tflops", 0)) if fp64_peak else None
+    per_kernel = {}
+    for k, ms_k in sweep_ms.items():
+        gbs, tfl = alg[k] / (ms_k * 1e-3) / 1e9, flops[k] / (ms_k * 1e-3) / 1e12
+        per_kernel[names[k]] = {"ms_per_launch": ms_k, "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak, "fp64_tflops": tfl,
+                                "fp64_frac": tfl / fp64_pk if fp64_pk else None}
+    ach_tf = flops[dom] / (sweep_ms[dom] * 1e-3) / 1e12
+    ach_gb = alg[dom] / (sweep_ms[dom] * 1e-3) / 1e9
+    iter_flops = sum(flops[k] for k in sweep_ms)
+    if d > 35 and fp64_pk:
+        # d = 100: 16.8 flop/B against a machine balance of 5.7 -> the fp64 tensor pipe (DMMA) binds, not HBM
+        roofline = {"bound": "tensor", "kernel": names[dom], "achieved": ach_tf, "peak": fp64_pk, "unit": "TFLOP/s",
+                    "frac": ach_tf / fp64_pk, "traffic": traffic,
+                    "peak_source": "fp64 DMMA (mma.sync.m8n8k4.f64) measured on this pool by tools/fp64_peak.cu -> "
+                                   "profiles/fp64_peak.json; tcgen05 has no f64 kind, MEASURED_PEAKS.json only has bf16",
+                    "ms_per_launch": sweep_ms[dom],
+                    "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
+                            "peak_source": peak_src},
+                    "kernels": per_kernel,
+                    "whole_iteration": {"fp64_frac": iter_flops / (ms / K * 1e-3) / 1e12 / fp64_pk,
+                                        "hbm_frac": (n_local * (24 * d + 48)) / (ms / K * 1e-3) / 1e9 / hbm_peak}}
+    else:
+        roofline = {"bound": "hbm", "kernel": names[dom], "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach_gb / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                    "ms_per_launch": sweep_ms[dom], "kernels": per_kernel,
+                    "whole_iteration": {"hbm_frac": (n_local * (24 * d + 48)) / (ms / K * 1e-3) / 1e9 / hbm_peak}}
 
     # ---- end to end through the reference-facing API with HOST buffers ---------------------------
     e2e = None

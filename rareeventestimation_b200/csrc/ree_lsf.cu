@@ -1,37 +1,13 @@
 // Limit-state functions, energy, layout transposes and the Philox sample generator.
 // Thread-per-particle kernels on the SoA ensemble (coalesced 8-byte loads along the particle axis).
 #include "common.cuh"
+#include "lsf_point.cuh"
 
-#define REE_LSF_LINEAR_SUM_INTERNAL 100
 
 // ---------------------------------------------------------------------------------------
 // toy LSFs (problem/toy_problems.py).  Operation order mirrors the NumPy expressions; _rn
 // intrinsics keep nvcc from contracting mul+add into FMA (NumPy does not fuse).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double lsf_oscillator(double x0, double x1, double x2, double x3, double x4, double x5) {
-    // toy_problems.py:72-80
-    double m = __dadd_rn(1.0, __dmul_rn(0.05, x0));
-    double c1 = __dadd_rn(1.0, __dmul_rn(0.1, x1));
-    double c2 = __dadd_rn(0.1, __dmul_rn(0.01, x2));
-    double r = __dadd_rn(0.5, __dmul_rn(0.05, x3));
-    double f1 = __dadd_rn(0.3, __dmul_rn(0.2, x4));
-    double t1 = __dadd_rn(1.0, __dmul_rn(0.2, x5));
-    double w2 = __ddiv_rn(__dadd_rn(c1, c2), m);  // omega^2 before the complex sqrt
-    double amp;
-    if (w2 >= 0.0) {
-        double om = __dsqrt_rn(w2);
-        double om2 = __dmul_rn(om, om);  // omega**2 as NumPy forms it
-        double a = __ddiv_rn(__dmul_rn(2.0, f1), __dmul_rn(m, om2));
-        amp = fabs(__dmul_rn(a, sin(__ddiv_rn(__dmul_rn(om, t1), 2.0))));
-    } else {  // omega = i*b: omega^2 = -b^2, sin(i y) = i sinh(y)
-        double b = __dsqrt_rn(-w2);
-        double om2 = -__dmul_rn(b, b);
-        double a = __ddiv_rn(__dmul_rn(2.0, f1), __dmul_rn(m, om2));
-        amp = fabs(__dmul_rn(a, sinh(__ddiv_rn(__dmul_rn(b, t1), 2.0))));
-    }
-    return __dsub_rn(__dmul_rn(3.0, r), amp);
-}
-
 __global__ void __launch_bounds__(REE_THREADS) k_lsf_simple(ree_lsf lsf, const double* __restrict__ x, int64_t n,
                                                             int64_t ld, double* __restrict__ g) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;

@@ -21,6 +21,15 @@ int ree_mma_maha(const double* x, int64_t n, int d, int64_t ld, const double* g,
 int ree_mma_sums(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* shift, double* ws_big,
                  double* ws_small, double* sums, cudaStream_t st);
 
+bool ree_small_supported(int d);
+int ree_small_step(const double* x, double* x_new, int64_t n, int d, int64_t ld, double t, const double* m_noise,
+                   const double* F, int tri, const double* z, uint64_t seed, uint64_t draw, int64_t first, int lsf_kind,
+                   const double* coef, double offset, const double* shift, double* g_new, double* e_new, double* ws_big,
+                   double* sums, cudaStream_t st);
+int ree_small_post(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* e, const double* mean,
+                   const double* Linv, const double* logdet, double sigma, double beta, int tgt_kind, const double* wmax,
+                   double* logq, double* w, double* ws_big, double* ws_small, double* sums, double* is4,
+                   cudaStream_t st);
 bool ree_split_supported(int d);
 int ree_split_step(const double* x, double* x_new, int64_t n, int d, int64_t ld, double t, const double* m_noise,
                    const double* F, int tri, const double* z, uint64_t seed, uint64_t draw, int64_t first, int lsf_mode,
@@ -309,6 +318,9 @@ extern "C" int64_t ree_workspace_bytes(int d) {
 extern "C" int ree_ensemble_sums(const double* x, int64_t n, int d, int64_t ld, const double* g, const double* shift,
                                  double* workspace, double* sums, void* stream) {
     if (!x || !workspace || !sums || d < 1 || n < 1) return ree_set_error(REE_E_BADARG, "ree_ensemble_sums: bad argument");
+    if (ree_small_supported(d))
+        return ree_small_post(x, n, d, ld, g, nullptr, shift, nullptr, nullptr, 0.0, 0.0, 0, nullptr, nullptr, nullptr,
+                              workspace + ws_big_offset(), workspace + REE_WS_HEADER, sums, nullptr, ree_stream(stream));
     if (ree_mma_supported(d))
         return ree_mma_sums(x, n, d, ld, g, shift, workspace + ws_big_offset(), workspace + REE_WS_HEADER, sums,
                             ree_stream(stream));
@@ -346,6 +358,24 @@ extern "C" int ree_cbree_step(const double* x, double* x_new, int64_t n, int d, 
                                 fused_lsf ? lsf->offset : 0.0, g_new, e_new, st);
         if (rc) return rc;
         if (lsf && lsf->kind != REE_LSF_EXTERNAL && !fused_lsf) return ree_lsf_launch(lsf, x_new, n, ld, g_new, st);
+        return 0;
+    }
+    if (ree_small_supported(d)) {  // thread-per-particle sweep; every closed-form LSF is evaluated in registers
+        int kind = 0;
+        if (lsf && lsf->kind >= REE_LSF_AFFINE && lsf->kind <= REE_LSF_OSCILLATOR) {
+            kind = (lsf->kind == REE_LSF_AFFINE && !lsf->coef) ? 100 /* -sum(x)/sqrt(d) + offset */ : lsf->kind;
+            if ((lsf->kind == REE_LSF_OSCILLATOR && d != 6) || (lsf->kind == REE_LSF_CONVEX && d < 2)) kind = 0;
+        }
+        int rc = ree_small_step(x, x_new, n, d, ld, t, m_noise, F, noise_mode == REE_NOISE_PHILOX ? 1 : 0,
+                                noise_mode == REE_NOISE_INJECT ? z : nullptr, seed, draw, first_particle, kind,
+                                lsf ? lsf->coef : nullptr, lsf ? lsf->offset : 0.0, shift, g_new, e_new,
+                                workspace + ws_big_offset(), sums, st);
+        if (rc) return rc;
+        if (lsf && lsf->kind != REE_LSF_EXTERNAL && !kind) {
+            rc = ree_lsf_launch(lsf, x_new, n, ld, g_new, st);
+            if (rc) return rc;
+            return ree_count_failed(g_new, n, workspace, sums + d + (size_t)d * d, stream);
+        }
         return 0;
     }
     if (ree_mma_supported(d)) {
@@ -397,6 +427,9 @@ extern "C" int ree_cbree_maha(const double* x, int64_t n, int d, int64_t ld, con
         return ree_split_maha(x, n, d, ld, g, e, mean, Linv, logdet, logq, workspace + REE_WS_HEADER, is4, st);
     }
     if (!wmax) return ree_set_error(REE_E_BADARG, "ree_cbree_maha: wmax is NULL");
+    if (ree_small_supported(d))
+        return ree_small_post(x, n, d, ld, g, e, mean, Linv, logdet, sigma, beta, tgt_kind, wmax, logq, w,
+                              workspace + ws_big_offset(), workspace + REE_WS_HEADER, sums, is4, st);
     if (ree_mma_supported(d))
         return ree_mma_maha(x, n, d, ld, g, e, mean, Linv, logdet, sigma, beta, tgt_kind, wmax, logq, w,
                             workspace + ws_big_offset(), workspace + REE_WS_HEADER, sums, is4, st);

@@ -17,12 +17,13 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=10_000_000)
 ap.add_argument("--d", type=int, default=100)
 ap.add_argument("--steps", type=int, default=8)
+ap.add_argument("--problem", default="linear", choices=["linear", "osc", "pde"])
 args = ap.parse_args()
 eng = Engine.get()
 dev_ms, host_ms, calls = defaultdict(float), defaultdict(float), defaultdict(int)
 events = []
-for name in ["cbree_step", "cbree_maha", "reduce_ess", "reduce_cvar", "reduce_scaled", "logtgt", "moments_chol",
-             "chol_scaled", "ensemble_sums", "count_failed", "to_device", "alloc_ensemble", "empty"]:
+for name in ["cbree_step", "cbree_moments", "cbree_maha", "reduce_ess", "reduce_cvar", "reduce_scaled", "logtgt", "moments_chol",
+             "chol_scaled", "ensemble_sums", "count_failed", "to_device", "alloc_ensemble", "empty", "lsf_eval", "energy"]:
     fn = getattr(eng, name)
 
     def wrap(fn=fn, name=name):
@@ -39,7 +40,12 @@ for name in ["cbree_step", "cbree_maha", "reduce_ess", "reduce_cvar", "reduce_sc
         return inner
     setattr(eng, name, wrap())
 
-prob = ree.make_linear_problem(args.d)
+if args.problem == "osc":
+    prob, args.d = ree.prob_nonlin_osc, 6
+elif args.problem == "pde":
+    prob, args.d = ree.diffusion_problem, 150
+else:
+    prob = ree.make_linear_problem(args.d)
 prob.sample = DeviceSample(args.n, args.d, seed=0x5EED)
 solver = ree.CBREE(seed=1, convergence_check=False, divergence_check=False, quiet=True, num_steps=10**9)
 cl = solver.start(prob)
