@@ -190,6 +190,9 @@ static int lsf_grid(int64_t n, int tpb) {
     return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
+bool ree_pde_mma_supported(const ree_lsf* l);
+int ree_pde_mma_launch(const ree_lsf* l, const double* x, int64_t n, int64_t ld, double* g, cudaStream_t st);
+
 static bool coef_is_linear_sum(const ree_lsf* lsf) { return lsf->kind == REE_LSF_AFFINE && lsf->coef == nullptr; }
 
 int ree_lsf_launch(const ree_lsf* lsf, const double* x, int64_t n, int64_t ld, double* g, cudaStream_t st) {
@@ -210,6 +213,7 @@ int ree_lsf_launch(const ree_lsf* lsf, const double* x, int64_t n, int64_t ld, d
             break;
         case REE_LSF_DIFFUSION: {
             if (!l.coef || l.n_ele < 1) return ree_set_error(REE_E_BADARG, "diffusion LSF needs a mode table");
+            if (ree_pde_mma_supported(&l)) return ree_pde_mma_launch(&l, x, n, ld, g, st);
             size_t smem = (size_t)l.d * REE_PDE_TPB * sizeof(double);
             if (smem > 200 * 1024) return ree_set_error(REE_E_UNSUPPORTED, "diffusion LSF: d too large for shared memory");
             cudaFuncSetAttribute(k_lsf_diffusion, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -474,8 +474,8 @@ bool ree_mma_supported(int d) {
 
 bool ree_split_supported(int d);
 extern "C" int ree_fused_path(int d) {
-    if (!ree_mma_supported(d)) return 0;
-    return ree_split_supported(d) ? 2 : 1;
+    if (ree_split_supported(d)) return 2;
+    return ree_mma_supported(d) ? 1 : 0;
 }
 
 size_t ree_mma_partial_doubles(int d) {

@@ -246,7 +246,7 @@ struct GramRegs2 {
 // macro type is taken once per tile and the k loop is straight-line code with immediate offsets.
 template <int MAXM, int S, int UPG, bool WEIGHTED>
 __device__ __forceinline__ void gram2_accumulate(uint32_t buf, uint32_t wts, const GramRegs2 (&gr)[MAXM],
-                                                 double (&au)[MAXM][4][2], double (&aw)[MAXM][4][2]) {
+                                                 double (&au)[MAXM][4][2], double (&aw)[WEIGHTED ? MAXM : 1][4][2]) {
     constexpr uint32_t R1 = 8 * S * 8;  // second tile of a macro tile: 8 rows further down
 #pragma unroll
     for (int m = 0; m < MAXM; ++m) {
@@ -265,9 +265,9 @@ __device__ __forceinline__ void gram2_accumulate(uint32_t buf, uint32_t wts, con
                     a1w = make_double2(a1.x * w.x, a1.y * w.y);
                 }
                 DX(au[m][0], a0, b0); DX(au[m][1], a0, b1); DX(au[m][2], a1, b0); DX(au[m][3], a1, b1);
-                if (WEIGHTED) { DX(aw[m][0], a0w, b0); DX(aw[m][1], a0w, b1); DX(aw[m][2], a1w, b0); DX(aw[m][3], a1w, b1); }
+                if (WEIGHTED) { DX(aw[WEIGHTED ? m : 0][0], a0w, b0); DX(aw[WEIGHTED ? m : 0][1], a0w, b1); DX(aw[WEIGHTED ? m : 0][2], a1w, b0); DX(aw[WEIGHTED ? m : 0][3], a1w, b1); }
                 DY(au[m][0], a0, b0); DY(au[m][1], a0, b1); DY(au[m][2], a1, b0); DY(au[m][3], a1, b1);
-                if (WEIGHTED) { DY(aw[m][0], a0w, b0); DY(aw[m][1], a0w, b1); DY(aw[m][2], a1w, b0); DY(aw[m][3], a1w, b1); }
+                if (WEIGHTED) { DY(aw[WEIGHTED ? m : 0][0], a0w, b0); DY(aw[WEIGHTED ? m : 0][1], a0w, b1); DY(aw[WEIGHTED ? m : 0][2], a1w, b0); DY(aw[WEIGHTED ? m : 0][3], a1w, b1); }
             }
         } else if (f == 13) {  // diagonal 2x2: tiles (0,0), (1,0), (1,1); B fragments are the A fragments
 #pragma unroll
@@ -280,9 +280,9 @@ __device__ __forceinline__ void gram2_accumulate(uint32_t buf, uint32_t wts, con
                     a1w = make_double2(a1.x * w.x, a1.y * w.y);
                 }
                 DX(au[m][0], a0, a0); DX(au[m][2], a1, a0); DX(au[m][3], a1, a1);
-                if (WEIGHTED) { DX(aw[m][0], a0w, a0); DX(aw[m][2], a1w, a0); DX(aw[m][3], a1w, a1); }
+                if (WEIGHTED) { DX(aw[WEIGHTED ? m : 0][0], a0w, a0); DX(aw[WEIGHTED ? m : 0][2], a1w, a0); DX(aw[WEIGHTED ? m : 0][3], a1w, a1); }
                 DY(au[m][0], a0, a0); DY(au[m][2], a1, a0); DY(au[m][3], a1, a1);
-                if (WEIGHTED) { DY(aw[m][0], a0w, a0); DY(aw[m][2], a1w, a0); DY(aw[m][3], a1w, a1); }
+                if (WEIGHTED) { DY(aw[WEIGHTED ? m : 0][0], a0w, a0); DY(aw[WEIGHTED ? m : 0][2], a1w, a0); DY(aw[WEIGHTED ? m : 0][3], a1w, a1); }
             }
         } else if (f == 3) {  // one row tile, two column tiles
 #pragma unroll
@@ -295,9 +295,9 @@ __device__ __forceinline__ void gram2_accumulate(uint32_t buf, uint32_t wts, con
                     a0w = make_double2(a0.x * w.x, a0.y * w.y);
                 }
                 DX(au[m][0], a0, b0); DX(au[m][1], a0, b1);
-                if (WEIGHTED) { DX(aw[m][0], a0w, b0); DX(aw[m][1], a0w, b1); }
+                if (WEIGHTED) { DX(aw[WEIGHTED ? m : 0][0], a0w, b0); DX(aw[WEIGHTED ? m : 0][1], a0w, b1); }
                 DY(au[m][0], a0, b0); DY(au[m][1], a0, b1);
-                if (WEIGHTED) { DY(aw[m][0], a0w, b0); DY(aw[m][1], a0w, b1); }
+                if (WEIGHTED) { DY(aw[WEIGHTED ? m : 0][0], a0w, b0); DY(aw[WEIGHTED ? m : 0][1], a0w, b1); }
             }
         } else {  // f == 1: single tile (two k-pairs per round so that the accumulator chain has company)
 #pragma unroll
@@ -310,9 +310,9 @@ __device__ __forceinline__ void gram2_accumulate(uint32_t buf, uint32_t wts, con
                     a0w = make_double2(a0.x * w.x, a0.y * w.y);
                 }
                 DX(au[m][0], a0, b0);
-                if (WEIGHTED) DX(aw[m][0], a0w, b0);
+                if (WEIGHTED) DX(aw[WEIGHTED ? m : 0][0], a0w, b0);
                 DY(au[m][0], a0, b0);
-                if (WEIGHTED) DY(aw[m][0], a0w, b0);
+                if (WEIGHTED) DY(aw[WEIGHTED ? m : 0][0], a0w, b0);
             }
         }
     }
@@ -339,8 +339,11 @@ __device__ __forceinline__ void gram2_store(double* __restrict__ part, const Gra
     }
 }
 
-template <int NTB, int NW, int MAXM, int KS, bool EXACT, bool WEIGHTED>
+// WM: 0 unweighted Gram only; 1 unweighted + weighted Gram from one tile (two accumulator sets); 2 weighted Gram only,
+// with the tile rewritten as y sqrt(w) (one accumulator set: the d <= 151 bucket has no registers for two)
+template <int NTB, int NW, int MAXM, int KS, bool EXACT, int WM>
 __global__ void __launch_bounds__(NW * 32, 1) k_gram2(const GramArgs a, const __grid_constant__ CUtensorMap tmap) {
+    constexpr bool WEIGHTED = WM != 0;
     constexpr int MT = NW * 32;
     constexpr int P = NW * 8;   // particles per CTA tile
     constexpr int S = P + 8;    // row stride of the shared tile (8 mod 16 doubles)
@@ -384,11 +387,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_gram2(const GramArgs a, const __
         const bool r1 = 2 * mr + 1 < nta, c1 = 2 * mc + 1 < nta, diag = mr == mc;
         gr[m].flags = live ? (1 | ((c1 && !diag) ? 2 : 0) | (r1 ? 4 : 0) | ((r1 && c1) ? 8 : 0)) : 0;
     }
-    double au[MAXM][4][2], aw[MAXM][4][2];
+    double au[MAXM][4][2], aw[WM == 1 ? MAXM : 1][4][2];
 #pragma unroll
     for (int m = 0; m < MAXM; ++m)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) au[m][q][0] = au[m][q][1] = aw[m][q][0] = aw[m][q][1] = 0.0;
+        for (int q = 0; q < 4; ++q) {
+            au[m][q][0] = au[m][q][1] = 0.0;
+            if (WM == 1 || m == 0) aw[WM == 1 ? m : 0][q][0] = aw[WM == 1 ? m : 0][q][1] = 0.0;
+        }
     __syncthreads();
 
     const double wmax = WEIGHTED ? a.wmax[0] : 0.0;
@@ -422,7 +428,22 @@ __global__ void __launch_bounds__(NW * 32, 1) k_gram2(const GramArgs a, const __
         mbar_wait(bar, phase);
         const int64_t ip = i0 + pw + 2 * lc;
         const bool v0 = ip < a.n, v1 = ip + 1 < a.n;
-        if (i0 + P <= a.n) {  // full tile (all but the last one): no column selects
+        // weights of the warp's 8 columns (lane l < 8 owns particle pw + l), failure count
+        double wv = 0.0;
+        if (lane < 8) {
+            const bool v = i0 + pw + lane < a.n;
+            if (WEIGHTED) wv = (v && isfinite(a_nxt)) ? exp(a_nxt - wmax) : 0.0;
+            if (WM == 1) asm volatile("st.shared.f64 [%0], %1;" ::"r"(wbuf + (uint32_t)(pw + lane) * 8u), "d"(wv) : "memory");
+            if (WM != 2) n_fail += (v && g_nxt <= 0.0) ? 1.0 : 0.0;
+        }
+        // column factors of the rewrite: 1 (0 for padding), or sqrt(w) when the tile itself carries the weights
+        double f0 = v0 ? 1.0 : 0.0, f1 = v1 ? 1.0 : 0.0;
+        if (WM == 2) {
+            const double sw = sqrt(wv);
+            f0 = __shfl_sync(0xffffffffu, sw, 2 * lc);
+            f1 = __shfl_sync(0xffffffffu, sw, 2 * lc + 1);
+        }
+        if (WM != 2 && i0 + P <= a.n) {  // full tile (all but the last one): no column selects
 #pragma unroll
             for (int mt = 0; mt < NTB; ++mt) {
                 if (EXACT ? (mt < NTB - 1) : (mt < ntd - 1)) {  // all 8 rows of the tile are dimensions
@@ -439,34 +460,27 @@ __global__ void __launch_bounds__(NW * 32, 1) k_gram2(const GramArgs a, const __
                     const uint32_t sa = buf + own_off + (uint32_t)(8 * mt * S * 8);
                     const double2 xv = lds128(sa);
                     const double srow = lds64(vs_addr + (uint32_t)((8 * mt + lr) * 8));
-                    sts128(sa, make_double2(v0 ? xv.x - srow : 0.0, v1 ? xv.y - srow : 0.0));
+                    // select, not multiply, for padding: padded lanes may hold anything
+                    sts128(sa, make_double2(f0 != 0.0 ? (xv.x - srow) * f0 : 0.0, f1 != 0.0 ? (xv.y - srow) * f1 : 0.0));
                 }
             }
         }
-        {  // last dimension tile: rows >= d are zero, row d (if it falls into this tile) is the row of ones
+        {  // last dimension tile: rows >= d are zero, row d (if it falls into this tile) is the row of ones / sqrt(w)
             const int mt = ntd - 1, row = 8 * mt + lr;
             const uint32_t sa = buf + own_off + (uint32_t)(8 * mt * S * 8);
             const double2 xv = lds128(sa);
             const double srow = lds64(vs_addr + (uint32_t)(row * 8));
             double2 y;
-            y.x = (row < d && v0) ? xv.x - srow : 0.0;  // select, not multiply: padded lanes may hold anything
-            y.y = (row < d && v1) ? xv.y - srow : 0.0;
+            y.x = (row < d && f0 != 0.0) ? (xv.x - srow) * f0 : 0.0;
+            y.y = (row < d && f1 != 0.0) ? (xv.y - srow) * f1 : 0.0;
             if (row == d) {
-                y.x = v0 ? 1.0 : 0.0;
-                y.y = v1 ? 1.0 : 0.0;
+                y.x = f0;
+                y.y = f1;
             }
             sts128(sa, y);
         }
         if (nta > ntd && lr == 0)  // d % 8 == 0: the augmented row lives in a tile of its own
-            sts128(buf + (uint32_t)((d * S + pw + 2 * lc) * 8), make_double2(v0 ? 1.0 : 0.0, v1 ? 1.0 : 0.0));
-        if (lane < 8) {
-            const bool v = i0 + pw + lane < a.n;
-            if (WEIGHTED) {
-                const double wv = (v && isfinite(a_nxt)) ? exp(a_nxt - wmax) : 0.0;
-                asm volatile("st.shared.f64 [%0], %1;" ::"r"(wbuf + (uint32_t)(pw + lane) * 8u), "d"(wv) : "memory");
-            }
-            n_fail += (v && g_nxt <= 0.0) ? 1.0 : 0.0;
-        }
+            sts128(buf + (uint32_t)((d * S + pw + 2 * lc) * 8), make_double2(f0, f1));
         __syncwarp();
         if (lane == 0) mbar_arrive(rdy);  // release: this warp's part of the buffer is final
     };
@@ -498,7 +512,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_gram2(const GramArgs a, const __
         mbar_wait(rdy0 + (b ? 8u : 0u), ph);  // acquire: every warp's part of tile k is in place
 #pragma unroll 1
         for (int c = 0; c < NCH; ++c) {
-            gram2_accumulate<MAXM, S, CH, WEIGHTED>(buf + (uint32_t)(c * CH * 64),
+            gram2_accumulate<MAXM, S, CH, WM == 1>(buf + (uint32_t)(c * CH * 64),
                                                     wbuf + (uint32_t)(((grp * UPG + c * CH) * 8 + 2 * lc) * 8), gr, au, aw);
             if (more && c == slot) prepare(i0n, nbuf, nwbuf, bar0 + (b ? 0u : 8u), rdy0 + (b ? 0u : 8u), nph);
         }
@@ -515,8 +529,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_gram2(const GramArgs a, const __
     }
     const int T = nta * (nta + 1) / 2;
     const size_t poff = ((size_t)blockIdx.x * KS + grp) * T * 64;
-    gram2_store<MAXM>(a.part_u + poff, a.plan, wi, nmac, nta, lr, lc, au);
-    if (WEIGHTED) gram2_store<MAXM>(a.part_w + poff, a.plan, wi, nmac, nta, lr, lc, aw);
+    gram2_store<MAXM>((WM == 2 ? a.part_w : a.part_u) + poff, a.plan, wi, nmac, nta, lr, lc, au);
+    if constexpr (WM == 1) gram2_store<MAXM>(a.part_w + poff, a.plan, wi, nmac, nta, lr, lc, aw);
     n_fail = block_sum(n_fail, red);
     if (tid == 0) a.small[blockIdx.x] = n_fail;
 }
@@ -553,6 +567,7 @@ static bool pick_split(int d, SplitCfg& c) {
     if (d < split_min_d()) return false;
     if (d <= 55) c = {7, 16, 8, 3, 2};
     else if (d <= 103) c = {13, 16, 12, 3, 1};
+    else if (d <= 151) c = {19, 8, 8, 7, 1};  // PDE problem (d = 150): Lf 97 KB + 8 staging blocks, 152-row Gram tiles
     else return false;
     return true;
 }
@@ -587,6 +602,14 @@ static int launch_xf_bucket(const SplitCfg& c, const XfArgs& a, cudaStream_t st)
         const int64_t want = (nwt + 15) / 16;
         return launch_xf_exact<MODE, 7, 16, TRI>(a, (int)(want < sms ? want : sms), st);
     }
+    if (c.ntb == 19) {
+        if constexpr (TRI) {
+            const int64_t want = (nwt + 7) / 8;
+            return launch_xf_exact<MODE, 19, 8, TRI>(a, (int)(want < sms ? want : sms), st);
+        } else {
+            return ree_set_error(REE_E_UNSUPPORTED, "split path: a dense factor at d > 103 uses the modular kernel");
+        }
+    }
     if constexpr (TRI) {
         if (MODE == 1 && (a.d + 7) / 8 == 13 && xf_variant() > 0) {  // tuning hook: warps x Philox batch
             const int v = xf_variant();
@@ -606,7 +629,7 @@ static int launch_xf_bucket(const SplitCfg& c, const XfArgs& a, cudaStream_t st)
     }
 }
 
-template <int NTB, int NW, int MAXM, int KS, bool EXACT, bool WEIGHTED>
+template <int NTB, int NW, int MAXM, int KS, bool EXACT, int WM>
 static int launch_g2(const GramArgs& a, int grid, cudaStream_t st) {
     constexpr int P = NW * 8, S = P + 8, ROWS = 8 * NTB;
     constexpr size_t smem = ((size_t)2 * ROWS * S + 2 * P + 8 * NTB) * sizeof(double);
@@ -614,19 +637,16 @@ static int launch_g2(const GramArgs& a, int grid, cudaStream_t st) {
     CUtensorMap tmap;
     int rc = make_ensemble_tmap(&tmap, a.x, a.ld, a.d, S, ROWS);
     if (rc) return rc;
-    auto kern = k_gram2<NTB, NW, MAXM, KS, EXACT, WEIGHTED>;
+    auto kern = k_gram2<NTB, NW, MAXM, KS, EXACT, WM>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, NW * 32, smem, st>>>(a, tmap);
     return ree_check_launch("k_gram2");
 }
 
-template <int NTB, int NW, int MAXM, int KS>
-static int launch_g2_variants(const GramArgs& a, int grid, bool weighted, cudaStream_t st) {
-    const bool exact = (a.d + 7) / 8 == NTB;
-    if (weighted) return exact ? launch_g2<NTB, NW, MAXM, KS, true, true>(a, grid, st)
-                               : launch_g2<NTB, NW, MAXM, KS, false, true>(a, grid, st);
-    return exact ? launch_g2<NTB, NW, MAXM, KS, true, false>(a, grid, st)
-                 : launch_g2<NTB, NW, MAXM, KS, false, false>(a, grid, st);
+template <int NTB, int NW, int MAXM, int KS, int WM>
+static int launch_g2_variants(const GramArgs& a, int grid, cudaStream_t st) {
+    if ((a.d + 7) / 8 == NTB) return launch_g2<NTB, NW, MAXM, KS, true, WM>(a, grid, st);
+    return launch_g2<NTB, NW, MAXM, KS, false, WM>(a, grid, st);
 }
 
 // ---- entry points used by ree_step.cu -----------------------------------------------------------
@@ -651,7 +671,7 @@ int ree_split_maha(const double* x, int64_t n, int d, int64_t ld, const double* 
     a.x = x; a.n = n; a.ld = ld; a.d = d; a.A = Linv; a.g = g; a.e = e; a.mean = mean; a.logdet = logdet;
     a.logq = logq; a.small = ws_small;
     const int sms = ree_grid_ctas() / 2;
-    const int64_t want = ((n + 7) / 8 + 15) / 16;
+    const int64_t want = ((n + 7) / 8 + c.xf_nw - 1) / c.xf_nw;
     const int grid = (int)(want < sms ? want : sms);
     int rc = launch_xf_bucket<2, true>(c, a, st);
     if (rc) return rc;
@@ -675,12 +695,22 @@ int ree_split_moments(const double* x, int64_t n, int d, int64_t ld, const doubl
     a.part_w = ws_big + (size_t)grid * c.g_ks * T * 64;
     a.small = ws_small;
     make_plan(a.plan, nta, c.g_nw / c.g_ks, c.g_maxm);
-    int rc = (c.ntb == 7) ? launch_g2_variants<7, 8, 3, 2>(a, grid, weighted, st)
-                          : launch_g2_variants<13, 12, 3, 1>(a, grid, weighted, st);
+    int rc;
+    if (c.ntb == 19) {  // no registers for two accumulator sets: unweighted pass first
+        rc = launch_g2_variants<19, 8, 7, 1, 0>(a, grid, st);
+    } else if (c.ntb == 7) {
+        rc = weighted ? launch_g2_variants<7, 8, 3, 2, 1>(a, grid, st) : launch_g2_variants<7, 8, 3, 2, 0>(a, grid, st);
+    } else {
+        rc = weighted ? launch_g2_variants<13, 12, 3, 1, 1>(a, grid, st) : launch_g2_variants<13, 12, 3, 1, 0>(a, grid, st);
+    }
     if (rc) return rc;
     rc = ree_mma_unpack(a.part_u, grid * c.g_ks, d, 0, sums_u, st);
     if (rc) return rc;
     rc = ree_mma_sum_small(ws_small, grid, sums_u + d + (size_t)d * d, st);
     if (rc || !weighted) return rc;
+    if (c.ntb == 19) {  // ... then the pass over the sqrt(w)-scaled tile
+        rc = launch_g2_variants<19, 8, 7, 1, 2>(a, grid, st);
+        if (rc) return rc;
+    }
     return ree_mma_unpack(a.part_w, grid * c.g_ks, d, 1, sums_w, st);
 }

@@ -350,6 +350,20 @@ extern "C" int ree_cbree_step(const double* x, double* x_new, int64_t n, int d, 
     cudaStream_t st = ree_stream(stream);
     const bool fused_lsf = lsf && lsf->kind == REE_LSF_AFFINE;
     if (lsf && lsf->kind != REE_LSF_EXTERNAL && !g_new) return ree_set_error(REE_E_BADARG, "ree_cbree_step: g_new is NULL");
+    if (!sums && noise_mode == REE_NOISE_INJECT && d > 103) {
+        // parity-mode (dense) factor beyond the DMMA transform's shared-memory budget: modular transform, no Gram
+        size_t smem = (size_t)d * TP * sizeof(double);
+        if (smem > 200 * 1024) return ree_set_error(REE_E_UNSUPPORTED, "ree_cbree_step: d too large");
+        StepArgs a{};
+        a.x = x; a.x_new = x_new; a.n = n; a.ld = ld; a.d = d; a.t = t; a.m_noise = m_noise; a.A = F; a.z = z;
+        a.seed = seed; a.draw = draw; a.first = first_particle; a.e_new = e_new;
+        cudaFuncSetAttribute(k_contract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_contract<0><<<contract_grid(n), TP, smem, st>>>(a);
+        int rc = ree_check_launch("ree_cbree_step(transform)");
+        if (rc) return rc;
+        if (lsf && lsf->kind != REE_LSF_EXTERNAL) return ree_lsf_launch(lsf, x_new, n, ld, g_new, st);
+        return 0;
+    }
     if (!sums) {  // split path: transform only
         const int tri = (noise_mode == REE_NOISE_PHILOX) ? 1 : 0;
         int lsf_mode = fused_lsf ? (lsf->coef ? 1 : 2) : 0;

@@ -365,7 +365,7 @@ class Engine:
     def cbree_maha(self, ens: Ensemble, mean, Linv, logdet, sigma, beta, kind, wmax, sums, is4, w=None, logq=None):
         """Sweep 2.  The weighted sums come back shifted by ``mean``."""
         ws = self.workspace(ens.d)
-        if w is None and sums is not None and not self.lib.ree_fused_path(ens.d):
+        if w is None and sums is not None and ens.d > 103:  # two-sweep calling sequence on the modular kernels
             w = self.empty(ens.ld)
         check(self.lib.ree_cbree_maha(ens.X.data_ptr(), ens.n, ens.d, ens.ld, ens.g.data_ptr(), ens.e.data_ptr(),
                                       mean.data_ptr(), Linv.data_ptr(), logdet.data_ptr(), float(sigma),

@@ -1,4 +1,4 @@
-"""GPU tests of the split DMMA path (ree_split.cu; ree_fused_path(d) == 2, 56 <= d <= 103): the transform-only step,
+"""GPU tests of the split DMMA path (ree_split.cu; ree_fused_path(d) == 2, 56 <= d <= 151): the transform-only step,
 the one-pass double Gram and the transform-only Mahalanobis kernel against the fused sweeps (same C ABI, sums != NULL)
 and against NumPy restatements of the reference formulas (solver.py:629-636, 665-674, 683-686)."""
 import numpy as np
@@ -28,7 +28,8 @@ def _setup(eng, n, d, seed):
     return rng, X, F, src, lsf, m_noise
 
 
-@pytest.mark.parametrize("n,d", [(1, 100), (7, 56), (96, 100), (1001, 100), (4099, 64), (3000, 103)])
+@pytest.mark.parametrize("n,d", [(1, 100), (7, 56), (96, 100), (1001, 100), (4099, 64), (3000, 103), (1000, 150),
+                                 (777, 120), (65, 151)])
 def test_split_step_matches_numpy_and_fused(eng, n, d):
     assert eng.path(d) == 2
     rng, X, F, src, lsf, m_noise = _setup(eng, n, d, n + d)
@@ -65,7 +66,7 @@ def test_split_step_matches_numpy_and_fused(eng, n, d):
     assert ss[d + d * d] == sf[d + d * d] == np.sum(c.g[:n].cpu().numpy() <= 0) and ss[d + d * d + 1] == n
 
 
-@pytest.mark.parametrize("n,d", [(5, 100), (1500, 100), (2500, 72)])
+@pytest.mark.parametrize("n,d", [(5, 100), (1500, 100), (2500, 72), (1200, 150), (900, 111)])
 def test_split_moments_and_maha_match_numpy(eng, n, d):
     rng = np.random.default_rng(n * d)
     X = rng.standard_normal((n, d)) @ (np.eye(d) + 0.1 * rng.standard_normal((d, d))) + 0.2

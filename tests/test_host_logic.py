@@ -36,7 +36,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert set(_lib.PROTOTYPES) <= set(names)
     assert lib.ree_abi_version() == _lib.ABI_VERSION
     assert lib.ree_sums_len(100) == 100 + 100 * 100 + 2
-    assert lib.ree_fused_path(100) == 2 and lib.ree_fused_path(6) == 1 and lib.ree_fused_path(150) == 0
+    assert lib.ree_fused_path(100) == 2 and lib.ree_fused_path(6) == 1 and lib.ree_fused_path(150) == 2 and lib.ree_fused_path(200) == 0
 
 
 def test_shared_object_is_sm100a_only():
