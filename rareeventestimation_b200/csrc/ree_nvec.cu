@@ -52,6 +52,125 @@ __device__ __forceinline__ Quad ldg_quad(const double* p) {
 }
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// ---------------------------------------------------------------------------------------
+// Shifted exponential sums at streaming speed.  The generic expsums_add costs two libdevice exp calls and a divergent
+// branch per element (127 instructions per element in k_reduce_scaled: issue-bound at 1.4 TB/s, profiles/
+// r1_nvec_small_ncu.txt).  Here a thread raises its running shift once per group of four elements (rare after the first
+// few groups) and evaluates exp(v - shift) for arguments <= 0 with a 64-entry table of 2^(j/64) in shared memory and a
+// degree-5 polynomial: exp(x) = 2^e * 2^(j/64) * exp(r), n = rint(x * 64/ln2) = 64 e + j, |r| <= ln2/128, relative
+// error <= 1.2 ulp (r^6/720 < 4e-17), 10 fp64 instructions.  Arguments below -708 give 0 (the reference's exp
+// underflows to subnormals there: relative weight < 1e-307).
+// ---------------------------------------------------------------------------------------
+#include "exp_table.cuh"
+
+__device__ __forceinline__ uint32_t load_exp_table(double* T) {  // returns the 32-bit shared address of the table
+    for (int j = threadIdx.x; j < 64; j += blockDim.x) T[j] = EXP2_64[j];
+    __syncthreads();
+    return (uint32_t)__cvta_generic_to_shared(T);
+}
+
+// branch-free; x <= 0, -inf or NaN (NaN / -inf / x < -708 -> 0)
+__device__ __forceinline__ double exp_nonpos(double x, uint32_t T) {
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: the low word of x*c + MAGIC is rint(x*c)
+    const double t = fma(x, 92.33248261689366, MAGIC);
+    const int n = __double2loint(t);
+    const double nd = t - MAGIC;
+    double r = fma(nd, -0x1.62e42ff000000p-7, x);  // ln2/64 = hi + lo, nd*hi exact
+    r = fma(nd, 0x1.718432a1b0e26p-41, r);
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    double tj;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(T + (uint32_t)((n & 63) << 3)));
+    const double v = tj * p;
+    const double scaled = __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+    return x >= -708.0 ? scaled : 0.0;
+}
+
+struct ExpAcc {  // per-thread running (shift, sum, sum of squares, count)
+    double m, s1, s2;
+    unsigned int cnt;
+};
+__device__ __forceinline__ ExpAcc expacc_empty() { return ExpAcc{-CUDART_INF, 0.0, 0.0, 0u}; }
+
+__device__ __forceinline__ void expacc_raise(ExpAcc& a, double m_new, uint32_t T) {
+    if (m_new > a.m) {  // exp(-inf) = 0 on the first group
+        const double f = exp_nonpos(a.m - m_new, T);
+        a.s1 *= f;
+        a.s2 *= f * f;
+        a.m = m_new;
+    }
+}
+
+__device__ __forceinline__ void expacc_add4(ExpAcc& a, const double (&v)[4], uint32_t T) {
+    bool ok[4];
+    double m4 = -CUDART_INF;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ok[k] = isfinite(v[k]);
+        m4 = (ok[k] && v[k] > m4) ? v[k] : m4;  // compare + select (fmax carries NaN handling: ~10 instructions)
+    }
+    expacc_raise(a, m4, T);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double w = exp_nonpos(ok[k] ? v[k] - a.m : -CUDART_INF, T);  // select the argument: no branch
+        a.s1 += w;
+        a.s2 = fma(w, w, a.s2);
+        a.cnt += ok[k] ? 1u : 0u;
+    }
+}
+
+__device__ __forceinline__ void expacc_add1(ExpAcc& a, double v, uint32_t T) {
+    if (!isfinite(v)) return;
+    expacc_raise(a, v, T);
+    const double w = exp_nonpos(v - a.m, T);
+    a.s1 += w;
+    a.s2 = fma(w, w, a.s2);
+    a.cnt += 1u;
+}
+
+__device__ __forceinline__ ExpSums expacc_finish(const ExpAcc& a) { return ExpSums{a.m, a.s1, a.s2, (double)a.cnt}; }
+
+// quad streams: `quad(i0, q...)` sees four consecutive elements starting at i0 (a multiple of 4), `one(i, ...)` the tail
+template <class QuadFn, class OneFn>
+__device__ __forceinline__ void stream1q(const double* __restrict__ a, int64_t n, QuadFn quad, OneFn one) {
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nq = aligned16(a) ? n / 4 : 0;
+    int64_t q = gt;
+    Quad cur{};
+    if (q < nq) cur = ldg_quad(a + 4 * q);
+    for (; q < nq; q += stride) {
+        const Quad now = cur;
+        if (q + stride < nq) cur = ldg_quad(a + 4 * (q + stride));
+        quad(4 * q, now);
+    }
+    for (int64_t i = 4 * nq + gt; i < n; i += stride) one(i, a[i]);
+}
+
+template <class QuadFn, class OneFn>
+__device__ __forceinline__ void stream2q(const double* __restrict__ a, const double* __restrict__ b, int64_t n,
+                                         QuadFn quad, OneFn one) {
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nq = (aligned16(a) && aligned16(b)) ? n / 4 : 0;
+    int64_t q = gt;
+    Quad ca{}, cb{};
+    if (q < nq) {
+        ca = ldg_quad(a + 4 * q);
+        cb = ldg_quad(b + 4 * q);
+    }
+    for (; q < nq; q += stride) {
+        const Quad na = ca, nb = cb;
+        if (q + stride < nq) {
+            ca = ldg_quad(a + 4 * (q + stride));
+            cb = ldg_quad(b + 4 * (q + stride));
+        }
+        quad(4 * q, na, nb);
+    }
+    for (int64_t i = 4 * nq + gt; i < n; i += stride) one(i, a[i], b[i]);
+}
+
 template <class Body>
 __device__ __forceinline__ void stream1(const double* __restrict__ a, int64_t n, Body body) {
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
@@ -103,15 +222,31 @@ __global__ void __launch_bounds__(REE_THREADS) k_reduce_ess(const double* __rest
                                                             double* __restrict__ a_out, double* ws, double* out4) {
     __shared__ ExpSums sh[32];
     __shared__ bool is_last;
-    ExpSums acc = expsums_empty();
-    auto body = [&](int64_t i, double gi, double ei) {
-        double a = __dmul_rn(ree_logtgt(gi, ei, sigma, kind), beta);
-        if (a_out) a_out[i] = a;
-        if (isfinite(a)) expsums_add(acc, a, 1.0);
+    __shared__ double Tsh[64];
+    const uint32_t T = load_exp_table(Tsh);
+    ExpAcc acc = expacc_empty();
+    const bool vec_out = a_out && aligned16(a_out);
+    auto quad = [&](int64_t i0, const Quad& gq, const Quad& eq) {
+        double a[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = __dmul_rn(ree_logtgt(gq.v[k], eq.v[k], sigma, kind), beta);
+        if (vec_out) {
+            reinterpret_cast<double2*>(a_out + i0)[0] = make_double2(a[0], a[1]);
+            reinterpret_cast<double2*>(a_out + i0)[1] = make_double2(a[2], a[3]);
+        } else if (a_out) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a_out[i0 + k] = a[k];
+        }
+        expacc_add4(acc, a, T);
     };
-    if (e) stream2(g, e, n, body);
-    else stream1(g, n, [&](int64_t i, double gi) { body(i, gi, 0.0); });
-    ExpSums blk = expsums_block_reduce(acc, sh);
+    auto one = [&](int64_t i, double gi, double ei) {
+        const double a = __dmul_rn(ree_logtgt(gi, ei, sigma, kind), beta);
+        if (a_out) a_out[i] = a;
+        expacc_add1(acc, a, T);
+    };
+    if (e) stream2q(g, e, n, quad, one);
+    else stream1q(g, n, [&](int64_t i0, const Quad& gq) { quad(i0, gq, Quad{}); }, [&](int64_t i, double gi) { one(i, gi, 0.0); });
+    ExpSums blk = expsums_block_reduce(expacc_finish(acc), sh);
     expsums_grid_finalize(blk, ws, out4, sh, &is_last);
 }
 
@@ -121,12 +256,18 @@ __global__ void __launch_bounds__(REE_THREADS) k_reduce_scaled(const double* __r
                                                                double* ws, double* out4) {
     __shared__ ExpSums sh[32];
     __shared__ bool is_last;
-    ExpSums acc = expsums_empty();
-    stream1(ell, n, [&](int64_t, double li) {
-        double a = __dmul_rn(li, scale);
-        if (isfinite(a)) expsums_add(acc, a, 1.0);
-    });
-    ExpSums blk = expsums_block_reduce(acc, sh);
+    __shared__ double Tsh[64];
+    const uint32_t T = load_exp_table(Tsh);
+    ExpAcc acc = expacc_empty();
+    stream1q(ell, n,
+             [&](int64_t, const Quad& lq) {
+                 double a[4];
+#pragma unroll
+                 for (int k = 0; k < 4; ++k) a[k] = __dmul_rn(lq.v[k], scale);
+                 expacc_add4(acc, a, T);
+             },
+             [&](int64_t, double li) { expacc_add1(acc, __dmul_rn(li, scale), T); });
+    ExpSums blk = expsums_block_reduce(expacc_finish(acc), sh);
     expsums_grid_finalize(blk, ws, out4, sh, &is_last);
 }
 
@@ -166,12 +307,21 @@ __global__ void __launch_bounds__(REE_THREADS) k_reduce_cvar(const double* __res
                                                              double* ws, double* out4) {
     __shared__ ExpSums sh[32];
     __shared__ bool is_last;
-    ExpSums acc = expsums_empty();
-    stream1(g, n, [&](int64_t, double gi) {
-        double a = __dsub_rn(ree_logtgt(gi, 0.0, sigma_new, kind), ree_logtgt(gi, 0.0, sigma_old, kind));
-        if (isfinite(a)) expsums_add(acc, a, 1.0);
-    });
-    ExpSums blk = expsums_block_reduce(acc, sh);
+    __shared__ double Tsh[64];
+    const uint32_t T = load_exp_table(Tsh);
+    ExpAcc acc = expacc_empty();
+    auto val = [&](double gi) {
+        return __dsub_rn(ree_logtgt(gi, 0.0, sigma_new, kind), ree_logtgt(gi, 0.0, sigma_old, kind));
+    };
+    stream1q(g, n,
+             [&](int64_t, const Quad& gq) {
+                 double a[4];
+#pragma unroll
+                 for (int k = 0; k < 4; ++k) a[k] = val(gq.v[k]);
+                 expacc_add4(acc, a, T);
+             },
+             [&](int64_t, double gi) { expacc_add1(acc, val(gi), T); });
+    ExpSums blk = expsums_block_reduce(expacc_finish(acc), sh);
     expsums_grid_finalize(blk, ws, out4, sh, &is_last);
 }
 

@@ -216,6 +216,174 @@ __global__ void __launch_bounds__(NW * 32, 1) k_xform(const XfArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// warp-specialised transform (Philox noise): NC consumer warps run the LDS + DMMA stream of k_xform<1>, NC producer
+// warps run Philox + Box-Muller and hand finished B fragments over through shared memory.
+//
+// Why: a warp issues in order.  In k_xform<1> every warp interleaves ~2500 integer / fp64 instructions of noise
+// generation with 182 DMMAs per tile; whenever its next instruction is a DMMA and the tensor pipe is busy, the ~14
+// independent Philox instructions behind it wait as well (math_pipe_throttle is the top stall, pipe 54 % busy, issue
+// 41 %: profiles/r1_split_kernels_ncu.txt).  With the two instruction streams in different warps the scheduler always
+// has a producer warp to issue while the consumers queue on the pipe.
+//
+// Hand-over: per consumer two noise buffers of NTB k-pairs x 32 lanes x (b0, b1); the producer lane with the same lane
+// id computes exactly the consumer lane's fragment values (Philox counter = (particle lr, pair 4q + lc)), so both sides
+// use conflict-free 16-byte accesses at lane * 16.  full/empty mbarriers per buffer, one elected arrival per warp.
+// ---------------------------------------------------------------------------------------
+struct GenNoise {  // B fragments of k-pair q from the consumer's noise buffer
+    uint32_t addr;  // buffer + lane * 16
+    __device__ __forceinline__ void operator()(int q, double& b0, double& b1) const {
+        const double2 v = lds128(addr + (uint32_t)(q * 512));
+        b0 = v.x;
+        b1 = v.y;
+    }
+};
+
+// NPC producer warps per consumer share one tile (k-pairs q = h, h + NPC, ...): a producer's fp64 instructions queue
+// behind the 16-cycle DMMAs of the shared pipe, so one producer per consumer is latency-bound at ~2.4 consumer tile
+// times.  With NPC > 1 the CTA has more than 512 threads; setmaxnreg moves registers from the producers (RP) to the
+// consumers (RC), whose 2 * NTB accumulators + fragment prefetch do not fit the launch-time allocation.
+template <int NTB, int NC, int NPC, bool EXACT, int PGB, int RC, int RP>
+__global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArgs a) {
+    constexpr int MT = (1 + NPC) * NC * 32;
+    constexpr int ROWS = 8 * NTB;
+    constexpr int STG = ROWS * 8;   // doubles of one consumer's X staging block: [row][8 particles]
+    constexpr int NZ = NTB * 64;    // doubles of one noise buffer: [k-pair][lane][2]
+    extern __shared__ double sm[];
+    const int d = a.d, ntd = (d + 7) >> 3;
+    double* Lf = sm;
+    double* nz = Lf + lf_doubles<NTB, true>();
+    double* stg = nz + NC * 2 * NZ;
+    double* vm = stg + NC * STG;
+    double* vc = vm + 8 * NTB;
+    double* bm = vc + 8 * NTB;
+    __shared__ __align__(8) unsigned long long bars[NC][2][2];  // [consumer][buffer][0: full, 1: empty]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lc = lane & 3;
+
+    pack_matrix<NTB, true, MT>(Lf, a.A, d);
+    for (int j = tid; j < 8 * NTB; j += MT) {
+        vm[j] = (j < d) ? a.m_noise[j] : 0.0;
+        vc[j] = (j < d) ? (a.lsf_mode == 1 ? a.coef[j] : 1.0) : 0.0;
+    }
+    for (int idx = tid; idx < NC * STG; idx += MT) stg[idx] = 0.0;
+    for (int idx = tid; idx < BM_TABLE_DOUBLES; idx += MT) bm[idx] = BM_TABLE[idx];
+    if (tid < NC * 4) mbar_init(smem_u32(&bars[0][0][0]) + 8u * (uint32_t)tid, (tid & 1) ? 1 : NPC);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const int64_t nwt = (a.n + 7) >> 3;
+    const int64_t stride = (int64_t)gridDim.x * NC;
+    const int c = warp % NC, h = warp / NC - 1;  // consumer c; producer h = 0 .. NPC-1 of consumer c
+    const uint32_t bar_c = smem_u32(&bars[c][0][0]);           // + 16 b (+ 8 for empty)
+    const uint32_t nz_c = smem_u32(nz + c * 2 * NZ) + lane * 16;  // + b * NZ * 8
+
+    if (warp >= NC) {
+        // ---------------- producer: Philox + Box-Muller for consumer c ----------------
+        if constexpr (RP > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RP));
+        BmTableShared tab;
+        tab.addr = smem_u32(bm);
+        int k = 0;
+        for (int64_t wt = (int64_t)blockIdx.x * NC + c; wt < nwt; wt += stride, ++k) {
+            const uint32_t b = (uint32_t)k & 1u, ph = ((uint32_t)k >> 1) & 1u;
+            const uint32_t buf = nz_c + b * (uint32_t)(NZ * 8);
+            mbar_wait(bar_c + 16u * b + 8u, ph ^ 1u);  // buffer b is free (passes at once the first two times)
+            const uint64_t particle = (uint64_t)(a.first + wt * 8 + lr);
+            constexpr int NQ = (NTB + NPC - 1) / NPC;  // k-pairs q = h + NPC * i, i < NQ
+#pragma unroll
+            for (int i0 = 0; i0 < NQ; i0 += PGB) {
+                double z0[PGB], z1[PGB];
+#pragma unroll
+                for (int j = 0; j < PGB; ++j) {
+                    const int q = h + NPC * (i0 + j);
+                    if (i0 + j < NQ && q < (EXACT ? NTB : ntd))
+                        philox_normal_pair(a.seed, particle, (uint32_t)(4 * q) + (uint32_t)lc, a.draw, tab, z0[j], z1[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < PGB; ++j) {
+                    const int q = h + NPC * (i0 + j);
+                    if (i0 + j < NQ && q < (EXACT ? NTB : ntd))
+                        sts128(buf + (uint32_t)(q * 512), make_double2(z0[j], z1[j]));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_c + 16u * b);
+        }
+        return;
+    }
+
+    // ---------------- consumer: F z on the tensor pipe, update, g', e' ----------------
+    if constexpr (RC > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RC));
+    const uint32_t lf_lane = smem_u32(Lf) + lane * 8;
+    const uint32_t stg_w = smem_u32(stg + warp * STG);
+    const uint32_t own = stg_w + (uint32_t)(lr * 64 + lc * 16);  // rows 8mt+lr, columns 2lc, 2lc+1
+    const double e_const = (double)d * REE_LOG_2PI;
+    auto prefetch = [&](int64_t wt) {
+        const double* src = a.x + wt * 8 + 2 * lc;
+#pragma unroll
+        for (int mt = 0; mt < NTB; ++mt) {
+            const int row = 8 * mt + lr;
+            if (row < d) cp_async16(own + (uint32_t)(mt * 512), src + (int64_t)row * a.ld);
+        }
+    };
+    int64_t wt = (int64_t)blockIdx.x * NC + warp;
+    if (wt < nwt) prefetch(wt);
+    int k = 0;
+    for (; wt < nwt; wt += stride, ++k) {
+        const int64_t ip = wt * 8 + 2 * lc;
+        const uint32_t b = (uint32_t)k & 1u, ph = ((uint32_t)k >> 1) & 1u;
+        double c2[NTB][2];
+#pragma unroll
+        for (int mt = 0; mt < NTB; ++mt) c2[mt][0] = c2[mt][1] = 0.0;
+        mbar_wait(bar_c + 16u * b, ph);
+        GenNoise gen;
+        gen.addr = nz_c + b * (uint32_t)(NZ * 8);
+        transform_tiles<NTB, true, EXACT, 3>(lf_lane, ntd, gen, c2);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_c + 16u * b + 8u);  // every fragment of the buffer has been read
+        cp_async_wait_all();  // own elements only: no warp barrier needed
+        double se0 = 0.0, se1 = 0.0, sg0 = 0.0, sg1 = 0.0;
+#pragma unroll
+        for (int mt = 0; mt < NTB; ++mt) {
+            if (EXACT || mt < ntd) {
+                const int row = 8 * mt + lr;
+                if (row < d) {
+                    const double2 xv = lds128(own + (uint32_t)(mt * 512));
+                    const double mrow = vm[row], crow = vc[row];
+                    double2 xn;  // t*X + (m_noise + Z F^T): grouping of solver.py:667
+                    xn.x = __dadd_rn(__dmul_rn(a.t, xv.x), __dadd_rn(mrow, c2[mt][0]));
+                    xn.y = __dadd_rn(__dmul_rn(a.t, xv.y), __dadd_rn(mrow, c2[mt][1]));
+                    *reinterpret_cast<double2*>(a.x_new + (int64_t)row * a.ld + ip) = xn;
+                    se0 = fma(xn.x, xn.x, se0);
+                    se1 = fma(xn.y, xn.y, se1);
+                    sg0 = fma(crow, xn.x, sg0);
+                    sg1 = fma(crow, xn.y, sg1);
+                }
+            }
+        }
+        if (wt + stride < nwt) prefetch(wt + stride);
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            se0 += __shfl_xor_sync(0xffffffffu, se0, o);
+            se1 += __shfl_xor_sync(0xffffffffu, se1, o);
+            sg0 += __shfl_xor_sync(0xffffffffu, sg0, o);
+            sg1 += __shfl_xor_sync(0xffffffffu, sg1, o);
+        }
+        if (lr == 0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (ip + h < a.n) {
+                    const double s = h ? se1 : se0, gsum = h ? sg1 : sg0;
+                    if (a.e_new) a.e_new[ip + h] = 0.5 * (e_const + s);
+                    if (a.lsf_mode)
+                        a.g_new[ip + h] = (a.lsf_mode == 1)
+                                              ? __dadd_rn(gsum, a.offset)
+                                              : __dadd_rn(__ddiv_rn(-gsum, __dsqrt_rn((double)d)), a.offset);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Gram kernel: unweighted and weighted shifted Grams of an ensemble in one pass
 // ---------------------------------------------------------------------------------------
 struct GramArgs {
@@ -588,6 +756,47 @@ static int launch_xf(const XfArgs& a, int grid, cudaStream_t st) {
     return ree_check_launch(MODE == 1 ? "k_xform<1>" : "k_xform<2>");
 }
 
+static int xf_ws() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("REE_XF_WS");  // tuning / test hook: 0 runs the unspecialised k_xform<1> for Philox noise
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
+template <int NTB, int NC, int NPC, bool EXACT, int PGB, int RC, int RP>
+static int launch_xf_ws(const XfArgs& a, int grid, cudaStream_t st) {
+    constexpr size_t smem = ((size_t)lf_doubles<NTB, true>() + (size_t)NC * 3 * NTB * 64 + 2 * 8 * NTB +
+                             BM_TABLE_DOUBLES + 2) * sizeof(double);
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    static_assert(RC == 0 || (NC * RC + NC * NPC * RP) * 32 <= 65536 / ((1 + NPC) * NC * 32) / 8 * 8 * (1 + NPC) * NC * 32,
+                  "register pool");
+    auto kern = k_xform_ws<NTB, NC, NPC, EXACT, PGB, RC, RP>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, (1 + NPC) * NC * 32, smem, st>>>(a);
+    return ree_check_launch("k_xform_ws");
+}
+
+template <int NTB, int NC>
+static int launch_xf_ws_variants(const XfArgs& a, cudaStream_t st) {
+    const int sms = ree_grid_ctas() / 2;  // persistent: one CTA per SM
+    const int64_t want = ((a.n + 7) / 8 + NC - 1) / NC;
+    const int grid = (int)(want < sms ? want : sms);
+    const int v = xf_variant();
+    if ((a.d + 7) / 8 == NTB) {
+        if (v == 1) return launch_xf_ws<NTB, NC, 1, true, 4, 0, 0>(a, grid, st);
+        if (v == 2) return launch_xf_ws<NTB, NC, 2, true, 4, 120, 56>(a, grid, st);
+        if (v == 3) return launch_xf_ws<NTB, NC, 2, true, 1, 128, 48>(a, grid, st);
+        if (v == 4) return launch_xf_ws<NTB, NC, 3, true, 1, 120, 40>(a, grid, st);
+        if (v == 5) return launch_xf_ws<NTB, NC, 1, true, 2, 168, 88>(a, grid, st);
+        if (v == 6) return launch_xf_ws<NTB, NC, 1, true, 4, 152, 104>(a, grid, st);
+        if (v == 7) return launch_xf_ws<NTB, NC, 2, true, 2, 120, 56>(a, grid, st);
+        return launch_xf_ws<NTB, NC, 1, true, 2, 0, 0>(a, grid, st);
+    }
+    return launch_xf_ws<NTB, NC, 1, false, 2, 0, 0>(a, grid, st);
+}
+
 template <int MODE, int NTB, int NW, bool TRI>
 static int launch_xf_exact(const XfArgs& a, int grid, cudaStream_t st) {
     if ((a.d + 7) / 8 == NTB) return launch_xf<MODE, NTB, NW, true, TRI>(a, grid, st);
@@ -598,6 +807,12 @@ template <int MODE, bool TRI>
 static int launch_xf_bucket(const SplitCfg& c, const XfArgs& a, cudaStream_t st) {
     const int sms = ree_grid_ctas() / 2;  // persistent: one CTA per SM
     const int64_t nwt = (a.n + 7) / 8;
+    if constexpr (MODE == 1 && TRI) {
+        if (!a.z && xf_ws()) {  // Philox noise: producer / consumer warps
+            if (c.ntb == 7) return launch_xf_ws_variants<7, 8>(a, st);
+            if (c.ntb == 13) return launch_xf_ws_variants<13, 8>(a, st);
+        }
+    }
     if (c.ntb == 7) {
         const int64_t want = (nwt + 15) / 16;
         return launch_xf_exact<MODE, 7, 16, TRI>(a, (int)(want < sms ? want : sms), st);

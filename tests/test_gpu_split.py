@@ -29,7 +29,7 @@ def _setup(eng, n, d, seed):
 
 
 @pytest.mark.parametrize("n,d", [(1, 100), (7, 56), (96, 100), (1001, 100), (4099, 64), (3000, 103), (1000, 150),
-                                 (777, 120), (65, 151)])
+                                 (777, 120), (65, 151), (70001, 100), (50003, 59)])
 def test_split_step_matches_numpy_and_fused(eng, n, d):
     assert eng.path(d) == 2
     rng, X, F, src, lsf, m_noise = _setup(eng, n, d, n + d)
