@@ -93,6 +93,11 @@ int ree_num_ctas(void);
 /* bytes of scratch a call with dimension d may need (partials of the d x d sums).  The workspace
  * must be zero-filled once after allocation (it holds a self-resetting ticket counter).          */
 int64_t ree_workspace_bytes(int d);
+/* Synchronising readback of n <= 64 doubles of device memory, stream-ordered behind the work already queued on
+ * `stream`: a one-warp kernel copies them into mapped pinned host memory, the caller spins on a sequence number
+ * (a few microseconds instead of a cudaMemcpy round trip).  Replaces the implicit host arrays of the reference's
+ * scalar objectives (solver.py:538-556, 591-601: every objective evaluation returns a Python float).              */
+int ree_fetch_small(const double* dev_src, int n, double* host_out, void* stream);
 
 /* ---- layout (host (N,d) C-order <-> device SoA); replaces nothing, it is the boundary -- */
 int ree_aos_to_soa(const double* aos, double* soa, int64_t n, int d, int64_t ld, void* stream);

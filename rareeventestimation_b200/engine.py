@@ -140,6 +140,7 @@ class Engine:
         self._pool = {}
         self._scratch = {}
         self._staging = None
+        self._fetch_buf = np.empty(64, dtype=np.float64)
         with torch.cuda.device(self.device):
             self.num_ctas = self.lib.ree_num_ctas()
 
@@ -216,6 +217,13 @@ class Engine:
         if t is None or t.numel() < numel:
             t = self._scratch[name] = self.empty(numel)
         return t
+
+    def fetch(self, t: torch.Tensor, n: Optional[int] = None) -> np.ndarray:
+        """Synchronising readback of a small fp64 device result (<= 64 values) through ``ree_fetch_small``."""
+        n = t.numel() if n is None else n
+        buf = self._fetch_buf
+        check(self.lib.ree_fetch_small(t.data_ptr(), n, buf.ctypes.data, self.stream), "ree_fetch_small")
+        return buf[:n].copy()
 
     def upload(self, host: np.ndarray, first: int = 0) -> Ensemble:
         """Host (n,d) C-order array -> SoA ensemble (chunked H2D + device transpose)."""

@@ -460,7 +460,7 @@ class CBREE(Solver):
                 out = eng.empty(4)
 
                 def obj_fun(sigma):
-                    t4 = eng.reduce_cvar(dev, sigma, cache.sigma, kind, out=out).cpu().numpy()
+                    t4 = eng.fetch(eng.reduce_cvar(dev, sigma, cache.sigma, kind, out=out))
                     return (cvar_from(t4) - self.cvar_tgt) ** 2
 
                 opt_sol = minimize_scalar(
@@ -479,9 +479,9 @@ class CBREE(Solver):
         repeated evaluations for different beta cost one exp per particle."""
         dev = cache._dev
         if ell is not None:
-            t4 = self._eng.reduce_scaled(ell, dev.n, dev.d, beta, out=out).cpu().numpy()
+            t4 = self._eng.fetch(self._eng.reduce_scaled(ell, dev.n, dev.d, beta, out=out))
         else:
-            t4 = self._eng.reduce_ess(dev, cache.sigma, beta, self._tgt_kind(), out=out).cpu().numpy()
+            t4 = self._eng.fetch(self._eng.reduce_ess(dev, cache.sigma, beta, self._tgt_kind(), out=out))
         if t4[3] <= 0:
             raise ValueError("attempt to get argmax of an empty sequence")
         return ess_from(t4)
