@@ -98,6 +98,10 @@ int64_t ree_workspace_bytes(int d);
  * (a few microseconds instead of a cudaMemcpy round trip).  Replaces the implicit host arrays of the reference's
  * scalar objectives (solver.py:538-556, 591-601: every objective evaluation returns a Python float).              */
 int ree_fetch_small(const double* dev_src, int n, double* host_out, void* stream);
+/* Synchronising copy of an n-vector of device memory into pageable host memory (double-buffered through pinned
+ * staging): what reading CBREECache.lsf_evals / e_fun_evals or a row of Solution.lsf_eval_hist costs
+ * (solver.py:63-116, solution.py:9-50 hold these as host arrays).                                                  */
+int ree_download_vector(const double* dev_src, double* host_dst, int64_t n, void* stream);
 
 /* ---- layout (host (N,d) C-order <-> device SoA); replaces nothing, it is the boundary -- */
 int ree_aos_to_soa(const double* aos, double* soa, int64_t n, int d, int64_t ld, void* stream);

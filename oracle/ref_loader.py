@@ -81,3 +81,23 @@ def load_reference_diffusion():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         return importlib.import_module(_PKG + ".problem.diffusion")
+
+
+def load_reference_evaluation():
+    """The reference's ``evaluation/convergence_analysis.py`` (do_multiple_solves, load_data, add_evaluations,
+    aggregate_df).  Its package pulls plotly through ``evaluation/constants.py``; a stub with the three names that
+    module touches at import time is enough."""
+    load_reference()
+
+    class _Templates(dict):
+        def __missing__(self, key):
+            self[key] = _Templates()
+            return self[key]
+
+    if "plotly" not in sys.modules:
+        colors = types.SimpleNamespace(qualitative=types.SimpleNamespace(D3=["#1f77b4"] * 10, Plotly=["#636efa"] * 10))
+        _stub("plotly", io=None, express=None)
+        pio = _stub("plotly.io", templates=_Templates())
+        px = _stub("plotly.express", colors=colors)
+        sys.modules["plotly"].io, sys.modules["plotly"].express = pio, px
+    return importlib.import_module(_PKG + ".evaluation.convergence_analysis")

@@ -11,6 +11,9 @@ from .lsf import AffineLSF, ConvexLSF, DeviceLSF, DiffusionLSF, FujitaRackwitzLS
 from .solution import Solution  # noqa: F401
 from .solver import CBREE, CBREECache, MixtureModel, Solver, flatten_cache_list, get_slope  # noqa: F401
 from .baselines import CMC, SIS  # noqa: F401
+from .evaluation import (  # noqa: F401
+    add_evaluations, aggregate_df, do_multiple_solves, load_data, study_cbree_observation_window,
+)
 from .toy_problems import (  # noqa: F401
     lsf_convex, lsf_lin, lsf_nonlin_osc, make_fujita_rackwitz, make_linear_problem, prob_convex, prob_nonlin_osc,
     problems_highdim, problems_lowdim,

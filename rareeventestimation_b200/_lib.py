@@ -52,6 +52,7 @@ PROTOTYPES = {
     "ree_fused_path": (_INT, [_INT]),
     "ree_workspace_bytes": (_I64, [_INT]),
     "ree_fetch_small": (_INT, [_P, _INT, _P, _P]),
+    "ree_download_vector": (_INT, [_P, _P, _I64, _P]),
     "ree_aos_to_soa": (_INT, [_P, _P, _I64, _INT, _I64, _P]),
     "ree_soa_to_aos": (_INT, [_P, _P, _I64, _INT, _I64, _P]),
     "ree_upload_ensemble": (_INT, [_P, _P, _I64, _INT, _I64, _P, _I64, _P]),

@@ -247,6 +247,12 @@ class Engine:
                                              st.numel(), self.stream), "ree_download_ensemble")
         return out
 
+    def download_vector(self, t: torch.Tensor, n: int) -> np.ndarray:
+        """First n values of a device N-vector as a new host array (``ree_download_vector``)."""
+        out = np.empty(n, dtype=np.float64)
+        check(self.lib.ree_download_vector(t.data_ptr(), out.ctypes.data, n, self.stream), "ree_download_vector")
+        return out
+
     def upload_vector(self, v: np.ndarray, ld: int) -> torch.Tensor:
         t = self.empty(ld)
         t[: v.shape[0]].copy_(torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)))

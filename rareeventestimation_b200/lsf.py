@@ -35,7 +35,7 @@ class DeviceLSF:
         eng = Engine.get()
         ens = eng.upload(flat)
         g = eng.lsf_eval(self.descriptor(eng, d), ens)
-        out = g[: ens.n].cpu().numpy()
+        out = eng.download_vector(g, ens.n)
         return out.reshape(lead) if lead else float(out[0])
 
 

@@ -27,7 +27,7 @@ class StandardNormalEnergy:
         flat = np.ascontiguousarray(x.reshape(-1, d))
         eng = Engine.get()
         ens = eng.upload(flat)
-        out = eng.energy(ens)[: ens.n].cpu().numpy()
+        out = eng.download_vector(eng.energy(ens), ens.n)
         return out.reshape(lead) if lead else float(out[0])
 
 

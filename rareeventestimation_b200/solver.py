@@ -118,7 +118,7 @@ class CBREECache:
                 self._host[name] = eng.download(dev)
             else:
                 t = dev.g if name == "lsf_evals" else dev.e
-                self._host[name] = t[: dev.n].cpu().numpy()
+                self._host[name] = eng.download_vector(t, dev.n)
         return self._host[name]
 
     def _set(self, name, value):
@@ -197,6 +197,20 @@ class Solver:
 
     def solve(self, prob: Problem):
         raise NotImplementedError
+
+    # state a finished solve leaves behind that belongs to the engine / the problem, not to the solver's options:
+    # shared by reference when the solver is copied (ctypes handles cannot be deep-copied; the next solve rebinds them)
+    _SHARED_ON_COPY = ("_eng", "_prob", "_dev_lsf_obj", "_table", "lsf", "e_fun")
+
+    def __deepcopy__(self, memo):
+        """``set_options(..., in_situ=False)`` copies solvers *after* they have solved (the reference's
+        do_multiple_solves does, convergence_analysis.py:70): every option, ``seed`` and ``rng`` are deep-copied,
+        the engine handles of the last solve are not."""
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in vars(self).items():
+            setattr(new, k, v if k in self._SHARED_ON_COPY else deepcopy(v, memo))
+        return new
 
     def set_options(self, options: dict, in_situ=True):
         """Reset members already in ``vars(self)``; ``in_situ=False`` returns a configured deep copy."""

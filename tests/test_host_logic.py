@@ -234,3 +234,23 @@ def test_two_rank_combination_gloo():
         np.testing.assert_allclose(ret[r][3], local_expsums(a), rtol=1e-13)
     np.testing.assert_array_equal(ret[0][2], ret[1][2])
     np.testing.assert_array_equal(ret[0][3], ret[1][3])
+
+
+def test_solver_is_deep_copyable_after_a_solve():
+    """do_multiple_solves copies the solver of the previous run (convergence_analysis.py:70); the engine handles a
+    solve leaves on the solver (ctypes / CUDA objects) must not break that, and options must not be shared."""
+    import ctypes
+    from copy import deepcopy
+
+    import rareeventestimation_b200 as ree
+
+    s = ree.CBREE(seed=3, quiet=True)
+    s._eng = ctypes.pointer(ctypes.c_int(1))  # stands in for the engine: ctypes pointers refuse to be pickled / copied
+    s._prob = object()
+    s.lsf = lambda x: x
+    c = s.set_options({"seed": 7, "rng": np.random.default_rng(7), "observation_window": 9}, in_situ=False)
+    assert c is not s and c.seed == 7 and c.observation_window == 9 and s.seed == 3 and s.observation_window != 9
+    assert c._eng is s._eng and c._prob is s._prob
+    assert c.rng is not s.rng
+    d = deepcopy(c)
+    assert d.rng is not c.rng and d.rng.integers(0, 10**9) == deepcopy(c).rng.integers(0, 10**9)
