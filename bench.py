@@ -95,6 +95,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm uses all the host threads it can get
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.pop(k, None)
+    try:
+        import numpy  # noqa: F401  (loads the BLAS the limits below apply to)
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
     val, dt = cpu_cbree(args.ref_n, args.d, args.steps, args.warmup)
     cores = blas_threads()
     sample = f"CBREE affine d={args.d}, N={args.ref_n} particles, {args.steps} iterations, NumPy/SciPy oracle port"

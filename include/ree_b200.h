@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define REE_ABI_VERSION 2
+#define REE_ABI_VERSION 3
 
 /* argument errors */
 #define REE_E_BADARG (-1)
@@ -206,6 +206,29 @@ int ree_cbree_maha(const double* x, int64_t n, int d, int64_t ld, const double* 
                    const double* mean, const double* Linv, const double* logdet, double sigma, double beta,
                    int tgt_kind, const double* wmax, double* logq, double* w, double* workspace, double* sums,
                    double* is4, void* stream);
+
+/* ---- resampling branch: one-component von Mises-Fisher-Nakagami model ---------------------------------------- */
+/* (CBREE(resample=True, mixture_model="vMFNM"), solver.py:654-663, 828-836; VMFNMixture mixturemodel.py:153-239;
+ *  EMvMFNM / vMFNM_sample / logvMFpdf / lognakagamipdf, era/EMvMFNM.py)
+ * Fit: with one component the EM reduces to one M-step (EMvMFNM.py:169-199), i.e. the weighted sums
+ *   sums = [S = sum w x/|x| (d) | sum w |x|^2 | sum w |x|^4 | sum w]        (w == NULL: all ones)
+ * rinv (n doubles, scratch) receives w_i/|x_i|.  The caller turns the sums into mu, kappa, m, omega.            */
+int ree_vmfn_fit_sums(const double* x, int64_t n, int d, int64_t ld, const double* w, double* rinv, double* workspace,
+                      double* sums, void* stream);
+/* Sample n points (EMvMFNM.py:274-285, 324-378): |x| = sqrt(Gamma(m, omega/m)), cosine to the mean direction by
+ * Wood's rejection sampler, uniform direction in the complement, Householder reflection I - b v v^T (house(mu),
+ * EMvMFNM.py:401-429; v is a DEVICE vector).  r_in / w_in / v_in all NULL: Philox variates (counter = global particle
+ * index, `draw`); otherwise injected variates (parity mode): radii r_in[n], accepted cosines w_in[n] and the raw
+ * normals of the complement direction v_in[(d-1)][ld] in the ensemble's SoA layout.                              */
+int ree_vmfn_sample(double* x, int64_t n, int d, int64_t ld, const double* householder_v, double householder_b,
+                    double kappa, double m, double omega, uint64_t seed, uint64_t draw, int64_t first_particle,
+                    const double* r_in, const double* w_in, const double* v_in, void* stream);
+/* logq_i = kappa mu.x_i/|x_i| + c0 - m |x_i|^2/omega + (2m - d) log|x_i|  with c0 = the vMF and Nakagami constants
+ * (mixturemodel.py:196-215).  is4 != NULL additionally returns the IS statistics of r = -e - logq with the indicator
+ * g <= 0, exactly as ree_cbree_maha does (solver.py:683-686, 843-846).  mu is a DEVICE vector.                   */
+int ree_vmfn_logpdf(const double* x, int64_t n, int d, int64_t ld, const double* mu, double kappa, double m, double omega,
+                    double c0, const double* g, const double* e, double* logq, double* workspace, double* is4,
+                    void* stream);
 
 /* ---- secondary path: SIS with adaptive conditional sampling (sis/SIS_aCS.py:64-306) ------------------------ */
 /* mode 0: v_i = Phi(-g_i/sigma_new) / Phi(-g_i/sigma_old)  (sigma_old <= 0: denominator 1)   SIS_aCS.py:151-183

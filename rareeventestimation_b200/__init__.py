@@ -9,7 +9,8 @@ from ._lib import ReeError  # noqa: F401
 from .problem import DeviceSample, NormalProblem, Problem, Vectorizer  # noqa: F401
 from .lsf import AffineLSF, ConvexLSF, DeviceLSF, DiffusionLSF, FujitaRackwitzLSF, OscillatorLSF  # noqa: F401
 from .solution import Solution  # noqa: F401
-from .solver import CBREE, CBREECache, MixtureModel, Solver, flatten_cache_list, get_slope  # noqa: F401
+from .mixture import MixtureModel, VMFNMixture  # noqa: F401
+from .solver import CBREE, CBREECache, Solver, flatten_cache_list, get_slope  # noqa: F401
 from .baselines import CMC, SIS  # noqa: F401
 from .evaluation import (  # noqa: F401
     add_evaluations, aggregate_df, do_multiple_solves, load_data, study_cbree_observation_window,

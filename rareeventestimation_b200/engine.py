@@ -225,6 +225,10 @@ class Engine:
         check(self.lib.ree_fetch_small(t.data_ptr(), n, buf.ctypes.data, self.stream), "ree_fetch_small")
         return buf[:n].copy()
 
+    def fetch_array(self, t: torch.Tensor) -> np.ndarray:
+        """Host copy of a small device vector of any length (ree_fetch_small up to 64 values, D2H copy beyond)."""
+        return self.fetch(t) if t.numel() <= 64 else t.cpu().numpy()
+
     def upload(self, host: np.ndarray, first: int = 0) -> Ensemble:
         """Host (n,d) C-order array -> SoA ensemble (chunked H2D + device transpose)."""
         host = np.ascontiguousarray(host, dtype=np.float64)
@@ -363,6 +367,40 @@ class Engine:
         if reduce and sums is not None:
             self.comm.allreduce_sum_(sums)
         return sums
+
+    # -- von Mises-Fisher-Nakagami model (resampling branch) ------------------------------------ #
+    def vmfn_fit_sums(self, ens: Ensemble, w: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[sum w x/|x| (d) | sum w |x|^2 | sum w |x|^4 | sum w] over all ranks (EMvMFNM.py:169-199)."""
+        sums = self.empty(ens.d + 3)
+        rinv = self.scratch("vmfn_rinv", ens.ld)
+        ws = self.workspace(ens.d)
+        check(self.lib.ree_vmfn_fit_sums(ens.X.data_ptr(), ens.n, ens.d, ens.ld, w.data_ptr() if w is not None else None,
+                                         rinv.data_ptr(), ws.data_ptr(), sums.data_ptr(), self.stream),
+              "ree_vmfn_fit_sums")
+        return self.comm.allreduce_sum_(sums)
+
+    def vmfn_sample(self, dst: Ensemble, hv: torch.Tensor, hb: float, kappa: float, m: float, omega: float, seed: int,
+                    draw: int, r=None, w=None, v: Optional[Ensemble] = None):
+        if v is not None and v.ld != dst.ld:
+            raise ValueError("injected direction normals must share the ensemble's leading dimension")
+        check(self.lib.ree_vmfn_sample(dst.X.data_ptr(), dst.n, dst.d, dst.ld, hv.data_ptr(), float(hb), float(kappa),
+                                       float(m), float(omega), seed & (2**64 - 1), draw, dst.first,
+                                       r.data_ptr() if r is not None else None,
+                                       w.data_ptr() if w is not None else None,
+                                       v.X.data_ptr() if v is not None else None, self.stream), "ree_vmfn_sample")
+        return dst
+
+    def vmfn_logpdf(self, ens: Ensemble, mu: torch.Tensor, kappa: float, m: float, omega: float, c0: float,
+                    logq: Optional[torch.Tensor] = None, is4: Optional[torch.Tensor] = None):
+        ws = self.workspace(ens.d)
+        check(self.lib.ree_vmfn_logpdf(ens.X.data_ptr(), ens.n, ens.d, ens.ld, mu.data_ptr(), float(kappa), float(m),
+                                       float(omega), float(c0),
+                                       ens.g.data_ptr() if is4 is not None else None,
+                                       ens.e.data_ptr() if is4 is not None else None,
+                                       logq.data_ptr() if logq is not None else None, ws.data_ptr(),
+                                       is4.data_ptr() if is4 is not None else None, self.stream), "ree_vmfn_logpdf")
+        if is4 is not None:
+            self.comm.combine_expsums_(is4)
 
     def moments_chol(self, sums, shift, d, ddof, weighted, mean, cov, L=None, Linv=None, stats=None):
         check(self.lib.ree_moments_chol(sums.data_ptr(), shift.data_ptr() if shift is not None else None, d, ddof,

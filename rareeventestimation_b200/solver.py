@@ -20,24 +20,18 @@ from scipy.optimize import minimize_scalar, root
 from . import _lib
 from .engine import Comm, DeviceLsf, Engine, Ensemble, cvar_from, ess_from
 from .lsf import DeviceLSF
+from .mixture import MixtureModel, VMFNMixture, vmfn_variates_numpy
 from .problem import DeviceSample, NormalProblem, Problem, ShardedHostSample
 from .solution import Solution
 
 _log = logging.getLogger(__name__)
 _STREAM_STEP = 0x01 << 24  # Philox draw index base of the Euler-Maruyama noise
+_STREAM_RESAMPLE = 0x02 << 24  # ... of the vMFNM resampling draws
 
 
 def warn(msg):
     """The reference reports step failures through ``distutils.log.warn`` (solver.py:5, 430)."""
     warnings.warn(str(msg), RuntimeWarning, stacklevel=2)
-
-
-class MixtureModel:
-    """Placeholder stored in every cache (mixturemodel.py:29-40); the GM path never fits it."""
-
-    def __init__(self, num_comps: int) -> None:
-        self.num_comps = num_comps
-        self.fitted = False
 
 
 class LazyHistory:
@@ -309,9 +303,8 @@ class CBREE(Solver):
         return _lib.TGT_KINDS.get(self.tgt_fun, _lib.TGT_KINDS["sigmoid"])
 
     def _setup(self, prob: Problem):
-        if self.resample or self.mixture_model != "GM":
-            raise NotImplementedError("only the Gaussian (GM, resample=False) CBREE path is built "
-                                      "(vMFNM resampling: SURVEY.md 8f rank 2)")
+        if self.mixture_model not in ("GM", "vMFNM"):
+            raise NotImplementedError(f"mixture_model={self.mixture_model!r}: CBREE knows 'GM' and 'vMFNM' (solver.py:186)")
         self._eng = Engine.get()
         self._prob = prob
         lsf = prob.lsf
@@ -368,7 +361,7 @@ class CBREE(Solver):
     # post-processing of an ensemble: moments, IS density, weights  (device)
     # ------------------------------------------------------------------ #
     def _post_ensemble(self, cache: CBREECache, sums_ready=None,
-                       shift_u=None, shift_w=None):
+                       shift_u=None, shift_w=None, model=None):
         """Everything the reference derives from (X, g, e, sigma, beta) of one cache:
         unweighted mean/cov + factorisation (solver.py:670-674), ESS shift (my_softmax), Mahalanobis sweep with
         IS statistics (683-686, 843-846) and the weighted mean/cov (629-636).  One D2H copy at the end."""
@@ -391,7 +384,10 @@ class CBREE(Solver):
             sums_uw = eng.empty(2 * slen)
             sums_u, sums_w = eng.cbree_moments(dev, a_vec, ess4[0:1], shift_u, sums_uw)
             eng.moments_chol(sums_u, shift_u, d, 1, False, mean, cov, L, Linv, stats)
-            eng.cbree_maha(dev, mean, Linv, stats[0:1], cache.sigma, cache.beta, kind, None, None, is4)
+            if model is None:
+                eng.cbree_maha(dev, mean, Linv, stats[0:1], cache.sigma, cache.beta, kind, None, None, is4)
+            else:  # the ensemble was drawn from the fitted vMFN model: its density replaces the Gaussian fit
+                model.logpdf_device(eng, dev, is4=is4)
             eng.moments_chol(sums_w, shift_u, d, 0, True, m_w, C_w)
         else:
             if sums_ready is None:
@@ -404,6 +400,8 @@ class CBREE(Solver):
             sums_w = eng.empty(slen)
             eng.cbree_maha(dev, mean, Linv, stats[0:1], cache.sigma, cache.beta, kind, ess4[0:1], sums_w, is4)
             eng.moments_chol(sums_w, mean, d, 0, True, m_w, C_w)  # weighted sums are centred at the unweighted mean
+            if model is not None:  # IS statistics of the vMFN density instead of the Gaussian fit's
+                model.logpdf_device(eng, dev, is4=is4)
         tails[0:2].copy_(sums_u[d + d * d:])
         tails[2:4].copy_(sums_w[d + d * d:])
         host = res.cpu().numpy()  # the one synchronising D2H of the iteration
@@ -413,6 +411,7 @@ class CBREE(Solver):
         cache.weighted_cov = host[2 * d + d * d:o].reshape(d, d).copy()
         st, i4, e4, tl = host[o:o + 4], host[o + 4:o + 8], host[o + 8:o + 12], host[o + 12:o + 16]
         cache._stats = dict(C_w=C_w)  # view into `res`; the O(N) scratch (w, L, Linv) is released here
+        cache._vmfn_density = model is not None
         cache._chol_info = int(st[1])
         cache._min_pivot, cache._max_diag = float(st[2]), float(st[3])
         cache.num_failed = float(tl[0])
@@ -439,6 +438,8 @@ class CBREE(Solver):
     def _check_density(self, cache: CBREECache):
         """SciPy's multivariate_normal refuses (numerically) singular covariances (SURVEY.md 7.2);
         the factorisation reports the same condition through its pivots."""
+        if getattr(cache, "_vmfn_density", False):
+            return  # no Gaussian fit behind this cache's importance density
         if cache._chol_info != 0 or not (cache._min_pivot > 2.220446049250313e-10 * cache._max_diag):
             raise np.linalg.LinAlgError(
                 "When `allow_singular is False`, the input matrix must be symmetric positive definite.")
@@ -555,6 +556,8 @@ class CBREE(Solver):
         small = eng.to_device(np.concatenate([m_noise, shift_u_h, cache.weighted_mean]))
         m_noise_d, shift_u, shift_w = small[0:d], small[d:2 * d], small[2 * d:3 * d]
         desc = self._lsf_descriptor(d)
+        resample = self.resample and self.mixture_model == "vMFNM"
+        step_desc = None if resample else desc  # the transformed ensemble of the resampling branch is only fitted
         if self.noise == "numpy":
             # Generator.multivariate_normal(method="svd"): mean + Z @ (U sqrt(S))^T   (solver.py:667)
             c_noise = scale * cache.weighted_cov
@@ -563,21 +566,26 @@ class CBREE(Solver):
             zdev = eng.upload(Z[lo:hi], first=src.first)
             u, s, _ = np.linalg.svd(c_noise)
             F = eng.to_device(u * np.sqrt(s))
-            eng.cbree_step(src, dst, t, m_noise_d, F, desc, shift_u, sums, z=zdev)
+            eng.cbree_step(src, dst, t, m_noise_d, F, step_desc, shift_u, sums, z=zdev)
         else:
             F = eng.empty(d * d)
             fstats = eng.empty(4)
             eng.chol_scaled(cache._stats["C_w"] if not cache._cw_dirty else eng.to_device(cache.weighted_cov), d,
                             scale, F, fstats)
             self._step_draws += 1
-            eng.cbree_step(src, dst, t, m_noise_d, F, desc, shift_u, sums, seed=self._philox_seed,
+            eng.cbree_step(src, dst, t, m_noise_d, F, step_desc, shift_u, sums, seed=self._philox_seed,
                            draw=_STREAM_STEP + self._step_draws)
-        if desc is None or not self._device_energy:
+        model = None
+        if resample:
+            # solver.py:654-663: fit a one-component vMFN model to the moved ensemble, redraw the ensemble from it
+            model = self._vmfn_redraw(dst)
+            sums, shift_u = None, shift_w
+        elif desc is None or not self._device_energy:
             self._evaluate_external(dst, desc is None, not self._device_energy)
             if desc is None and sums is not None:
                 sums[d + d * d: d + d * d + 1].copy_(eng.count_failed(dst))
         self.lsf.counter += self._n_total
-        new = CBREECache(eng, dst, mixture_model=MixtureModel(1))
+        new = CBREECache(eng, dst, mixture_model=model if model is not None else MixtureModel(1))
         new.iteration = cache.iteration + 1
         new.converged = cache.converged
         new.sigma = cache.sigma
@@ -585,10 +593,31 @@ class CBREE(Solver):
         new.t_step = cache.t_step
         new.num_lsf_evals = self.lsf.counter
         new._cw_dirty = False
-        self._post_ensemble(new, sums_ready=sums, shift_u=shift_u, shift_w=shift_w)
+        self._post_ensemble(new, sums_ready=sums, shift_u=shift_u, shift_w=shift_w, model=model)
         self._finish_is_stats(new)
         self._compute_weights_check(new)
         return new
+
+    def _vmfn_redraw(self, dev: Ensemble) -> VMFNMixture:
+        """``model = VMFNMixture(1); model.fit(X); X = model.sample(N, rng)`` on the device ensemble ``dev`` (in place)
+        followed by the limit state and the energy of the new points (solver.py:659-663, 676-680)."""
+        eng = self._eng
+        model = VMFNMixture(1)
+        model.fit_device(eng, dev)
+        if self.noise == "numpy":  # replay the reference's draws (Generator.gamma / beta / uniform / normal)
+            variates = vmfn_variates_numpy(self.rng, self._n_total, dev.d, *model._scalars())
+            model.sample_device(eng, dev, 0, 0, variates)
+        else:
+            self._step_draws += 1
+            model.sample_device(eng, dev, self._philox_seed, _STREAM_RESAMPLE + self._step_draws)
+        desc = self._lsf_descriptor(dev.d)
+        if desc is not None:
+            eng.lsf_eval(desc, dev, out=dev.g)
+        if self._device_energy:
+            eng.energy(dev, out=dev.e)
+        if desc is None or not self._device_energy:
+            self._evaluate_external(dev, desc is None, not self._device_energy)
+        return model
 
     # ------------------------------------------------------------------ #
     # stopping
@@ -674,6 +703,18 @@ class CBREE(Solver):
         produced; they are recomputed only if a callback replaced N-sized fields."""
         if cache.sync_to_device():
             self._refresh(cache)
+        if self.mixture_model == "vMFNM" and not cache.mixture_model.fitted and cache._dev is not None:
+            # solver.py:828-836: fit the model to the cache's ensemble, replace the ensemble by a sample of the model,
+            # re-evaluate the limit state there; the estimate uses the model's density
+            cache.mixture_model = self._vmfn_redraw(cache._dev)
+            cache._host.pop("ensemble", None)
+            cache._host.pop("lsf_evals", None)
+            self.lsf.counter += self._n_total
+            cache.num_lsf_evals = self.lsf.counter
+            is4 = self._eng.empty(4)
+            cache.mixture_model.logpdf_device(self._eng, cache._dev, is4=is4)
+            cache._is4 = self._eng.fetch(is4)
+            cache._vmfn_density = True
         self._check_density(cache)
         cache.estimate = self._estimate_of(cache)
 
@@ -760,7 +801,7 @@ class CBREE(Solver):
         msg = self._msg
         if not cache_list[-1].converged and cache_list[-1].iteration > self.num_steps:
             msg = "Not Converged."
-        return self._build_solution(cache_list, msg, self.lsf.counter)
+        return self._build_solution(cache_list, msg, None)  # costs after the final importance sampling (solver.py:497)
 
     def solve(self, prob: Problem) -> Solution:
         """Estimate the rare event of `prob` (solver.py:365-503)."""
@@ -801,6 +842,7 @@ class CBREE(Solver):
         ens_hist = tmp["ensemble"]
         if not isinstance(ens_hist, LazyHistory) and ens_hist.ndim == 2:
             ens_hist = ens_hist[None, ...]
+        costs = self.lsf.counter if costs is None else costs
         return Solution(ens_hist, tmp["beta"], tmp["lsf_evals"], tmp["estimate"], costs, msg,
                         num_steps=last.iteration, other=other)
 
