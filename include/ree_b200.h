@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define REE_ABI_VERSION 3
+#define REE_ABI_VERSION 4
 
 /* argument errors */
 #define REE_E_BADARG (-1)
@@ -142,8 +142,13 @@ int ree_reduce_ess(const double* g, const double* e, int64_t n, double sigma, do
 int ree_reduce_cvar(const double* g, int64_t n, double sigma_new, double sigma_old, int tgt_kind,
                     double* workspace, double* out4, void* stream);
 /* Same four outputs for a = scale * ell_i with a precomputed log-target vector (ree_logtgt): the beta root find
- * (solver.py:591-601) evaluates ESS(beta) many times for one sigma.                                            */
-int ree_reduce_scaled(const double* ell, int64_t n, double scale, double* workspace, double* out4, void* stream);
+ * (solver.py:591-601) evaluates ESS(beta) many times for one sigma.
+ * range2 (optional, DEVICE [max ell, min ell] over the finite entries, from ree_vector_range): the shift
+ * max(scale * ell) is then known in advance and the kernel runs without a running maximum.                      */
+int ree_reduce_scaled(const double* ell, int64_t n, double scale, const double* range2, double* workspace, double* out4,
+                      void* stream);
+/* out2 = [max, min] over the finite entries of v (-inf, +inf if none).                                          */
+int ree_vector_range(const double* v, int64_t n, double* workspace, double* out2, void* stream);
 /* Merge `nparts` 4-tuples [M, S1, S2, cnt] (e.g. all_gather'ed from the ranks) into one, shifted to the global
  * max; fixed order, so every rank computes identical bits.                                                    */
 int ree_merge_expsums(const double* parts, int nparts, double* out4, void* stream);

@@ -127,6 +127,97 @@ __device__ __forceinline__ ExpSums expsums_block_reduce(ExpSums v, ExpSums* smem
     return v;
 }
 
+// ---------------------------------------------------------------------------------------
+// Shifted exponential sums at streaming speed.  The generic expsums_add costs two libdevice exp calls and a divergent
+// branch per element (127 instructions per element in k_reduce_scaled: issue-bound at 1.4 TB/s, profiles/
+// r1_small_d_kernels_ncu.txt).  Here a thread raises its running shift once per group of four elements (rare after the first
+// few groups) and evaluates exp(v - shift) for arguments <= 0 with a 64-entry table of 2^(j/64) in shared memory and a
+// degree-5 polynomial: exp(x) = 2^e * 2^(j/64) * exp(r), n = rint(x * 64/ln2) = 64 e + j, |r| <= ln2/128, relative
+// error <= 1.2 ulp (r^6/720 < 4e-17), 10 fp64 instructions.  Arguments below -708 give 0 (the reference's exp
+// underflows to subnormals there: relative weight < 1e-307).
+// ---------------------------------------------------------------------------------------
+#include "exp_table.cuh"
+
+__device__ __forceinline__ uint32_t load_exp_table(double* T) {  // returns the 32-bit shared address of the table
+    for (int j = threadIdx.x; j < 64; j += blockDim.x) T[j] = EXP2_64[j];
+    __syncthreads();
+    return (uint32_t)__cvta_generic_to_shared(T);
+}
+
+// branch-free; x <= 0, -inf or NaN (NaN / -inf / x < -708 -> 0)
+__device__ __forceinline__ double exp_nonpos(double x, uint32_t T) {
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: the low word of x*c + MAGIC is rint(x*c)
+    const double t = fma(x, 92.33248261689366, MAGIC);
+    const int n = __double2loint(t);
+    const double nd = t - MAGIC;
+    double r = fma(nd, -0x1.62e42ff000000p-7, x);  // ln2/64 = hi + lo, nd*hi exact
+    r = fma(nd, 0x1.718432a1b0e26p-41, r);
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    double tj;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(T + (uint32_t)((n & 63) << 3)));
+    const double v = tj * p;
+    const double scaled = __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+    return x >= -708.0 ? scaled : 0.0;
+}
+
+struct ExpAcc {  // per-thread running (shift, sum, sum of squares, count)
+    double m, s1, s2;
+    unsigned int cnt;
+};
+__device__ __forceinline__ ExpAcc expacc_empty() { return ExpAcc{-CUDART_INF, 0.0, 0.0, 0u}; }
+
+__device__ __forceinline__ void expacc_raise(ExpAcc& a, double m_new, uint32_t T) {
+    if (m_new > a.m) {  // exp(-inf) = 0 on the first group
+        const double f = exp_nonpos(a.m - m_new, T);
+        a.s1 *= f;
+        a.s2 *= f * f;
+        a.m = m_new;
+    }
+}
+
+__device__ __forceinline__ void expacc_add4(ExpAcc& a, const double (&v)[4], uint32_t T) {
+    bool ok[4];
+    double m4 = -CUDART_INF;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ok[k] = isfinite(v[k]);
+        m4 = (ok[k] && v[k] > m4) ? v[k] : m4;  // compare + select (fmax carries NaN handling: ~10 instructions)
+    }
+    expacc_raise(a, m4, T);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double w = exp_nonpos(ok[k] ? v[k] - a.m : -CUDART_INF, T);  // select the argument: no branch
+        a.s1 += w;
+        a.s2 = fma(w, w, a.s2);
+        a.cnt += ok[k] ? 1u : 0u;
+    }
+}
+
+__device__ __forceinline__ void expacc_add1(ExpAcc& a, double v, uint32_t T) {
+    if (!isfinite(v)) return;
+    expacc_raise(a, v, T);
+    const double w = exp_nonpos(v - a.m, T);
+    a.s1 += w;
+    a.s2 = fma(w, w, a.s2);
+    a.cnt += 1u;
+}
+
+// one value whose exponential is multiplied by `mult` (an indicator): IS statistics of sweep 2
+__device__ __forceinline__ void expacc_add1_mult(ExpAcc& a, double v, double mult, uint32_t T) {
+    if (!isfinite(v)) return;
+    expacc_raise(a, v, T);
+    const double w = exp_nonpos(v - a.m, T) * mult;
+    a.s1 += w;
+    a.s2 = fma(w, w, a.s2);
+    a.cnt += 1u;
+}
+
+__device__ __forceinline__ ExpSums expacc_finish(const ExpAcc& a) { return ExpSums{a.m, a.s1, a.s2, (double)a.cnt}; }
+
 // plain fp64 sums -------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

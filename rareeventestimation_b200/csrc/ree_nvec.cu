@@ -52,87 +52,6 @@ __device__ __forceinline__ Quad ldg_quad(const double* p) {
 }
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// ---------------------------------------------------------------------------------------
-// Shifted exponential sums at streaming speed.  The generic expsums_add costs two libdevice exp calls and a divergent
-// branch per element (127 instructions per element in k_reduce_scaled: issue-bound at 1.4 TB/s, profiles/
-// r1_nvec_small_ncu.txt).  Here a thread raises its running shift once per group of four elements (rare after the first
-// few groups) and evaluates exp(v - shift) for arguments <= 0 with a 64-entry table of 2^(j/64) in shared memory and a
-// degree-5 polynomial: exp(x) = 2^e * 2^(j/64) * exp(r), n = rint(x * 64/ln2) = 64 e + j, |r| <= ln2/128, relative
-// error <= 1.2 ulp (r^6/720 < 4e-17), 10 fp64 instructions.  Arguments below -708 give 0 (the reference's exp
-// underflows to subnormals there: relative weight < 1e-307).
-// ---------------------------------------------------------------------------------------
-#include "exp_table.cuh"
-
-__device__ __forceinline__ uint32_t load_exp_table(double* T) {  // returns the 32-bit shared address of the table
-    for (int j = threadIdx.x; j < 64; j += blockDim.x) T[j] = EXP2_64[j];
-    __syncthreads();
-    return (uint32_t)__cvta_generic_to_shared(T);
-}
-
-// branch-free; x <= 0, -inf or NaN (NaN / -inf / x < -708 -> 0)
-__device__ __forceinline__ double exp_nonpos(double x, uint32_t T) {
-    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: the low word of x*c + MAGIC is rint(x*c)
-    const double t = fma(x, 92.33248261689366, MAGIC);
-    const int n = __double2loint(t);
-    const double nd = t - MAGIC;
-    double r = fma(nd, -0x1.62e42ff000000p-7, x);  // ln2/64 = hi + lo, nd*hi exact
-    r = fma(nd, 0x1.718432a1b0e26p-41, r);
-    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    double tj;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(T + (uint32_t)((n & 63) << 3)));
-    const double v = tj * p;
-    const double scaled = __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
-    return x >= -708.0 ? scaled : 0.0;
-}
-
-struct ExpAcc {  // per-thread running (shift, sum, sum of squares, count)
-    double m, s1, s2;
-    unsigned int cnt;
-};
-__device__ __forceinline__ ExpAcc expacc_empty() { return ExpAcc{-CUDART_INF, 0.0, 0.0, 0u}; }
-
-__device__ __forceinline__ void expacc_raise(ExpAcc& a, double m_new, uint32_t T) {
-    if (m_new > a.m) {  // exp(-inf) = 0 on the first group
-        const double f = exp_nonpos(a.m - m_new, T);
-        a.s1 *= f;
-        a.s2 *= f * f;
-        a.m = m_new;
-    }
-}
-
-__device__ __forceinline__ void expacc_add4(ExpAcc& a, const double (&v)[4], uint32_t T) {
-    bool ok[4];
-    double m4 = -CUDART_INF;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        ok[k] = isfinite(v[k]);
-        m4 = (ok[k] && v[k] > m4) ? v[k] : m4;  // compare + select (fmax carries NaN handling: ~10 instructions)
-    }
-    expacc_raise(a, m4, T);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const double w = exp_nonpos(ok[k] ? v[k] - a.m : -CUDART_INF, T);  // select the argument: no branch
-        a.s1 += w;
-        a.s2 = fma(w, w, a.s2);
-        a.cnt += ok[k] ? 1u : 0u;
-    }
-}
-
-__device__ __forceinline__ void expacc_add1(ExpAcc& a, double v, uint32_t T) {
-    if (!isfinite(v)) return;
-    expacc_raise(a, v, T);
-    const double w = exp_nonpos(v - a.m, T);
-    a.s1 += w;
-    a.s2 = fma(w, w, a.s2);
-    a.cnt += 1u;
-}
-
-__device__ __forceinline__ ExpSums expacc_finish(const ExpAcc& a) { return ExpSums{a.m, a.s1, a.s2, (double)a.cnt}; }
-
 // quad streams: `quad(i0, q...)` sees four consecutive elements starting at i0 (a multiple of 4), `one(i, ...)` the tail
 template <class QuadFn, class OneFn>
 __device__ __forceinline__ void stream1q(const double* __restrict__ a, int64_t n, QuadFn quad, OneFn one) {
@@ -271,6 +190,101 @@ __global__ void __launch_bounds__(REE_THREADS) k_reduce_scaled(const double* __r
     expsums_grid_finalize(blk, ws, out4, sh, &is_last);
 }
 
+// Same sums with the shift known in advance: a = scale * ell is monotone in ell, so max a = scale * (max ell or min ell)
+// exactly (rounding is monotone).  No running shift, no divergent block: ~28 instructions per element.
+__global__ void __launch_bounds__(REE_THREADS) k_reduce_scaled_known(const double* __restrict__ ell, int64_t n,
+                                                                     double scale, const double* __restrict__ range2,
+                                                                     double* ws, double* out4) {
+    __shared__ ExpSums sh[32];
+    __shared__ bool is_last;
+    __shared__ double Tsh[64];
+    const uint32_t T = load_exp_table(Tsh);
+    const double M = __dmul_rn(scale >= 0.0 ? range2[0] : range2[1], scale);
+    double s1 = 0.0, s2 = 0.0;
+    unsigned int cnt = 0;
+    auto one = [&](double li) {
+        const double a = __dmul_rn(li, scale);
+        const bool ok = isfinite(a);
+        const double w = exp_nonpos(ok ? a - M : -CUDART_INF, T);
+        s1 += w;
+        s2 = fma(w, w, s2);
+        cnt += ok ? 1u : 0u;
+    };
+    stream1q(ell, n,
+             [&](int64_t, const Quad& lq) {
+#pragma unroll
+                 for (int k = 0; k < 4; ++k) one(lq.v[k]);
+             },
+             [&](int64_t, double li) { one(li); });
+    ExpSums acc{cnt ? M : -CUDART_INF, s1, s2, (double)cnt};
+    ExpSums blk = expsums_block_reduce(acc, sh);
+    expsums_grid_finalize(blk, ws, out4, sh, &is_last);
+}
+
+// out2 = [max, min] over the finite entries of v (-inf / +inf if there are none); two-stage, order-independent
+__global__ void __launch_bounds__(REE_THREADS) k_vector_range(const double* __restrict__ v, int64_t n, double* ws,
+                                                              double* out2) {
+    __shared__ double shx[32], shn[32];
+    __shared__ bool is_last;
+    double mx = -CUDART_INF, mn = CUDART_INF;
+    stream1(v, n, [&](int64_t, double x) {
+        if (isfinite(x)) {
+            mx = x > mx ? x : mx;
+            mn = x < mn ? x : mn;
+        }
+    });
+    auto block_minmax = [&]() {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double a = __shfl_xor_sync(0xffffffffu, mx, o), b = __shfl_xor_sync(0xffffffffu, mn, o);
+            mx = a > mx ? a : mx;
+            mn = b < mn ? b : mn;
+        }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if (lane == 0) {
+            shx[warp] = mx;
+            shn[warp] = mn;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            mx = lane < nw ? shx[lane] : -CUDART_INF;
+            mn = lane < nw ? shn[lane] : CUDART_INF;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double a = __shfl_xor_sync(0xffffffffu, mx, o), b = __shfl_xor_sync(0xffffffffu, mn, o);
+                mx = a > mx ? a : mx;
+                mn = b < mn ? b : mn;
+            }
+        }
+        __syncthreads();
+    };
+    block_minmax();
+    double* part = ws + REE_WS_HEADER;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
+    if (threadIdx.x == 0) {
+        part[2 * blockIdx.x] = mx;
+        part[2 * blockIdx.x + 1] = mn;
+        __threadfence();
+        unsigned int t = atomicInc(ticket, gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    mx = -CUDART_INF;
+    mn = CUDART_INF;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        const double a = ((const volatile double*)part)[2 * b], c = ((const volatile double*)part)[2 * b + 1];
+        mx = a > mx ? a : mx;
+        mn = c < mn ? c : mn;
+    }
+    block_minmax();
+    if (threadIdx.x == 0) {
+        out2[0] = mx;
+        out2[1] = mn;
+    }
+}
+
 // algebraic target, sigma_new >= sigma_old: exp(a_i) = I(sigma_new; g_i) / I(sigma_old; g_i) with the smoothed
 // indicator I = (1 - sigma g / sqrt(1 + sigma^2 g^2)) / 2 -- the same rounded 1 - q the reference feeds to log1p, so
 // the ratio equals exp(l_new - l_old) to an ulp, without log / exp.  Entries whose l_new or l_old is -inf (1 - q
@@ -391,9 +405,18 @@ extern "C" int ree_count_failed(const double* g, int64_t n, double* workspace, d
     return ree_check_launch("ree_count_failed");
 }
 
-extern "C" int ree_reduce_scaled(const double* ell, int64_t n, double scale, double* workspace, double* out4,
-                                 void* stream) {
+extern "C" int ree_reduce_scaled(const double* ell, int64_t n, double scale, const double* range2, double* workspace,
+                                 double* out4, void* stream) {
     if (!ell || !workspace || !out4 || n < 0) return ree_set_error(REE_E_BADARG, "ree_reduce_scaled: bad argument");
-    k_reduce_scaled<<<nvec_grid(n), REE_THREADS, 0, ree_stream(stream)>>>(ell, n, scale, workspace, out4);
+    if (range2)
+        k_reduce_scaled_known<<<nvec_grid(n), REE_THREADS, 0, ree_stream(stream)>>>(ell, n, scale, range2, workspace, out4);
+    else
+        k_reduce_scaled<<<nvec_grid(n), REE_THREADS, 0, ree_stream(stream)>>>(ell, n, scale, workspace, out4);
     return ree_check_launch("ree_reduce_scaled");
+}
+
+extern "C" int ree_vector_range(const double* v, int64_t n, double* workspace, double* out2, void* stream) {
+    if (!v || !workspace || !out2 || n < 0) return ree_set_error(REE_E_BADARG, "ree_vector_range: bad argument");
+    k_vector_range<<<nvec_grid(n), REE_THREADS, 0, ree_stream(stream)>>>(v, n, workspace, out2);
+    return ree_check_launch("ree_vector_range");
 }

@@ -305,13 +305,22 @@ class Engine:
                                        ws.data_ptr(), out.data_ptr(), self.stream), "ree_reduce_cvar")
         return self.comm.combine_expsums_(out)
 
-    def reduce_scaled(self, ell: torch.Tensor, n: int, d: int, scale: float, out=None) -> torch.Tensor:
-        """[max, sum exp, sum exp^2, count] of scale*ell (a log-target vector from :meth:`logtgt`)."""
+    def reduce_scaled(self, ell: torch.Tensor, n: int, d: int, scale: float, out=None, range2=None) -> torch.Tensor:
+        """[max, sum exp, sum exp^2, count] of scale*ell (a log-target vector from :meth:`logtgt`); ``range2`` (from
+        :meth:`vector_range`) makes the shift known in advance."""
         out = out if out is not None else self.empty(4)
         ws = self.workspace(d)
-        check(self.lib.ree_reduce_scaled(ell.data_ptr(), n, float(scale), ws.data_ptr(), out.data_ptr(), self.stream),
-              "ree_reduce_scaled")
+        check(self.lib.ree_reduce_scaled(ell.data_ptr(), n, float(scale),
+                                         range2.data_ptr() if range2 is not None else None, ws.data_ptr(),
+                                         out.data_ptr(), self.stream), "ree_reduce_scaled")
         return self.comm.combine_expsums_(out)
+
+    def vector_range(self, v: torch.Tensor, n: int, d: int) -> torch.Tensor:
+        """Device [max, min] over the finite entries of this rank's part of an N-vector."""
+        out = self.empty(2)
+        ws = self.workspace(d)
+        check(self.lib.ree_vector_range(v.data_ptr(), n, ws.data_ptr(), out.data_ptr(), self.stream), "ree_vector_range")
+        return out
 
     def count_failed(self, ens: Ensemble, out=None, reduce=True) -> torch.Tensor:
         out = out if out is not None else self.empty(1)

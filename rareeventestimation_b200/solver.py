@@ -489,12 +489,12 @@ class CBREE(Solver):
             else:
                 _log.info(f"Iteration {cache.iteration}: {msg}")
 
-    def _ess(self, cache: CBREECache, beta, out=None, ell=None) -> float:
+    def _ess(self, cache: CBREECache, beta, out=None, ell=None, range2=None) -> float:
         """ESS of the weights exp(beta*l).  `ell` (the log-target vector for cache.sigma, from ree_logtgt) makes
         repeated evaluations for different beta cost one exp per particle."""
         dev = cache._dev
         if ell is not None:
-            t4 = self._eng.fetch(self._eng.reduce_scaled(ell, dev.n, dev.d, beta, out=out))
+            t4 = self._eng.fetch(self._eng.reduce_scaled(ell, dev.n, dev.d, beta, out=out, range2=range2))
         else:
             t4 = self._eng.fetch(self._eng.reduce_ess(dev, cache.sigma, beta, self._tgt_kind(), out=out))
         if t4[3] <= 0:
@@ -506,9 +506,11 @@ class CBREE(Solver):
         out = self._eng.empty(4)
         n_tot = cache._n_total
         ell = self._ell_of(cache)
+        # the shift max(beta * l) of every evaluation follows from the range of l on this rank (ranks merge their tuples)
+        rng2 = self._eng.vector_range(ell, cache._dev.n, cache._dev.d)
 
         def obj_fun(temperature):
-            return self._ess(cache, float(np.asarray(temperature).reshape(-1)[0]), out, ell) - self.ess_tgt * n_tot
+            return self._ess(cache, float(np.asarray(temperature).reshape(-1)[0]), out, ell, rng2) - self.ess_tgt * n_tot
 
         try:
             sol = root(obj_fun, cache.beta)

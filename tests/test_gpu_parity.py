@@ -111,6 +111,32 @@ def test_reductions_vs_oracle(eng, n):
     assert eng.count_failed(ens).item() == np.sum(fin <= 0)
 
 
+@pytest.mark.parametrize("n", [1, 5, 1001, 100_003])
+def test_reduce_scaled_with_and_without_known_shift(eng, n):
+    """ESS(beta) of a precomputed log-target vector (solver.py:591-601): running shift vs shift from the vector's range,
+    both against NumPy; positive, negative and zero scale (hybr probes negative beta), masked non-finite entries."""
+    from rareeventestimation_b200.engine import ess_from
+
+    rng = np.random.default_rng(n)
+    ell = -np.abs(rng.standard_normal(n)) * 40 - 3.0
+    if n > 100:
+        ell[7], ell[11] = -np.inf, np.nan
+    ens = eng.alloc_ensemble(n, 5)
+    ld = dev_vec(eng, ens, ell)
+    rng2 = eng.vector_range(ld, n, 5)
+    fin = ell[np.isfinite(ell)]
+    np.testing.assert_array_equal(rng2.cpu().numpy(), [fin.max(), fin.min()])
+    for scale in [1.0, 0.137, 17.0, -0.5, 0.0]:
+        a = ell * scale
+        a = a[np.isfinite(a)]
+        w = np.exp(a - a.max())
+        want = np.array([a.max(), w.sum(), (w * w).sum(), a.size])
+        for r in (None, rng2):
+            t4 = eng.reduce_scaled(ld, n, 5, scale, range2=r).cpu().numpy()
+            np.testing.assert_allclose(t4, want, rtol=1e-12, atol=0)
+            assert ess_from(t4) == pytest.approx(w.sum() ** 2 / (w * w).sum(), rel=1e-12)
+
+
 def test_reductions_are_deterministic(eng):
     n = 300_001
     rng = np.random.default_rng(5)
