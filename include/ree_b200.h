@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define REE_ABI_VERSION 4
+#define REE_ABI_VERSION 5
 
 /* argument errors */
 #define REE_E_BADARG (-1)
@@ -211,6 +211,18 @@ int ree_cbree_maha(const double* x, int64_t n, int d, int64_t ld, const double* 
                    const double* mean, const double* Linv, const double* logdet, double sigma, double beta,
                    int tgt_kind, const double* wmax, double* logq, double* w, double* workspace, double* sums,
                    double* is4, void* stream);
+
+/* ---- multi-GPU: 4-tuple exchange over NVLink peer memory (one box, one process per GPU) ------------------------ */
+/* No counterpart in the single-process reference.  Replaces all_gather + ree_merge_expsums for the 32-byte results of
+ * ree_reduce_ess / _scaled / _cvar and the IS statistics: every rank stores its tuple into every rank's mailbox
+ * (CUDA IPC mapping), waits for the others' and merges in rank order -- one kernel, identical bits on all ranks.
+ * Setup: ree_peer_create (returns this rank's 64-byte IPC handle), exchange the handles by any transport,
+ * ree_peer_connect(handles[world][64]).  All ranks must call ree_peer_combine_expsums in the same order.           */
+int ree_peer_create(int rank, int world, unsigned char* handle_out64);
+int ree_peer_connect(const unsigned char* handles);
+int ree_peer_ready(void);
+int ree_peer_combine_expsums(double* out4, void* stream);
+int ree_peer_check(void);
 
 /* ---- resampling branch: one-component von Mises-Fisher-Nakagami model ---------------------------------------- */
 /* (CBREE(resample=True, mixture_model="vMFNM"), solver.py:654-663, 828-836; VMFNMixture mixturemodel.py:153-239;

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libree_b200.so")
 TGT_KINDS = {"algebraic": 0, "tanh": 1, "arctan": 2, "erf": 3, "relu": 4, "sigmoid": 5}
 LSF_EXTERNAL, LSF_AFFINE, LSF_CONVEX, LSF_FUJITA_RACKWITZ, LSF_OSCILLATOR, LSF_DIFFUSION = range(6)
 NOISE_INJECT, NOISE_PHILOX = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class ReeError(RuntimeError):
@@ -68,6 +68,11 @@ PROTOTYPES = {
     "ree_reduce_cvar": (_INT, [_P, _I64, _DBL, _DBL, _INT, _P, _P, _P]),
     "ree_reduce_scaled": (_INT, [_P, _I64, _DBL, _P, _P, _P, _P]),
     "ree_vector_range": (_INT, [_P, _I64, _P, _P, _P]),
+    "ree_peer_create": (_INT, [_INT, _INT, _P]),
+    "ree_peer_connect": (_INT, [_P]),
+    "ree_peer_ready": (_INT, []),
+    "ree_peer_combine_expsums": (_INT, [_P, _P]),
+    "ree_peer_check": (_INT, []),
     "ree_merge_expsums": (_INT, [_P, _INT, _P, _P]),
     "ree_count_failed": (_INT, [_P, _I64, _P, _P, _P]),
     "ree_cbree_step": (_INT, [_P, _P, _I64, _INT, _I64, _DBL, _P, _P, _INT, _P, _U64, _U64, _I64, _LSFP, _P, _P, _P,

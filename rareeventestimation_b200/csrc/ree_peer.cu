@@ -1,0 +1,153 @@
+// Exchange of the per-rank 4-tuples [M, S1, S2, cnt] over NVLink peer memory (one box, one process per GPU).
+//
+// Every objective evaluation of the sigma / beta optimisers ends in a cross-rank merge of 32 bytes per rank
+// (DESIGN.md section 6).  Through NCCL that is an all_gather launch + a merge kernel: ~40 us of latency for a
+// reduction that itself takes ~20-40 us, ~30 times per iteration.  Here each rank owns a small mailbox in its own HBM,
+// exported with CUDA IPC and mapped by every peer.  One kernel
+//   1. stores this rank's tuple and then a sequence number into slot [seq & 1][rank] of EVERY rank's mailbox (plain
+//      stores through the peer mapping: NVLink writes land in the owner's L2),
+//   2. spins on its OWN mailbox until all slots of parity seq & 1 carry `seq`,
+//   3. merges the tuples in rank order (same arithmetic as ree_merge_expsums => identical bits on every rank).
+// Two slot parities: rank A can only overwrite a slot of parity p after it finished exchange seq + 1, which needs
+// everybody's seq + 1 tuple, which a rank sends after it has read all seq tuples.  Every rank calls the exchange in the
+// same order (the host control flow is identical on all ranks), so `seq` is a plain per-process counter.
+#include <string.h>
+
+#include "common.cuh"
+
+#define REE_PEER_MAX 16
+
+struct PeerSlot {  // 64 bytes
+    double v[4];
+    unsigned long long seq;
+    unsigned long long pad[3];
+};
+struct PeerBox {
+    PeerSlot slot[2][REE_PEER_MAX];
+};
+
+struct PeerState {
+    int rank, world;
+    PeerBox* local;                 // this rank's mailbox (cudaMalloc)
+    PeerBox* box[REE_PEER_MAX];     // every rank's mailbox as mapped into this process (box[rank] == local)
+    unsigned long long seq;
+    int* d_error;                   // device flag: a spin timed out
+};
+static PeerState g_peer[64];
+static bool g_peer_ready[64] = {false};
+
+struct PeerArgs {
+    PeerBox* box[REE_PEER_MAX];
+    int rank, world;
+    unsigned long long seq;
+    int* error;
+};
+
+__global__ void __launch_bounds__(32) k_peer_exchange(double* out4, const PeerArgs a) {
+    __shared__ double t[REE_PEER_MAX][4];
+    const int r = threadIdx.x;
+    const int par = (int)(a.seq & 1ull);
+    if (r < a.world) {
+        volatile PeerSlot* dst = &a.box[r]->slot[par][a.rank];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst->v[k] = out4[k];
+        __threadfence_system();
+        dst->seq = a.seq;
+        __threadfence_system();
+        volatile PeerSlot* src = &a.box[a.rank]->slot[par][r];
+        unsigned long long spins = 0;
+        while (src->seq != a.seq) {
+            if (++spins > (1ull << 28)) {  // ~ seconds: a peer died or the call order diverged
+                *a.error = 1;
+                break;
+            }
+        }
+        __threadfence_system();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[r][k] = src->v[k];
+    }
+    __syncwarp();
+    if (r == 0) {
+        ExpSums acc{t[0][0], t[0][1], t[0][2], t[0][3]};
+        for (int q = 1; q < a.world; ++q) acc = expsums_merge(acc, ExpSums{t[q][0], t[q][1], t[q][2], t[q][3]});
+        out4[0] = acc.m; out4[1] = acc.s1; out4[2] = acc.s2; out4[3] = acc.cnt;
+    }
+}
+
+// ---- setup -------------------------------------------------------------------------------------
+// 1. every rank: ree_peer_create(rank, world, handle_out[64])      -> allocates the mailbox, returns its IPC handle
+// 2. exchange the handles (any transport; engine.py uses torch.distributed.all_gather_object)
+// 3. every rank: ree_peer_connect(handles[world][64])               -> maps the peers' mailboxes
+extern "C" int ree_peer_create(int rank, int world, unsigned char* handle_out) {
+    if (rank < 0 || world < 2 || world > REE_PEER_MAX || rank >= world || !handle_out)
+        return ree_set_error(REE_E_BADARG, "ree_peer_create: bad argument");
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess || dev < 0 || dev >= 64) return ree_set_error(REE_E_BADARG, "ree_peer_create: no device");
+    PeerState& s = g_peer[dev];
+    if (!s.local) {
+        err = cudaMalloc((void**)&s.local, sizeof(PeerBox));
+        if (err == cudaSuccess) err = cudaMemset(s.local, 0, sizeof(PeerBox));
+        if (err == cudaSuccess) err = cudaMalloc((void**)&s.d_error, sizeof(int));
+        if (err == cudaSuccess) err = cudaMemset(s.d_error, 0, sizeof(int));
+        if (err == cudaSuccess) err = cudaDeviceSynchronize();  // the mailbox is zero before its handle leaves the process
+        if (err != cudaSuccess) return ree_set_error((int)err, cudaGetErrorString(err));
+    }
+    s.rank = rank; s.world = world; s.seq = 0;
+    cudaIpcMemHandle_t h;
+    err = cudaIpcGetMemHandle(&h, s.local);
+    if (err != cudaSuccess) return ree_set_error((int)err, cudaGetErrorString(err));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle_out, &h, 64);
+    return 0;
+}
+
+extern "C" int ree_peer_connect(const unsigned char* handles) {
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess || dev < 0 || dev >= 64 || !g_peer[dev].local || !handles)
+        return ree_set_error(REE_E_BADARG, "ree_peer_connect: ree_peer_create first");
+    PeerState& s = g_peer[dev];
+    for (int r = 0; r < s.world; ++r) {
+        if (r == s.rank) {
+            s.box[r] = s.local;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * (size_t)r, 64);
+        void* p = nullptr;
+        err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (err != cudaSuccess) return ree_set_error((int)err, cudaGetErrorString(err));
+        s.box[r] = (PeerBox*)p;
+    }
+    g_peer_ready[dev] = true;
+    return 0;
+}
+
+extern "C" int ree_peer_ready(void) {
+    int dev = 0;
+    return (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && g_peer_ready[dev]) ? 1 : 0;
+}
+
+// In place: out4 (DEVICE, this rank's tuple) becomes the merge over all ranks.  Stream ordered; all ranks must call it
+// in the same order.  A timed-out wait is reported by the NEXT call (the flag is read back lazily) or by ree_peer_check.
+extern "C" int ree_peer_combine_expsums(double* out4, void* stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_peer_ready[dev] || !out4)
+        return ree_set_error(REE_E_BADARG, "ree_peer_combine_expsums: peers are not connected");
+    PeerState& s = g_peer[dev];
+    PeerArgs a{};
+    for (int r = 0; r < s.world; ++r) a.box[r] = s.box[r];
+    a.rank = s.rank; a.world = s.world; a.seq = ++s.seq; a.error = s.d_error;
+    k_peer_exchange<<<1, 32, 0, ree_stream(stream)>>>(out4, a);
+    return ree_check_launch("ree_peer_combine_expsums");
+}
+
+extern "C" int ree_peer_check(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_peer_ready[dev]) return 0;
+    int flag = 0;
+    cudaError_t err = cudaMemcpy(&flag, g_peer[dev].d_error, sizeof(int), cudaMemcpyDeviceToHost);
+    if (err != cudaSuccess) return ree_set_error((int)err, cudaGetErrorString(err));
+    return flag ? ree_set_error(REE_E_BADARG, "peer exchange timed out (a rank died or the call order diverged)") : 0;
+}

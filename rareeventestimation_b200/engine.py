@@ -55,6 +55,28 @@ class Comm:
         self.group = group
         self.rank = dist.get_rank(group) if self.enabled else 0
         self.world = dist.get_world_size(group) if self.enabled else 1
+        self.peer = None  # None: not tried yet; True / False: NVLink mailboxes connected / NCCL all_gather instead
+
+    def _connect_peers(self, device) -> bool:
+        """Map every rank's mailbox into this process (CUDA IPC).  All ranks decide together: peer mode only if every
+        rank is on this host and every mapping succeeded; otherwise all of them keep the NCCL all_gather."""
+        import os
+        import socket
+
+        lib = _lib.load()
+        ok = os.environ.get("REE_PEER", "1") != "0" and self.world <= 16
+        buf = (C.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            if ok:
+                ok = lib.ree_peer_create(self.rank, self.world, buf) == 0
+            infos = [None] * self.world
+            self.dist.all_gather_object(infos, (socket.gethostname(), ok, bytes(buf)), group=self.group)
+            ok = all(i[1] for i in infos) and len({i[0] for i in infos}) == 1
+            if ok:
+                ok = lib.ree_peer_connect(b"".join(i[2] for i in infos)) == 0
+            flags = [None] * self.world
+            self.dist.all_gather_object(flags, ok, group=self.group)  # also the barrier before the first exchange
+        return all(flags)
 
     def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
         if self.enabled:
@@ -63,6 +85,13 @@ class Comm:
 
     def combine_expsums_(self, out4: torch.Tensor) -> torch.Tensor:
         """all_gather the local 4-tuple and merge in rank order (identical bits on every rank)."""
+        if self.enabled and out4.is_cuda:
+            if self.peer is None:
+                self.peer = self._connect_peers(out4.device)
+            if self.peer:  # one kernel: store to all mailboxes, wait, merge (csrc/ree_peer.cu)
+                stream = C.c_void_p(torch.cuda.current_stream(out4.device).cuda_stream)
+                check(_lib.load().ree_peer_combine_expsums(out4.data_ptr(), stream), "ree_peer_combine_expsums")
+                return out4
         if self.enabled:
             gathered = torch.empty(self.world * 4, dtype=out4.dtype, device=out4.device)
             self.dist.all_gather_into_tensor(gathered, out4.contiguous(), group=self.group)
@@ -73,6 +102,11 @@ class Comm:
             else:
                 out4.copy_(merge_expsums(gathered.view(self.world, 4)))
         return out4
+
+    def check_peers(self) -> None:
+        """Raise if a peer exchange timed out since the last check (one 4-byte D2H copy)."""
+        if self.peer:
+            check(_lib.load().ree_peer_check(), "ree_peer_check")
 
     def shard(self, n_global: int):
         """Contiguous slice [lo, hi) of this rank."""

@@ -405,6 +405,7 @@ class CBREE(Solver):
         tails[0:2].copy_(sums_u[d + d * d:])
         tails[2:4].copy_(sums_w[d + d * d:])
         host = res.cpu().numpy()  # the one synchronising D2H of the iteration
+        eng.comm.check_peers()
         cache.ens_mean = host[0:d].copy()
         cache.ens_cov = host[d:d + d * d].reshape(d, d).copy()
         cache.weighted_mean = host[d + d * d:2 * d + d * d].copy()
