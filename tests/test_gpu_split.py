@@ -141,3 +141,42 @@ def test_split_kernels_are_deterministic(eng):
         outs.append((eng.download(a), su.cpu().numpy().copy(), sw.cpu().numpy().copy()))
     for x, y in zip(outs[0], outs[1]):
         np.testing.assert_array_equal(x, y)
+
+
+@pytest.mark.parametrize("n,d", [(1, 100), (9471, 100), (9473, 64), (20001, 100), (37, 6), (1001, 4), (515, 20)])
+def test_update_kernels_stay_inside_their_buffers(eng, n, d):
+    """Guard bands around X', g', e' (all written by the update sweeps: warp-specialised transform for 56 <= d <= 103,
+    DMMA-Gram thread-per-particle sweep for d <= 6, fused sweep in between) must survive ragged sizes untouched."""
+    import torch
+
+    from rareeventestimation_b200 import _lib
+    from rareeventestimation_b200.engine import DeviceLsf, Ensemble
+
+    rng = np.random.default_rng(n + d)
+    src = eng.upload(rng.standard_normal((n, d)))
+    ld = src.ld
+    big = torch.full(((d + 2) * ld,), float("nan"), dtype=torch.float64, device=src.X.device)
+    vec = torch.full((2, 3 * ld), float("nan"), dtype=torch.float64, device=src.X.device)
+    dst = Ensemble(big[ld:(d + 1) * ld].view(d, ld), n, d, ld, 0, vec[0, ld:2 * ld], vec[1, ld:2 * ld])
+    A = rng.standard_normal((d, d)) / np.sqrt(d)
+    F = eng.to_device(np.linalg.cholesky(A @ A.T + 0.5 * np.eye(d)))
+    lsf = DeviceLsf(_lib.LSF_AFFINE, d, None, 3.5)
+    split = eng.path(d) == 2
+    sums = None if split else eng.empty(d + d * d + 2)
+    eng.cbree_step(src, dst, 0.7, eng.zeros(d), F, lsf, None, sums, seed=5, draw=9)
+    torch.cuda.synchronize()
+    assert torch.isnan(big[:ld]).all() and torch.isnan(big[(d + 1) * ld:]).all()
+    assert torch.isnan(vec[:, :ld]).all() and torch.isnan(vec[:, 2 * ld:]).all()
+    assert torch.isfinite(dst.X[:, :n]).all() and torch.isfinite(dst.g[:n]).all() and torch.isfinite(dst.e[:n]).all()
+    # the redraw of the resampling branch writes the same buffers
+    if d >= 2:
+        model_mu = rng.standard_normal(d)
+        model_mu /= np.linalg.norm(model_mu)
+        from rareeventestimation_b200.mixture import _house
+
+        v, b = _house(model_mu)
+        big.fill_(float("nan"))
+        eng.vmfn_sample(dst, eng.to_device(v), b, 4.0, d / 2, float(d), 11, 3)
+        torch.cuda.synchronize()
+        assert torch.isnan(big[:ld]).all() and torch.isnan(big[(d + 1) * ld:]).all()
+        assert torch.isfinite(dst.X[:, :n]).all()
