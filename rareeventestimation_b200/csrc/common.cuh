@@ -238,6 +238,29 @@ __device__ __forceinline__ double block_sum(double v, double* smem /* >= 32 */) 
     return v;
 }
 
+// Block-wide merge of per-thread ExpAcc: one max reduction, one rescale per thread (exp_nonpos), three plain sums --
+// instead of ten pairwise merges with two libdevice exp each (which cost as many instructions as a thread's whole
+// stream at ~8 quads per thread).  Fixed trees => deterministic.  Result valid in thread 0.
+__device__ __forceinline__ ExpSums expacc_block_reduce(const ExpAcc& a, uint32_t T, double* smem /* >= 32 */) {
+    double m = a.m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double q = __shfl_xor_sync(0xffffffffu, m, o);
+        m = q > m ? q : m;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) smem[warp] = m;
+    __syncthreads();
+    double mb = -CUDART_INF;
+    for (int w = 0; w < nw; ++w) mb = smem[w] > mb ? smem[w] : mb;  // every thread: the block's shift
+    __syncthreads();
+    const double f = exp_nonpos(a.m - mb, T);  // a.m = -inf (empty thread) or mb = -inf (empty block): 0 / NaN -> 0
+    const double s1 = block_sum(a.s1 * f, smem);
+    const double s2 = block_sum(a.s2 * f * f, smem);
+    const double cnt = block_sum((double)a.cnt, smem);
+    return ExpSums{mb, s1, s2, cnt};
+}
+
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011) + Box-Muller in fp64.
 // counter = (particle lo, particle hi, dim pair, draw[31:0]), key = seed.  One call yields two N(0,1).

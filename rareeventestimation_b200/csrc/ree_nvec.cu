@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(REE_THREADS) k_reduce_ess(const double* __rest
                                                             double* __restrict__ a_out, double* ws, double* out4) {
     __shared__ ExpSums sh[32];
     __shared__ bool is_last;
-    __shared__ double Tsh[64];
+    __shared__ double Tsh[64], red[32];
     const uint32_t T = load_exp_table(Tsh);
     ExpAcc acc = expacc_empty();
     const bool vec_out = a_out && aligned16(a_out);
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(REE_THREADS) k_reduce_ess(const double* __rest
     };
     if (e) stream2q(g, e, n, quad, one);
     else stream1q(g, n, [&](int64_t i0, const Quad& gq) { quad(i0, gq, Quad{}); }, [&](int64_t i, double gi) { one(i, gi, 0.0); });
-    ExpSums blk = expsums_block_reduce(expacc_finish(acc), sh);
+    ExpSums blk = expacc_block_reduce(acc, T, red);
     expsums_grid_finalize(blk, ws, out4, sh, &is_last);
 }
 
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(REE_THREADS) k_reduce_scaled(const double* __r
                                                                double* ws, double* out4) {
     __shared__ ExpSums sh[32];
     __shared__ bool is_last;
-    __shared__ double Tsh[64];
+    __shared__ double Tsh[64], red[32];
     const uint32_t T = load_exp_table(Tsh);
     ExpAcc acc = expacc_empty();
     stream1q(ell, n,
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(REE_THREADS) k_reduce_scaled(const double* __r
                  expacc_add4(acc, a, T);
              },
              [&](int64_t, double li) { expacc_add1(acc, __dmul_rn(li, scale), T); });
-    ExpSums blk = expsums_block_reduce(expacc_finish(acc), sh);
+    ExpSums blk = expacc_block_reduce(acc, T, red);
     expsums_grid_finalize(blk, ws, out4, sh, &is_last);
 }
 
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(REE_THREADS) k_reduce_scaled_known(const doubl
                                                                      double* ws, double* out4) {
     __shared__ ExpSums sh[32];
     __shared__ bool is_last;
-    __shared__ double Tsh[64];
+    __shared__ double Tsh[64], red[32];
     const uint32_t T = load_exp_table(Tsh);
     const double M = __dmul_rn(scale >= 0.0 ? range2[0] : range2[1], scale);
     double s1 = 0.0, s2 = 0.0;
@@ -216,8 +216,10 @@ __global__ void __launch_bounds__(REE_THREADS) k_reduce_scaled_known(const doubl
                  for (int k = 0; k < 4; ++k) one(lq.v[k]);
              },
              [&](int64_t, double li) { one(li); });
-    ExpSums acc{cnt ? M : -CUDART_INF, s1, s2, (double)cnt};
-    ExpSums blk = expsums_block_reduce(acc, sh);
+    s1 = block_sum(s1, red);  // every thread used the same shift: plain sums
+    s2 = block_sum(s2, red);
+    const double cn = block_sum((double)cnt, red);
+    ExpSums blk{cn > 0.0 ? M : -CUDART_INF, s1, s2, cn};
     expsums_grid_finalize(blk, ws, out4, sh, &is_last);
 }
 
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(REE_THREADS) k_reduce_cvar(const double* __res
                                                              double* ws, double* out4) {
     __shared__ ExpSums sh[32];
     __shared__ bool is_last;
-    __shared__ double Tsh[64];
+    __shared__ double Tsh[64], red[32];
     const uint32_t T = load_exp_table(Tsh);
     ExpAcc acc = expacc_empty();
     auto val = [&](double gi) {
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(REE_THREADS) k_reduce_cvar(const double* __res
                  expacc_add4(acc, a, T);
              },
              [&](int64_t, double gi) { expacc_add1(acc, val(gi), T); });
-    ExpSums blk = expsums_block_reduce(expacc_finish(acc), sh);
+    ExpSums blk = expacc_block_reduce(acc, T, red);
     expsums_grid_finalize(blk, ws, out4, sh, &is_last);
 }
 

@@ -301,13 +301,21 @@ __global__ void __launch_bounds__(SM_T, SG_CTAS) k_small_post_g(const SmallArgs 
 
 // second stage of the Gram variants: fixed-order sum of the per-CTA 8 x 8 Grams, expanded to the public layout
 //   sums = [S1 (d) | S2 (d x d) | a | b]: step / plain: a = #{g<=0} = G[D+1][D], b = n = G[D][D]; weighted: a = sum w, b = 0
-__global__ void __launch_bounds__(64) k_small_finish_g(const double* __restrict__ partials, int nparts, int d, int weighted,
-                                                       double* __restrict__ sums) {
-    __shared__ double G[64];
+__global__ void __launch_bounds__(512) k_small_finish_g(const double* __restrict__ partials, int nparts, int d,
+                                                        int weighted, double* __restrict__ sums) {
+    __shared__ double G[64], part[8][64];
+    const int e = threadIdx.x & 63, grp = threadIdx.x >> 6;  // 8 groups of CTA partials, summed in group order
     double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * 64 + threadIdx.x];
-    G[threadIdx.x] = s;
+    for (int p = grp; p < nparts; p += 8) s += partials[(size_t)p * 64 + e];
+    part[grp][e] = s;
     __syncthreads();
+    if (threadIdx.x >= 64) return;
+    s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += part[q][e];
+    G[e] = s;
+    __syncwarp();
+    asm volatile("bar.sync 1, 64;" ::: "memory");  // the 64 surviving threads (two warps)
     const int r = threadIdx.x >> 3, c = threadIdx.x & 7;
     if (r < d && c < d) sums[d + r * d + c] = G[(r >= c ? r : c) * 8 + (r >= c ? c : r)];  // the lower triangle's bits
     if (r == d && c < d) sums[c] = G[d * 8 + c];
@@ -562,7 +570,7 @@ static int dispatch_small(int which, int d, const SmallArgs& a, int grid, cudaSt
 
 static int finish_small(const double* partials, int grid, int d, int weighted, double* sums, cudaStream_t st) {
     if (small_gram_path(d)) {
-        k_small_finish_g<<<1, 64, 0, st>>>(partials, grid, d, weighted, sums);
+        k_small_finish_g<<<1, 512, 0, st>>>(partials, grid, d, weighted, sums);
         return ree_check_launch("k_small_finish_g");
     }
     k_small_finish<<<1, 64, 0, st>>>(partials, grid, d, sums);
