@@ -183,8 +183,7 @@ class SIS(Solver):
         assert hasattr(prob, "eranataf_dist"), \
             "For sequential importance sampling, prob needs to have an ERANataf distribution."
         eng = Engine.get()
-        if eng.comm.enabled:
-            raise NotImplementedError("SIS-aCS runs on one GPU (resampling would move particles between ranks)")
+        comm = eng.comm
         lib = eng.lib
         N, d = prob.sample.shape
         p = self.num_chains_wrt_sample
@@ -192,41 +191,50 @@ class SIS(Solver):
             raise RuntimeError("N*p and 1/p must be positive integers. Adjust N and p accordingly")
         seed = int(np.random.SeedSequence(self.seed).generate_state(1)[0]) if self.seed is not None else \
             int(np.random.SeedSequence().generate_state(1)[0])
+        if comm.enabled:  # one seed for all ranks (the unseeded case draws from OS entropy per process)
+            box = [seed]
+            comm.dist.broadcast_object_list(box, src=0, group=comm.group)
+            seed = box[0]
         nchain, lenchain, burn = int(N * p), int(round(1 / p)), int(self.burn_in)
         tar = float(self.cvar_tgt)
         max_it = 100
+        # Multi-GPU: every rank owns a slice of the population; only sums cross ranks.  Resampling
+        # moves no particle: the number of seeds a rank contributes is multinomial in the ranks' weight sums (drawn
+        # from a generator all ranks share), each rank then resamples locally and runs its own chains, so the next
+        # level's population of a rank is (its seeds) x (chain length) particles.
+        lo, hi = comm.shard(N)
         # level-0 population (solver.py:1128-1131)
         if isinstance(prob.sample, DeviceSample):
-            pop = prob.sample.materialise(eng)
+            pop = prob.sample.materialise(eng, lo, hi)
         elif self.fixed_initial_sample:
-            pop = eng.upload(np.asarray(prob.sample))
+            pop = eng.upload(np.asarray(prob.sample)[lo:hi], first=lo)
         else:
-            pop = eng.philox_normal(N, d, seed, _STREAM_SIS)
+            pop = eng.philox_normal(hi - lo, d, seed, _STREAM_SIS, first=lo)
         _evaluate(prob, eng, pop)
         n_evals = N
         ws = eng.workspace(d)
         out4 = eng.empty(4)
         stream = lambda: eng.stream  # noqa: E731
+        split_rng = np.random.default_rng(seed)  # identical on every rank
 
         def stats(ens, s_new, s_old, mode, w_out=None):
-            check(lib.ree_sis_reduce(ens.g.data_ptr(), ens.n, float(s_new), float(s_old), mode,
-                                     w_out.data_ptr() if w_out is not None else None, ws.data_ptr(),
-                                     out4.data_ptr(), stream()), "ree_sis_reduce")
-            t = out4.cpu().numpy()
+            """Global mean / std of the level weights (mode 0) or of the indicator (mode 1): plain sums, added over ranks."""
+            if ens.n > 0:
+                check(lib.ree_sis_reduce(ens.g.data_ptr(), ens.n, float(s_new), float(s_old), mode,
+                                         w_out.data_ptr() if w_out is not None else None, ws.data_ptr(),
+                                         out4.data_ptr(), stream()), "ree_sis_reduce")
+            else:
+                out4.zero_()
+            t = comm.allreduce_sum_(out4).cpu().numpy()
             mean = t[1] / t[3]
             var = max(t[2] / t[3] - mean * mean, 0.0)
-            return mean, math.sqrt(var)
+            return mean, math.sqrt(var), float(t[1])
 
-        gmu = float(pop.g[:N].mean().item())
+        gsum = pop.g[:pop.n].sum().reshape(1)
+        gmu = float(comm.allreduce_sum_(gsum).item()) / N
         sigmak = np.zeros(max_it + 1)
         Sk = np.ones(max_it)
         lam = 0.6
-        w = eng.empty(pop.ld)
-        cdf = eng.empty(pop.ld)
-        scan_scratch = eng.empty(lib.ree_scan_scratch_doubles(N))
-        idx = torch.empty(nchain, dtype=torch.int64, device=eng.device)
-        cur, cand = eng.alloc_ensemble(nchain, d), eng.alloc_ensemble(nchain, d)
-        nxt = eng.alloc_ensemble(N, d)
         cov_sl, m, draw = math.nan, 0, 0
         for m in range(max_it):
             s_old = sigmak[m] if m > 0 else -1.0
@@ -234,24 +242,43 @@ class SIS(Solver):
             def obj(x):  # |CoV(w(x)) - tarCoV|, SIS_aCS.py:153-178
                 if not x > 0:
                     return math.inf
-                mean, std = stats(pop, x, s_old, 0)
+                mean, std, _ = stats(pop, x, s_old, 0)
                 return abs(std / mean - tar) if mean > 0 else math.inf
 
-            hi = 10.0 * gmu if m == 0 else sigmak[m]
+            hi_s = 10.0 * gmu if m == 0 else sigmak[m]
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
-                sigmak[m + 1] = optimize.fminbound(obj, 0, hi)
-            mean, _ = stats(pop, sigmak[m + 1], s_old, 0, w_out=w)
+                sigmak[m + 1] = optimize.fminbound(obj, 0, hi_s)
+            w = eng.empty(max(pop.ld, 8))
+            mean, _, _ = stats(pop, sigmak[m + 1], s_old, 0, w_out=w)
             Sk[m] = mean
             if Sk[m] == 0:
                 break
+            # how many of the nchain seeds each rank contributes: multinomial in the ranks' weight sums
+            wsum = (w[:pop.n].sum() if pop.n > 0 else eng.zeros(1).sum()).reshape(1)
+            if comm.enabled:
+                parts = torch.empty(comm.world, dtype=wsum.dtype, device=wsum.device)
+                comm.dist.all_gather_into_tensor(parts, wsum, group=comm.group)
+                pw = parts.cpu().numpy()
+                counts = split_rng.multinomial(nchain, pw / pw.sum())
+                my_chains, chain0 = int(counts[comm.rank]), int(counts[:comm.rank].sum())
+            else:
+                my_chains, chain0 = nchain, 0
+            cur, cand = eng.alloc_ensemble(max(my_chains, 1), d), eng.alloc_ensemble(max(my_chains, 1), d)
+            nxt = eng.alloc_ensemble(max(my_chains * lenchain, 1), d)
+            cur.n = cand.n = my_chains
+            nxt.n = my_chains * lenchain
             # seeds: multinomial resampling by scan + search + gather (SIS_aCS.py:194-196)
-            check(lib.ree_scan_inclusive(w.data_ptr(), N, cdf.data_ptr(), scan_scratch.data_ptr(), stream()), "scan")
             draw += 1
-            check(lib.ree_sis_resample(cdf.data_ptr(), N, nchain, seed, _STREAM_SIS + draw, 0, idx.data_ptr(), stream()),
-                  "ree_sis_resample")
-            check(lib.ree_gather_columns(pop.X.data_ptr(), d, pop.ld, idx.data_ptr(), nchain, cur.X.data_ptr(), cur.ld,
-                                         pop.g.data_ptr(), cur.g.data_ptr(), stream()), "ree_gather_columns")
+            if my_chains > 0:
+                cdf = eng.empty(pop.ld)
+                scan_scratch = eng.empty(lib.ree_scan_scratch_doubles(pop.n))
+                idx = torch.empty(my_chains, dtype=torch.int64, device=eng.device)
+                check(lib.ree_scan_inclusive(w.data_ptr(), pop.n, cdf.data_ptr(), scan_scratch.data_ptr(), stream()), "scan")
+                check(lib.ree_sis_resample(cdf.data_ptr(), pop.n, my_chains, seed, _STREAM_SIS + draw, chain0,
+                                           idx.data_ptr(), stream()), "ree_sis_resample")
+                check(lib.ree_gather_columns(pop.X.data_ptr(), d, pop.ld, idx.data_ptr(), my_chains, cur.X.data_ptr(),
+                                             cur.ld, pop.g.data_ptr(), cur.g.data_ptr(), stream()), "ree_gather_columns")
             # aCS chains: all chains advance together; lambda is adapted between sub-batches of the chain steps
             # (the reference adapts after every 10 *sequential* chains, SIS_aCS.py:257-268 -- statistically
             # equivalent, not bit-reproducible)
@@ -262,33 +289,36 @@ class SIS(Solver):
                 sigmafk = min(lam, 1.0)
                 rhok = math.sqrt(1 - sigmafk**2)
                 draw += 1
-                check(lib.ree_acs_propose(cur.X.data_ptr(), nchain, d, cur.ld, rhok, sigmafk, seed, _STREAM_SIS + draw,
-                                          0, cand.X.data_ptr(), stream()), "ree_acs_propose")
-                _evaluate(prob, eng, cand)
-                n_evals += nchain
                 keep = step >= burn
-                check(lib.ree_acs_accept(cur.X.data_ptr(), cur.g.data_ptr(), cand.X.data_ptr(), cand.g.data_ptr(), nchain,
-                                         d, cur.ld, float(sigmak[m + 1]), seed, _STREAM_SIS + draw, 0,
-                                         nxt.X.data_ptr() if keep else cand.X.data_ptr(),
-                                         nxt.ld if keep else cand.ld, col if keep else 0,
-                                         nxt.g.data_ptr() if keep else cand.g.data_ptr(), ws.data_ptr(), out4.data_ptr(),
-                                         stream()), "ree_acs_accept")
+                if my_chains > 0:
+                    check(lib.ree_acs_propose(cur.X.data_ptr(), my_chains, d, cur.ld, rhok, sigmafk, seed,
+                                              _STREAM_SIS + draw, chain0, cand.X.data_ptr(), stream()), "ree_acs_propose")
+                    _evaluate(prob, eng, cand)
+                    check(lib.ree_acs_accept(cur.X.data_ptr(), cur.g.data_ptr(), cand.X.data_ptr(), cand.g.data_ptr(),
+                                             my_chains, d, cur.ld, float(sigmak[m + 1]), seed, _STREAM_SIS + draw, chain0,
+                                             nxt.X.data_ptr() if keep else cand.X.data_ptr(),
+                                             nxt.ld if keep else cand.ld, col if keep else 0,
+                                             nxt.g.data_ptr() if keep else cand.g.data_ptr(), ws.data_ptr(),
+                                             out4.data_ptr(), stream()), "ree_acs_accept")
+                else:
+                    out4.zero_()
+                n_evals += nchain
                 if keep:
-                    col += nchain
-                t = out4.cpu().numpy()
+                    col += my_chains
+                t = comm.allreduce_sum_(out4).cpu().numpy()
                 alpha_mu = t[1] / t[3]
                 alphas.append(alpha_mu)
                 counta += 1
                 lam = min(math.exp(math.log(lam) + counta ** (-0.5) * (alpha_mu - 0.44)), 1.0)
-            pop, nxt = nxt, pop
-            mean, std = stats(pop, sigmak[m + 1], -1.0, 1)
+            pop = nxt
+            mean, std, _ = stats(pop, sigmak[m + 1], -1.0, 1)
             cov_sl = std / mean if mean > 0 else math.nan
             if self.verbose:
                 print(f"\nCOV_Sl = {cov_sl}\n\t*aCS lambda = {lam}\t*aCS accrate = {np.mean(alphas)}")
             if cov_sl < tar:
                 break
         l_tot = m + 1
-        mean, _ = stats(pop, sigmak[m + 1], -1.0, 1)
+        mean, _, _ = stats(pop, sigmak[m + 1], -1.0, 1)
         pr = mean * float(np.prod(Sk))
         other = {"k_fin": math.nan, "COV_Sl": cov_sl} if self.return_other else None
         return Solution(_LazyEnsemble(eng, pop), np.array([math.nan]), np.zeros((1, N)) * math.nan, np.array([pr]),
