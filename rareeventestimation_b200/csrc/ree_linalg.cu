@@ -8,8 +8,16 @@
 // in-place lower Cholesky of A (row-major, leading dimension lda) in shared memory.
 // psd = true: a pivot <= tiny * max_diag gives a zero column (semi-definite factor, no failure);
 // psd = false: the first non-positive pivot is reported in *info (1-based) and the sweep stops.
-__device__ void chol_smem(double* A, int d, int lda, bool psd, double* s_stat /* [4] smem */) {
-    const int tid = threadIdx.x, nt = blockDim.x;
+//
+// Blocked right-looking sweep, panels of CH_NB columns: warp 0 factors a panel with warp-level synchronisation only
+// (lane = row), then all warps apply the panel to the trailing matrix (warp = row, lane = column).  Every element still
+// receives its updates one column at a time in increasing column order, so the factor has the same bits as the
+// column-by-column sweep it replaces -- with 2 CTA barriers per panel instead of 3 per column, and the logarithms of
+// the pivots (log det) taken off the critical path.  pivlog: d doubles of shared scratch.
+#define CH_NB 8
+
+__device__ void chol_smem(double* A, int d, int lda, bool psd, double* s_stat /* [4] smem */, double* pivlog) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     if (tid == 0) {
         double mx = 0.0;
         for (int j = 0; j < d; ++j) mx = fmax(mx, A[j * lda + j]);
@@ -18,42 +26,71 @@ __device__ void chol_smem(double* A, int d, int lda, bool psd, double* s_stat /*
         s_stat[2] = CUDART_INF;   // min pivot
         s_stat[3] = mx;           // max diag
     }
+    for (int j = tid; j < d; j += nt) pivlog[j] = 0.0;  // accepted pivots (0: zero column / not reached)
     __syncthreads();
     const double mx = s_stat[3];
-    for (int k = 0; k < d; ++k) {
-        if (tid == 0) {
-            double piv = A[k * lda + k];
-            s_stat[2] = fmin(s_stat[2], piv);
-            if (!(piv > 0.0) || !isfinite(piv)) {
-                if (psd && isfinite(piv)) {
-                    A[k * lda + k] = 0.0;
-                } else if (s_stat[1] == 0.0) {
-                    s_stat[1] = (double)(k + 1);
+    for (int kb = 0; kb < d; kb += CH_NB) {
+        const int ke = min(kb + CH_NB, d);
+        if (warp == 0) {  // ---- panel: columns kb .. ke-1, rows kb .. d-1 ----
+            for (int k = kb; k < ke; ++k) {
+                if (lane == 0) {
+                    const double piv = A[k * lda + k];
+                    s_stat[2] = fmin(s_stat[2], piv);
+                    if (!(piv > 0.0) || !isfinite(piv)) {
+                        if (psd && isfinite(piv)) {
+                            A[k * lda + k] = 0.0;
+                        } else if (s_stat[1] == 0.0) {
+                            s_stat[1] = (double)(k + 1);
+                        }
+                    } else if (psd && piv <= 1e-14 * mx) {
+                        A[k * lda + k] = 0.0;
+                    } else {
+                        pivlog[k] = piv;
+                        A[k * lda + k] = sqrt(piv);
+                    }
                 }
-            } else if (psd && piv <= 1e-14 * mx) {
-                A[k * lda + k] = 0.0;
-            } else {
-                s_stat[0] += log(piv);
-                A[k * lda + k] = sqrt(piv);
+                __syncwarp();
+                if (s_stat[1] != 0.0) break;
+                const double lkk = A[k * lda + k];
+                const double inv = lkk > 0.0 ? 1.0 / lkk : 0.0;
+                for (int j = k + 1 + lane; j < d; j += 32) A[j * lda + k] *= inv;
+                __syncwarp();
+                // the rest of the panel: A[j][l] -= A[j][k] * A[l][k], k < l < ke, l <= j
+                for (int j = k + 1 + lane; j < d; j += 32) {
+                    const double ajk = A[j * lda + k];
+                    const int le = min(ke, j + 1);
+                    for (int l = k + 1; l < le; ++l) A[j * lda + l] = fma(-ajk, A[l * lda + k], A[j * lda + l]);
+                }
+                __syncwarp();
             }
         }
         __syncthreads();
         if (s_stat[1] != 0.0) break;
-        const double lkk = A[k * lda + k];
-        const double inv = lkk > 0.0 ? 1.0 / lkk : 0.0;
-        for (int j = k + 1 + tid; j < d; j += nt) A[j * lda + k] *= inv;
-        __syncthreads();
-        // trailing update of the lower triangle: A[j][l] -= A[j][k]*A[l][k], k < l <= j
-        const int m = d - k - 1;
-        for (int idx = tid; idx < m * m; idx += nt) {
-            int jj = idx / m, ll = idx - jj * m;
-            if (ll <= jj) {
-                int j = k + 1 + jj, l = k + 1 + ll;
-                A[j * lda + l] = fma(-A[j * lda + k], A[l * lda + k], A[j * lda + l]);
+        // ---- trailing matrix: rows j >= ke, columns ke .. j; the panel's columns one after the other ----
+        for (int j = ke + warp; j < d; j += nw) {
+            double ajk[CH_NB];
+#pragma unroll
+            for (int c = 0; c < CH_NB; ++c) ajk[c] = (kb + c < ke) ? A[j * lda + kb + c] : 0.0;
+            for (int l = ke + lane; l <= j; l += 32) {
+                double v = A[j * lda + l];
+#pragma unroll
+                for (int c = 0; c < CH_NB; ++c)
+                    if (kb + c < ke) v = fma(-ajk[c], A[l * lda + kb + c], v);
+                A[j * lda + l] = v;
             }
         }
         __syncthreads();
     }
+    // log det = sum of log(pivot) in column order (same summation order as before)
+    for (int j = tid; j < d; j += nt) pivlog[j] = pivlog[j] > 0.0 ? log(pivlog[j]) : 0.0;
+    __syncthreads();
+    if (tid == 0) {
+        double acc = 0.0;
+        for (int j = 0; j < d; ++j)
+            if (pivlog[j] != 0.0) acc += pivlog[j];
+        s_stat[0] = acc;
+    }
+    __syncthreads();
 }
 
 // mean / cov from shifted raw sums, then chol(cov) and its inverse.
@@ -68,6 +105,7 @@ __global__ void __launch_bounds__(REE_LA_THREADS) k_moments_chol(const double* _
     double* A = sm;                 // d x lda
     double* ybar = A + d * lda;     // d
     double* s_stat = ybar + d;      // 4
+    double* pivlog = s_stat + 4;    // d
     const int tid = threadIdx.x, nt = blockDim.x;
     const double tot = weighted ? sums[d + d * d] : sums[d + d * d + 1];
     for (int j = tid; j < d; j += nt) {
@@ -89,8 +127,7 @@ __global__ void __launch_bounds__(REE_LA_THREADS) k_moments_chol(const double* _
     if (!L) return;
     if (Linv)  // stays zero if the factorisation fails (callers check stats4[1])
         for (int idx = tid; idx < d * d; idx += nt) Linv[idx] = 0.0;
-    chol_smem(A, d, lda, false, s_stat);
-    __syncthreads();
+    chol_smem(A, d, lda, false, s_stat, pivlog);
     for (int idx = tid; idx < d * d; idx += nt) {
         int j = idx / d, k = idx - j * d;
         L[idx] = (k <= j) ? A[j * lda + k] : 0.0;
@@ -102,14 +139,24 @@ __global__ void __launch_bounds__(REE_LA_THREADS) k_moments_chol(const double* _
         stats4[3] = s_stat[3];
     }
     if (!Linv || s_stat[1] != 0.0) return;
-    // inverse of the lower factor, one column per thread: solve L x = e_c by forward substitution.
-    // x lives in global memory (row-major Linv => coalesced across the threads of a warp).
+    // inverse of the lower factor, one column per thread: solve L x = e_c by forward substitution (same arithmetic as
+    // before: bit-identical).  Column c of the inverse lives in shared memory next to the factor: the strict upper
+    // triangle plus the padding column of A has exactly d(d+1)/2 free slots, x_j goes to A[c][j+1] (row c: contiguous
+    // for the thread, rows d+1 apart across threads: conflict-free) -- no global-memory round trip per term.
+    __syncthreads();
     for (int c = tid; c < d; c += nt) {
+        double* x = A + c * lda + 1;  // x[j], j >= c
         for (int j = c; j < d; ++j) {
             double s = (j == c) ? 1.0 : 0.0;
-            for (int k = c; k < j; ++k) s = fma(-A[j * lda + k], Linv[k * d + c], s);
-            Linv[j * d + c] = s / A[j * lda + j];
+            const double* Lj = A + j * lda;
+            for (int k = c; k < j; ++k) s = fma(-Lj[k], x[k], s);
+            x[j] = s / Lj[j];
         }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < d * d; idx += nt) {
+        int j = idx / d, c = idx - j * d;
+        if (c <= j) Linv[idx] = A[c * lda + j + 1];
     }
 }
 
@@ -119,6 +166,7 @@ __global__ void __launch_bounds__(REE_LA_THREADS) k_chol_scaled(const double* __
     const int lda = d + 1;
     double* A = sm;
     double* s_stat = A + d * lda;
+    double* pivlog = s_stat + 4;
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int idx = tid; idx < d * d; idx += nt) {
         int j = idx / d, k = idx - j * d;
@@ -127,8 +175,7 @@ __global__ void __launch_bounds__(REE_LA_THREADS) k_chol_scaled(const double* __
         A[j * lda + k] = scale * v;
     }
     __syncthreads();
-    chol_smem(A, d, lda, true, s_stat);
-    __syncthreads();
+    chol_smem(A, d, lda, true, s_stat, pivlog);
     for (int idx = tid; idx < d * d; idx += nt) {
         int j = idx / d, k = idx - j * d;
         L[idx] = (k <= j) ? A[j * lda + k] : 0.0;
@@ -146,7 +193,7 @@ extern "C" int ree_moments_chol(const double* sums, const double* shift, int d, 
     if (!sums || !mean || !cov || d < 1 || (L && !stats4))
         return ree_set_error(REE_E_BADARG, "ree_moments_chol: bad argument");
     if (d > REE_MAX_D) return ree_set_error(REE_E_UNSUPPORTED, "ree_moments_chol: d > 160 not supported");
-    size_t smem = ((size_t)d * (d + 1) + d + 4) * sizeof(double);
+    size_t smem = ((size_t)d * (d + 1) + 2 * d + 4) * sizeof(double);
     cudaFuncSetAttribute(k_moments_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_moments_chol<<<1, REE_LA_THREADS, smem, ree_stream(stream)>>>(sums, shift, d, ddof, weighted, mean, cov, L, Linv,
                                                                     stats4);
@@ -156,7 +203,7 @@ extern "C" int ree_moments_chol(const double* sums, const double* shift, int d, 
 extern "C" int ree_chol_scaled(const double* C, int d, double scale, double* L, double* stats4, void* stream) {
     if (!C || !L || d < 1) return ree_set_error(REE_E_BADARG, "ree_chol_scaled: bad argument");
     if (d > REE_MAX_D) return ree_set_error(REE_E_UNSUPPORTED, "ree_chol_scaled: d > 160 not supported");
-    size_t smem = ((size_t)d * (d + 1) + 4) * sizeof(double);
+    size_t smem = ((size_t)d * (d + 1) + d + 4) * sizeof(double);
     cudaFuncSetAttribute(k_chol_scaled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_chol_scaled<<<1, REE_LA_THREADS, smem, ree_stream(stream)>>>(C, d, scale, L, stats4);
     return ree_check_launch("ree_chol_scaled");
