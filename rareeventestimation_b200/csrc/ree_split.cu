@@ -785,13 +785,10 @@ static int launch_xf_ws_variants(const XfArgs& a, cudaStream_t st) {
     const int grid = (int)(want < sms ? want : sms);
     const int v = xf_variant();
     if ((a.d + 7) / 8 == NTB) {
+        // tuning hooks: 1 = four Philox chains per producer batch, 2 = two producers per consumer
+        // with setmaxnreg 120 / 56 (measured slower: the extra DFMA streams take pipe slots from the consumers)
         if (v == 1) return launch_xf_ws<NTB, NC, 1, true, 4, 0, 0>(a, grid, st);
-        if (v == 2) return launch_xf_ws<NTB, NC, 2, true, 4, 120, 56>(a, grid, st);
-        if (v == 3) return launch_xf_ws<NTB, NC, 2, true, 1, 128, 48>(a, grid, st);
-        if (v == 4) return launch_xf_ws<NTB, NC, 3, true, 1, 120, 40>(a, grid, st);
-        if (v == 5) return launch_xf_ws<NTB, NC, 1, true, 2, 168, 88>(a, grid, st);
-        if (v == 6) return launch_xf_ws<NTB, NC, 1, true, 4, 152, 104>(a, grid, st);
-        if (v == 7) return launch_xf_ws<NTB, NC, 2, true, 2, 120, 56>(a, grid, st);
+        if (v == 2) return launch_xf_ws<NTB, NC, 2, true, 2, 120, 56>(a, grid, st);
         return launch_xf_ws<NTB, NC, 1, true, 2, 0, 0>(a, grid, st);
     }
     return launch_xf_ws<NTB, NC, 1, false, 2, 0, 0>(a, grid, st);
@@ -826,16 +823,6 @@ static int launch_xf_bucket(const SplitCfg& c, const XfArgs& a, cudaStream_t st)
         }
     }
     if constexpr (TRI) {
-        if (MODE == 1 && (a.d + 7) / 8 == 13 && xf_variant() > 0) {  // tuning hook: warps x Philox batch
-            const int v = xf_variant();
-            const int nw = (v == 1 || v == 2) ? 12 : 16;
-            const int64_t want = (nwt + nw - 1) / nw;
-            const int grid = (int)(want < sms ? want : sms);
-            if (v == 1) return launch_xf<MODE, 13, 12, true, TRI, 2>(a, grid, st);
-            if (v == 2) return launch_xf<MODE, 13, 12, true, TRI, 4>(a, grid, st);
-            if (v == 3) return launch_xf<MODE, 13, 16, true, TRI, 1>(a, grid, st);
-            return launch_xf<MODE, 13, 16, true, TRI, 3>(a, grid, st);
-        }
         const int64_t want = (nwt + 15) / 16;
         return launch_xf_exact<MODE, 13, 16, TRI>(a, (int)(want < sms ? want : sms), st);
     } else {  // dense parity-mode factor: 86 KB of fragments, fewer warps
