@@ -32,6 +32,7 @@ struct PeerState {
     PeerBox* box[REE_PEER_MAX];     // every rank's mailbox as mapped into this process (box[rank] == local)
     unsigned long long seq;
     int* d_error;                   // device flag: a spin timed out
+    unsigned char handle[REE_PEER_MAX][64];  // IPC handles already mapped (a second process group reuses the mappings)
 };
 static PeerState g_peer[64];
 static bool g_peer_ready[64] = {false};
@@ -92,7 +93,15 @@ extern "C" int ree_peer_create(int rank, int world, unsigned char* handle_out) {
         if (err == cudaSuccess) err = cudaMemset(s.d_error, 0, sizeof(int));
         if (err == cudaSuccess) err = cudaDeviceSynchronize();  // the mailbox is zero before its handle leaves the process
         if (err != cudaSuccess) return ree_set_error((int)err, cudaGetErrorString(err));
+    } else {
+        // a new process group in the same process: empty the mailbox again (the handle exchange that follows is the
+        // barrier before any peer writes into it) and forget the old error
+        err = cudaMemset(s.local, 0, sizeof(PeerBox));
+        if (err == cudaSuccess) err = cudaMemset(s.d_error, 0, sizeof(int));
+        if (err == cudaSuccess) err = cudaDeviceSynchronize();
+        if (err != cudaSuccess) return ree_set_error((int)err, cudaGetErrorString(err));
     }
+    g_peer_ready[dev] = false;
     s.rank = rank; s.world = world; s.seq = 0;
     cudaIpcMemHandle_t h;
     err = cudaIpcGetMemHandle(&h, s.local);
@@ -113,12 +122,14 @@ extern "C" int ree_peer_connect(const unsigned char* handles) {
             s.box[r] = s.local;
             continue;
         }
+        if (s.box[r] && memcmp(s.handle[r], handles + 64 * (size_t)r, 64) == 0) continue;  // already mapped
         cudaIpcMemHandle_t h;
         memcpy(&h, handles + 64 * (size_t)r, 64);
         void* p = nullptr;
         err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
         if (err != cudaSuccess) return ree_set_error((int)err, cudaGetErrorString(err));
         s.box[r] = (PeerBox*)p;
+        memcpy(s.handle[r], handles + 64 * (size_t)r, 64);
     }
     g_peer_ready[dev] = true;
     return 0;
