@@ -171,6 +171,11 @@ class VMFNMixture(MixtureModel):
     def pdf(self, sample: np.ndarray) -> np.ndarray:
         return np.exp(self.logpdf(sample))
 
+    def predict(self, sample: np.ndarray) -> np.ndarray:
+        """Component every row belongs to (mixturemodel.py:226-239): with one component, component 0."""
+        assert self.fitted, "Fit vMFNM before accessing parameters!"
+        return np.zeros(np.asarray(sample).shape[0], dtype=np.int64)
+
 
 def vmfn_variates_numpy(rng, n: int, d: int, kappa: float, m: float, omega: float):
     """Parity mode (``CBREE(noise="numpy")``): consume ``rng`` exactly like ``vMFNM_sample`` does for one component
