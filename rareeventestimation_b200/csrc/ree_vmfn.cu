@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(VM_T) k_vmfn_sample(const VmSampleArgs a) {
                 if (t >= log(u)) break;
             }
         }
-        // direction in the orthogonal complement: pass 1 accumulates |v|^2 and hv . v, pass 2 regenerates and writes
+        // direction in the orthogonal complement: pass 1 accumulates |v|^2 and hv . v, pass 2 rescales and reflects
         double s2 = 0.0, sv = 0.0;
         const int npairs = (dm1 + 1) >> 1;
         for (int p = 0; p < npairs; ++p) {
@@ -167,8 +167,11 @@ __global__ void __launch_bounds__(VM_T) k_vmfn_sample(const VmSampleArgs a) {
                 z0 = a.v_in[(int64_t)(2 * p) * a.ld + i];
                 z1 = (2 * p + 1 < dm1) ? a.v_in[(int64_t)(2 * p + 1) * a.ld + i] : 0.0;
             } else {
+                // generated once: the raw normals are parked in the output rows and rescaled in place by pass 2
                 philox_normal_pair(a.seed, (uint64_t)(a.first + i), (uint32_t)p, a.draw, z0, z1);
                 if (2 * p + 1 >= dm1) z1 = 0.0;
+                a.x[(int64_t)(2 * p) * a.ld + i] = z0;
+                if (2 * p + 1 < dm1) a.x[(int64_t)(2 * p + 1) * a.ld + i] = z1;
             }
             s2 = fma(z0, z0, fma(z1, z1, s2));
             sv = fma(hv_s[2 * p], z0, sv);
@@ -183,7 +186,8 @@ __global__ void __launch_bounds__(VM_T) k_vmfn_sample(const VmSampleArgs a) {
                 z0 = a.v_in[(int64_t)(2 * p) * a.ld + i];
                 z1 = (2 * p + 1 < dm1) ? a.v_in[(int64_t)(2 * p + 1) * a.ld + i] : 0.0;
             } else {
-                philox_normal_pair(a.seed, (uint64_t)(a.first + i), (uint32_t)p, a.draw, z0, z1);
+                z0 = a.x[(int64_t)(2 * p) * a.ld + i];
+                z1 = (2 * p + 1 < dm1) ? a.x[(int64_t)(2 * p + 1) * a.ld + i] : 0.0;
             }
             a.x[(int64_t)(2 * p) * a.ld + i] = r * (scale * z0 - f * hv_s[2 * p]);
             if (2 * p + 1 < dm1) a.x[(int64_t)(2 * p + 1) * a.ld + i] = r * (scale * z1 - f * hv_s[2 * p + 1]);

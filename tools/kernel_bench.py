@@ -84,3 +84,24 @@ timeit("ree_cbree_step(inject)", lambda: eng.cbree_step(X, Y, 0.6, m_noise, F, l
 timeit("ree_philox_normal", lambda: eng.philox_normal(n, d, 3, 3, out=Z), n * 8 * d)
 timeit("ree_lsf_eval(affine)", lambda: eng.lsf_eval(lsf, X, out=X.g), n * (8 * d + 8))
 timeit("ree_energy", lambda: eng.energy(X, out=X.e), n * (8 * d + 8))
+# von Mises-Fisher-Nakagami model (resampling branch)
+from rareeventestimation_b200.mixture import VMFNMixture, _house  # noqa: E402
+
+Xs = eng.philox_normal(n, d, 5, 5)
+Xs.X.add_(1.0)  # a population away from the origin: a well-defined mean direction
+model = VMFNMixture(1)
+timeit("ree_vmfn_fit_sums", lambda: eng.vmfn_fit_sums(Xs), n * 16 * d)
+model.fit_device(eng, Xs)
+hv, hb = _house(model.mu[:, 0])
+hvd = eng.to_device(hv)
+kap, mm, om = model._scalars()
+timeit("ree_vmfn_sample(philox)", lambda: eng.vmfn_sample(Y, hvd, hb, kap, mm, om, 3, 4), n * 8 * d)
+eng.lsf_eval(lsf, Y, out=Y.g)
+eng.energy(Y, out=Y.e)
+mud = eng.to_device(np.ascontiguousarray(model.mu[:, 0]))
+timeit("ree_vmfn_logpdf(+IS statistics)", lambda: eng.vmfn_logpdf(Y, mud, kap, mm, om, model._c0(), is4=is4),
+       n * (8 * d + 16))
+timeit("ree_vector_range", lambda: eng.vector_range(X.g, n, d), n * 8)
+rng2 = eng.vector_range(X.e, n, d)
+timeit("ree_reduce_scaled(known shift)", lambda: eng.reduce_scaled(X.e, n, d, -0.3, out=ess4, range2=rng2), n * 8)
+timeit("ree_reduce_scaled(running shift)", lambda: eng.reduce_scaled(X.e, n, d, -0.3, out=ess4), n * 8)
