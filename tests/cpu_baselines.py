@@ -1,7 +1,7 @@
 """CPU timings of the oracle (the NumPy / SciPy restatement of the reference) for the BASELINE.json configurations other
 than the headline one, on bounded samples (PDE limit state at N=1e3, CMC at 1e5..1e6, SIS-aCS at N=1e4,
 CBREE oscillator); one JSON line per configuration.  Test / measurement infrastructure: imports oracle/.
-Usage: python tools/cpu_baselines.py > gpurun_out/cpu_baselines.jsonl"""
+Usage: python tests/cpu_baselines.py > gpurun_out/cpu_baselines.jsonl"""
 import json
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repo root
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import baselines_oracle as bo  # noqa: E402
 import cbree_oracle as co  # noqa: E402

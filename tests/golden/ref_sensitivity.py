@@ -1,13 +1,13 @@
 """Sensitivity of the REFERENCE's own diffusion trajectory (N=300, d=150, seeds 2/2) to a perturbation of the initial
 sample in the last bits: runs the live reference (build container only) twice and compares the caches.
-Usage: python tools/debug/ref_sensitivity.py [relative perturbation, default 1e-14]"""
+Usage: python tests/golden/ref_sensitivity.py [relative perturbation, default 1e-14]"""
 import os
 import sys
 from copy import deepcopy
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # tests/golden -> repo root
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import ref_loader  # noqa: E402
 

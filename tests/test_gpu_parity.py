@@ -400,7 +400,7 @@ def test_solve_diffusion_trace(ree):
     # redrawn as m_w + Z (U sqrt(S))^T from the SVD of the weighted covariance (Generator.multivariate_normal,
     # solver.py:667).  The signs LAPACK gives the columns of U flip under perturbations of 1e-8 -- the size the rounding
     # differences have grown to by cache 6 (x10 per iteration in the reference itself) -- and a flipped column is a
-    # different, equally distributed sample (tools/debug/trace_diff.py shows the flip).  Whether caches 7.. reproduce the
+    # different, equally distributed sample (tests/golden/ref_sensitivity.py shows the flip on the reference alone).  Whether caches 7.. reproduce the
     # golden run therefore depends on the last bits of the exp in the ESS sums, not on the algorithm.
     k = 7
     for key in ["sigma", "beta", "t_step", "sfp", "ess"]:
