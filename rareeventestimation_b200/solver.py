@@ -510,13 +510,20 @@ class CBREE(Solver):
         # the shift max(beta * l) of every evaluation follows from the range of l on this rank (ranks merge their tuples)
         rng2 = self._eng.vector_range(ell, cache._dev.n, cache._dev.d)
 
+        seen = {}  # hybr evaluates its starting point three times (fcn, fdjac1, first step): one sweep is enough
+
         def obj_fun(temperature):
-            return self._ess(cache, float(np.asarray(temperature).reshape(-1)[0]), out, ell, rng2) - self.ess_tgt * n_tot
+            b = float(np.asarray(temperature).reshape(-1)[0])
+            if b not in seen:
+                seen[b] = self._ess(cache, b, out, ell, rng2) - self.ess_tgt * n_tot
+            return seen[b]
 
         try:
             sol = root(obj_fun, cache.beta)
             new_beta = cache.beta if sol.x.item() <= 0 else sol.x.item()
             cache.beta = new_beta
+            if new_beta in seen:  # ESS(beta) of the accepted temperature is already known (solver.py:523)
+                cache._ess_known = (new_beta, cache.sigma, seen[new_beta] + self.ess_tgt * n_tot)
         except Exception as e:
             msg = f"Failed to update beta: {str(e)}"
             if self.verbose:
@@ -539,7 +546,11 @@ class CBREE(Solver):
             self._update_sigma_sfp(cache)
         if self.beta_adaptivity:
             self._update_beta(cache)
-        cache.ess = self._ess(cache, cache.beta)
+        known = getattr(cache, "_ess_known", None)
+        if known is not None and known[0] == cache.beta and known[1] == cache.sigma:
+            cache.ess = known[2]
+        else:
+            cache.ess = self._ess(cache, cache.beta)
 
     # ------------------------------------------------------------------ #
     # the step
