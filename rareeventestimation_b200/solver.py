@@ -759,7 +759,9 @@ class CBREE(Solver):
         self._setup(prob)
         dev = self._initial_ensemble(prob)
         if not self.save_history:  # the window's HBM buffers, allocated once and recycled by _retire
-            self._eng.reserve(dev.n, dev.d, int(min(self.observation_window, self.num_steps + 1)) + 1)
+            # window + the ensemble being produced + the trial step of the step-size controller: no cudaMalloc of an
+            # 8 GB ensemble inside the iteration loop (it showed up as a sporadic +50 ms in one of the first steps)
+            self._eng.reserve(dev.n, dev.d, int(min(self.observation_window, self.num_steps + 1)) + 2)
         cache = CBREECache(self._eng, dev, sigma=self.sigma, beta=self.beta, num_lsf_evals=self.lsf.counter)
         self._post_ensemble(cache)
         self._compute_weights_check(cache)
