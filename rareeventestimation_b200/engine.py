@@ -163,8 +163,29 @@ class Engine:
         eng = cls._instances.get(key)
         if eng is None:
             eng = cls._instances[key] = Engine(torch.device("cuda", key))
+            eng.comm = Comm(enabled=False)
+            eng._load_nvector_kernels()
         eng.comm = comm if comm is not None else Comm()
         return eng
+
+    def _load_nvector_kernels(self):
+        """CUDA loads a kernel at its first launch; the sigma / beta searches reach some reduction kernels only after
+        several iterations (the Brent search takes over from the closed-form sigma update around iteration 9), where
+        the load showed up as a sporadic +50 ms.  One launch of each on an 8-element vector at engine creation."""
+        with torch.cuda.device(self.device):
+            ens = self.alloc_ensemble(8, 1)
+            ens.g.fill_(0.5)
+            ens.e.fill_(1.0)
+            out = self.empty(4)
+            ell = self.logtgt(ens.g, ens.e, 8, 1.0, 0)
+            rng2 = self.vector_range(ell, 8, 1)
+            self.reduce_ess(ens, 1.0, 1.0, 0, out=out, a_out=self.empty(ens.ld))
+            self.reduce_scaled(ell, 8, 1, 0.5, out=out)
+            self.reduce_scaled(ell, 8, 1, 0.5, out=out, range2=rng2)
+            self.reduce_cvar(ens, 2.0, 1.0, 0, out=out)   # algebraic kernel (sigma grows)
+            self.reduce_cvar(ens, 1.0, 2.0, 0, out=out)   # generic kernel
+            self.count_failed(ens)
+            self.fetch(out)
 
     def __init__(self, device: torch.device):
         self.lib = _lib.load()
