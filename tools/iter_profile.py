@@ -18,12 +18,14 @@ ap.add_argument("--n", type=int, default=10_000_000)
 ap.add_argument("--d", type=int, default=100)
 ap.add_argument("--steps", type=int, default=8)
 ap.add_argument("--problem", default="linear", choices=["linear", "osc", "pde"])
+ap.add_argument("--resample", action="store_true", help="vMFNM resampling branch (resample=True, mixture_model='vMFNM')")
 args = ap.parse_args()
 eng = Engine.get()
 dev_ms, host_ms, calls = defaultdict(float), defaultdict(float), defaultdict(int)
 events = []
 for name in ["cbree_step", "cbree_moments", "cbree_maha", "reduce_ess", "reduce_cvar", "reduce_scaled", "logtgt", "moments_chol",
-             "chol_scaled", "ensemble_sums", "count_failed", "to_device", "alloc_ensemble", "empty", "lsf_eval", "energy"]:
+             "chol_scaled", "ensemble_sums", "count_failed", "to_device", "alloc_ensemble", "empty", "lsf_eval", "energy",
+             "vmfn_fit_sums", "vmfn_sample", "vmfn_logpdf", "vector_range"]:
     fn = getattr(eng, name)
 
     def wrap(fn=fn, name=name):
@@ -47,7 +49,8 @@ elif args.problem == "pde":
 else:
     prob = ree.make_linear_problem(args.d)
 prob.sample = DeviceSample(args.n, args.d, seed=0x5EED)
-solver = ree.CBREE(seed=1, convergence_check=False, divergence_check=False, quiet=True, num_steps=10**9)
+extra = dict(resample=True, mixture_model="vMFNM") if args.resample else {}
+solver = ree.CBREE(seed=1, convergence_check=False, divergence_check=False, quiet=True, num_steps=10**9, **extra)
 cl = solver.start(prob)
 for _ in range(3):
     solver.advance(cl)
