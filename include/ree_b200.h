@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define REE_ABI_VERSION 5
+#define REE_ABI_VERSION 6
 
 /* argument errors */
 #define REE_E_BADARG (-1)
@@ -242,10 +242,13 @@ int ree_vmfn_sample(double* x, int64_t n, int d, int64_t ld, const double* house
                     const double* r_in, const double* w_in, const double* v_in, void* stream);
 /* logq_i = kappa mu.x_i/|x_i| + c0 - m |x_i|^2/omega + (2m - d) log|x_i|  with c0 = the vMF and Nakagami constants
  * (mixturemodel.py:196-215).  is4 != NULL additionally returns the IS statistics of r = -e - logq with the indicator
- * g <= 0, exactly as ree_cbree_maha does (solver.py:683-686, 843-846).  mu is a DEVICE vector.                   */
+ * g <= 0, exactly as ree_cbree_maha does (solver.py:683-686, 843-846).  mu is a DEVICE vector.
+ * fuse_lsf != NULL (affine limit state of dimension d): g and e are OUTPUTS -- the kernel evaluates the limit state and
+ * the energy of the points it reads anyway (same arithmetic as ree_lsf_eval / ree_energy), as the redraw of the
+ * resampling branch needs g, e and log q of the same fresh ensemble (solver.py:663, 676-686).                     */
 int ree_vmfn_logpdf(const double* x, int64_t n, int d, int64_t ld, const double* mu, double kappa, double m, double omega,
-                    double c0, const double* g, const double* e, double* logq, double* workspace, double* is4,
-                    void* stream);
+                    double c0, double* g, double* e, double* logq, double* workspace, double* is4,
+                    const ree_lsf* fuse_lsf, void* stream);
 
 /* ---- secondary path: SIS with adaptive conditional sampling (sis/SIS_aCS.py:64-306) ------------------------ */
 /* mode 0: v_i = Phi(-g_i/sigma_new) / Phi(-g_i/sigma_old)  (sigma_old <= 0: denominator 1)   SIS_aCS.py:151-183

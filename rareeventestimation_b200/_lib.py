@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libree_b200.so")
 TGT_KINDS = {"algebraic": 0, "tanh": 1, "arctan": 2, "erf": 3, "relu": 4, "sigmoid": 5}
 LSF_EXTERNAL, LSF_AFFINE, LSF_CONVEX, LSF_FUJITA_RACKWITZ, LSF_OSCILLATOR, LSF_DIFFUSION = range(6)
 NOISE_INJECT, NOISE_PHILOX = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class ReeError(RuntimeError):
@@ -55,7 +55,7 @@ PROTOTYPES = {
     "ree_download_vector": (_INT, [_P, _P, _I64, _P]),
     "ree_vmfn_fit_sums": (_INT, [_P, _I64, _INT, _I64, _P, _P, _P, _P, _P]),
     "ree_vmfn_sample": (_INT, [_P, _I64, _INT, _I64, _P, _DBL, _DBL, _DBL, _DBL, _U64, _U64, _I64, _P, _P, _P, _P]),
-    "ree_vmfn_logpdf": (_INT, [_P, _I64, _INT, _I64, _P, _DBL, _DBL, _DBL, _DBL, _P, _P, _P, _P, _P, _P]),
+    "ree_vmfn_logpdf": (_INT, [_P, _I64, _INT, _I64, _P, _DBL, _DBL, _DBL, _DBL, _P, _P, _P, _P, _P, _LSFP, _P]),
     "ree_aos_to_soa": (_INT, [_P, _P, _I64, _INT, _I64, _P]),
     "ree_soa_to_aos": (_INT, [_P, _P, _I64, _INT, _I64, _P]),
     "ree_upload_ensemble": (_INT, [_P, _P, _I64, _INT, _I64, _P, _I64, _P]),

@@ -200,30 +200,51 @@ __global__ void __launch_bounds__(VM_T) k_vmfn_sample(const VmSampleArgs a) {
 // log-density + IS statistics
 // ---------------------------------------------------------------------------------------
 // logq_i = kappa mu.x/r + c0 - m r^2/omega + (2m - d) log r,   c0 = vMF constant + Nakagami constant (host)
+// FUSE: 0 g and e are inputs; 1 / 2: the kernel also evaluates the energy and the affine limit state of the points it
+// reads anyway (1: g = offset + coef . x, 2: g = offset - sum(x)/sqrt(d); same operation order as k_lsf_simple / k_energy)
+// and writes them to g / e -- the redraw of the resampling branch needs all three for the same fresh ensemble.
+template <int FUSE>
 __global__ void __launch_bounds__(VM_T) k_vmfn_logpdf(const double* __restrict__ x, int64_t n, int d, int64_t ld,
                                                       const double* __restrict__ mu, double kappa, double m,
-                                                      double omega, double c0, const double* __restrict__ g,
-                                                      const double* __restrict__ e, double* __restrict__ logq,
-                                                      double* __restrict__ small) {
-    extern __shared__ double mu_s[];
+                                                      double omega, double c0, double* __restrict__ g,
+                                                      double* __restrict__ e, double* __restrict__ logq,
+                                                      double* __restrict__ small, const double* __restrict__ coef,
+                                                      double offset) {
+    extern __shared__ double mu_s[];  // mu (d) | coef (d, FUSE == 1)
     __shared__ ExpSums sh[32];
-    for (int j = threadIdx.x; j < d; j += VM_T) mu_s[j] = mu[j];
+    for (int j = threadIdx.x; j < d; j += VM_T) {
+        mu_s[j] = mu[j];
+        if (FUSE == 1) mu_s[d + j] = coef[j];
+    }
     __syncthreads();
+    const double e_const = (double)d * REE_LOG_2PI;
     ExpSums acc = expsums_empty();
     const int64_t stride = (int64_t)gridDim.x * VM_T;
     for (int64_t i = (int64_t)blockIdx.x * VM_T + threadIdx.x; i < n; i += stride) {
-        double r2 = 0.0, dot = 0.0;
+        double r2 = 0.0, dot = 0.0, gs = 0.0;
         for (int j = 0; j < d; ++j) {
             const double v = x[(int64_t)j * ld + i];
             r2 = fma(v, v, r2);
             dot = fma(mu_s[j], v, dot);
+            if (FUSE == 1) gs = __dadd_rn(gs, __dmul_rn(mu_s[d + j], v));
+            if (FUSE == 2) gs = __dadd_rn(gs, v);
         }
         const double r = sqrt(r2);
         const double lq = kappa * (dot / r) + c0 - m * (r2 / omega) + (2.0 * m - (double)d) * log(r);
         if (logq) logq[i] = lq;
+        double gi, ei;
+        if (FUSE) {
+            gi = (FUSE == 1) ? __dadd_rn(gs, offset) : __dadd_rn(__ddiv_rn(-gs, __dsqrt_rn((double)d)), offset);
+            ei = 0.5 * (e_const + r2);
+            g[i] = gi;
+            e[i] = ei;
+        } else if (small) {
+            gi = g[i];
+            ei = e[i];
+        }
         if (small) {
-            const double rr = __dsub_rn(-e[i], lq);  // -e_fun - log_pdf  (solver.py:684)
-            if (isfinite(rr)) expsums_add(acc, rr, g[i] <= 0.0 ? 1.0 : 0.0);
+            const double rr = __dsub_rn(-ei, lq);  // -e_fun - log_pdf  (solver.py:684)
+            if (isfinite(rr)) expsums_add(acc, rr, gi <= 0.0 ? 1.0 : 0.0);
         }
     }
     if (small) {
@@ -281,14 +302,24 @@ extern "C" int ree_vmfn_sample(double* x, int64_t n, int d, int64_t ld, const do
 }
 
 extern "C" int ree_vmfn_logpdf(const double* x, int64_t n, int d, int64_t ld, const double* mu, double kappa, double m,
-                               double omega, double c0, const double* g, const double* e, double* logq,
-                               double* workspace, double* is4, void* stream) {
-    if (!x || !mu || d < 1 || n < 1 || ld < n || (is4 && (!g || !e || !workspace)) || (!is4 && !logq))
+                               double omega, double c0, double* g, double* e, double* logq, double* workspace,
+                               double* is4, const ree_lsf* fuse_lsf, void* stream) {
+    if (!x || !mu || d < 1 || n < 1 || ld < n || (is4 && (!g || !e || !workspace)) || (!is4 && !logq && !fuse_lsf))
         return ree_set_error(REE_E_BADARG, "ree_vmfn_logpdf: bad argument");
+    int fuse = 0;
+    if (fuse_lsf) {
+        if (fuse_lsf->kind == REE_LSF_AFFINE && fuse_lsf->d == d && g && e) fuse = fuse_lsf->coef ? 1 : 2;
+        else return ree_set_error(REE_E_UNSUPPORTED, "ree_vmfn_logpdf: only the affine limit state can be fused");
+    }
     cudaStream_t st = ree_stream(stream);
     const int ctas = vm_grid(n);
     double* small = is4 ? workspace + 8 : nullptr;
-    k_vmfn_logpdf<<<ctas, VM_T, (size_t)d * sizeof(double), st>>>(x, n, d, ld, mu, kappa, m, omega, c0, g, e, logq, small);
+    const size_t smem = (size_t)(fuse == 1 ? 2 * d : d) * sizeof(double);
+    const double* coef = fuse ? fuse_lsf->coef : nullptr;
+    const double off = fuse ? fuse_lsf->offset : 0.0;
+    if (fuse == 1) k_vmfn_logpdf<1><<<ctas, VM_T, smem, st>>>(x, n, d, ld, mu, kappa, m, omega, c0, g, e, logq, small, coef, off);
+    else if (fuse == 2) k_vmfn_logpdf<2><<<ctas, VM_T, smem, st>>>(x, n, d, ld, mu, kappa, m, omega, c0, g, e, logq, small, coef, off);
+    else k_vmfn_logpdf<0><<<ctas, VM_T, smem, st>>>(x, n, d, ld, mu, kappa, m, omega, c0, g, e, logq, small, coef, off);
     int rc = ree_check_launch("k_vmfn_logpdf");
     if (rc || !is4) return rc;
     return ree_mma_merge_small(small, ctas, is4, st);

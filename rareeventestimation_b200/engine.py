@@ -455,14 +455,19 @@ class Engine:
         return dst
 
     def vmfn_logpdf(self, ens: Ensemble, mu: torch.Tensor, kappa: float, m: float, omega: float, c0: float,
-                    logq: Optional[torch.Tensor] = None, is4: Optional[torch.Tensor] = None):
+                    logq: Optional[torch.Tensor] = None, is4: Optional[torch.Tensor] = None,
+                    fuse_lsf: Optional[DeviceLsf] = None):
+        """``fuse_lsf`` (affine): the kernel also writes ``ens.g`` and ``ens.e`` of the points it reads."""
         ws = self.workspace(ens.d)
+        s = fuse_lsf.struct() if fuse_lsf is not None else None
+        need_ge = is4 is not None or fuse_lsf is not None
         check(self.lib.ree_vmfn_logpdf(ens.X.data_ptr(), ens.n, ens.d, ens.ld, mu.data_ptr(), float(kappa), float(m),
                                        float(omega), float(c0),
-                                       ens.g.data_ptr() if is4 is not None else None,
-                                       ens.e.data_ptr() if is4 is not None else None,
+                                       ens.g.data_ptr() if need_ge else None,
+                                       ens.e.data_ptr() if need_ge else None,
                                        logq.data_ptr() if logq is not None else None, ws.data_ptr(),
-                                       is4.data_ptr() if is4 is not None else None, self.stream), "ree_vmfn_logpdf")
+                                       is4.data_ptr() if is4 is not None else None,
+                                       C.byref(s) if s is not None else None, self.stream), "ree_vmfn_logpdf")
         if is4 is not None:
             self.comm.combine_expsums_(is4)
 

@@ -132,10 +132,10 @@ class VMFNMixture(MixtureModel):
             raise ValueError("leading dimensions differ")
         return eng.vmfn_sample(dst, hv, b, kappa, m, om, 0, 0, r=rd, w=wd, v=vd)
 
-    def logpdf_device(self, eng: Engine, ens: Ensemble, logq=None, is4=None) -> None:
+    def logpdf_device(self, eng: Engine, ens: Ensemble, logq=None, is4=None, fuse_lsf=None) -> None:
         assert self.fitted, "Fit vMFNM before accessing parameters!"
         kappa, m, om = self._scalars()
-        eng.vmfn_logpdf(ens, self._mu_device(eng), kappa, m, om, self._c0(), logq=logq, is4=is4)
+        eng.vmfn_logpdf(ens, self._mu_device(eng), kappa, m, om, self._c0(), logq=logq, is4=is4, fuse_lsf=fuse_lsf)
 
     # ------------------------------------------------------------------ #
     # the reference's host-array interface

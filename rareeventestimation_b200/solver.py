@@ -386,6 +386,8 @@ class CBREE(Solver):
             eng.moments_chol(sums_u, shift_u, d, 1, False, mean, cov, L, Linv, stats)
             if model is None:
                 eng.cbree_maha(dev, mean, Linv, stats[0:1], cache.sigma, cache.beta, kind, None, None, is4)
+            elif getattr(model, "_is4_dev", None) is not None:  # already computed with g and e of the redraw
+                is4.copy_(model._is4_dev)
             else:  # the ensemble was drawn from the fitted vMFN model: its density replaces the Gaussian fit
                 model.logpdf_device(eng, dev, is4=is4)
             eng.moments_chol(sums_w, shift_u, d, 0, True, m_w, C_w)
@@ -400,7 +402,9 @@ class CBREE(Solver):
             sums_w = eng.empty(slen)
             eng.cbree_maha(dev, mean, Linv, stats[0:1], cache.sigma, cache.beta, kind, ess4[0:1], sums_w, is4)
             eng.moments_chol(sums_w, mean, d, 0, True, m_w, C_w)  # weighted sums are centred at the unweighted mean
-            if model is not None:  # IS statistics of the vMFN density instead of the Gaussian fit's
+            if model is not None and getattr(model, "_is4_dev", None) is not None:
+                is4.copy_(model._is4_dev)
+            elif model is not None:  # IS statistics of the vMFN density instead of the Gaussian fit's
                 model.logpdf_device(eng, dev, is4=is4)
         tails[0:2].copy_(sums_u[d + d * d:])
         tails[2:4].copy_(sums_w[d + d * d:])
@@ -625,6 +629,12 @@ class CBREE(Solver):
             self._step_draws += 1
             model.sample_device(eng, dev, self._philox_seed, _STREAM_RESAMPLE + self._step_draws)
         desc = self._lsf_descriptor(dev.d)
+        model._is4_dev = None
+        if desc is not None and desc.kind == _lib.LSF_AFFINE and self._device_energy:
+            # one pass over the fresh ensemble: limit state, energy, model density and the IS statistics
+            model._is4_dev = eng.empty(4)
+            model.logpdf_device(eng, dev, is4=model._is4_dev, fuse_lsf=desc)
+            return model
         if desc is not None:
             eng.lsf_eval(desc, dev, out=dev.g)
         if self._device_energy:
@@ -725,8 +735,10 @@ class CBREE(Solver):
             cache._host.pop("lsf_evals", None)
             self.lsf.counter += self._n_total
             cache.num_lsf_evals = self.lsf.counter
-            is4 = self._eng.empty(4)
-            cache.mixture_model.logpdf_device(self._eng, cache._dev, is4=is4)
+            is4 = cache.mixture_model._is4_dev
+            if is4 is None:
+                is4 = self._eng.empty(4)
+                cache.mixture_model.logpdf_device(self._eng, cache._dev, is4=is4)
             cache._is4 = self._eng.fetch(is4)
             cache._vmfn_density = True
         self._check_density(cache)
