@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--ref-n", type=int, default=100_000, help="particles of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-code-warmup", action="store_true",
+                    help="skip the small warm-up solve (profiling runs under ncu: its launches would fill the capture)")
     return ap.parse_args()
 
 
@@ -224,10 +226,11 @@ def run_b200(args):
     # Code warm-up on a small ensemble of the same dimension: 16 iterations touch every kernel and both sigma-update
     # branches (the closed-form one of the first iterations and the Brent search that takes over around iteration 9).
     # CUDA loads kernels lazily at their first launch; inside the timed steps that was a sporadic +50 ms.
-    warm = ree.make_linear_problem(d)
-    warm.sample = DeviceSample(8192 * world, d, seed=1)
-    ree.CBREE(num_steps=16, **kw).solve(warm)
-    del warm
+    if not args.no_code_warmup:
+        warm = ree.make_linear_problem(d)
+        warm.sample = DeviceSample(8192 * world, d, seed=1)
+        ree.CBREE(num_steps=16, **kw).solve(warm)
+        del warm
     prob = ree.make_linear_problem(d)
     prob.sample = DeviceSample(n_total, d, seed=0x5EED)
     solver = ree.CBREE(num_steps=10**9, **kw)

@@ -12,7 +12,7 @@ timeout 600 python bench.py > $OUT/bench_$TAG.log 2> $OUT/bench_$TAG.err; echo "
 timeout 300 python tools/iter_profile.py --n 10000000 > $OUT/iter_$TAG.log 2>&1; cat $OUT/iter_$TAG.log
 timeout 300 python tools/kernel_bench.py --n 4000000 > $OUT/kernels_$TAG.jsonl 2>&1; cat $OUT/kernels_$TAG.jsonl
 if [ "${2:-}" != "skip-ncu" ]; then
-  CMD="python bench.py --steps 2 --warmup 1 --n 2000000 --no-e2e --no-cpu"
+  CMD="python bench.py --steps 2 --warmup 1 --n 2000000 --no-e2e --no-cpu --no-code-warmup"
   $CMD > $OUT/plain_$TAG.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_list_$TAG.log 2>&1
   echo "ncu list rc=$?"
