@@ -4,7 +4,6 @@ Same constructor arguments and ``Solution`` layout as the reference.
 """
 from __future__ import annotations
 
-import ctypes as C
 import math
 import warnings
 
@@ -12,7 +11,6 @@ import numpy as np
 import torch
 from scipy import optimize
 
-from . import _lib
 from ._lib import check
 from .engine import Engine, Ensemble, _pad
 from .lsf import DeviceLSF

@@ -18,10 +18,10 @@ import numpy as np
 from scipy.optimize import minimize_scalar, root
 
 from . import _lib
-from .engine import Comm, DeviceLsf, Engine, Ensemble, cvar_from, ess_from
+from .engine import DeviceLsf, Engine, Ensemble, cvar_from, ess_from
 from .lsf import DeviceLSF
 from .mixture import MixtureModel, VMFNMixture, vmfn_variates_numpy
-from .problem import DeviceSample, NormalProblem, Problem, ShardedHostSample
+from .problem import DeviceSample, Problem, ShardedHostSample
 from .solution import Solution
 
 _log = logging.getLogger(__name__)
