@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define REE_ABI_VERSION 6
+#define REE_ABI_VERSION 7
 
 /* argument errors */
 #define REE_E_BADARG (-1)
@@ -154,6 +154,47 @@ int ree_vector_range(const double* v, int64_t n, double* workspace, double* out2
 int ree_merge_expsums(const double* parts, int nparts, double* out4, void* stream);
 /* out[0] = #{g_i <= 0} (as double)       replaces sum(lsf_evals <= 0), solver.py:534, 570, 709-712 */
 int ree_count_failed(const double* g, int64_t n, double* workspace, double* out1, void* stream);
+
+/* ---- sigma / beta adaptation in one persistent kernel ------------------------------------------------------------- */
+/* Replaces CBREE.__update_beta_and_sigma (solver.py:505-523): the bounded Brent search over sigma
+ * (scipy.optimize.minimize_scalar(method="Bounded"), solver.py:538-556; objective (cvar - cvar_tgt)^2 of the
+ * incremental weights, my_log_cvar utilities.py:76-102) and the MINPACK hybrd root find over beta
+ * (scipy.optimize.root, solver.py:591-605; objective ESS(beta) - ess_tgt N) run inside ONE cooperative kernel: the same
+ * scalar algorithms in the same arithmetic, every objective evaluation a grid-wide reduction over g / the log-target
+ * vector with the cross-rank merge of the 4-tuple (NVLink mailboxes, ree_peer_*) as the epilogue of the reduction.     */
+typedef struct ree_adapt {
+    int32_t tgt_kind;    /* enum ree_tgt_kind */
+    int32_t do_sigma;    /* 1: search sigma in [sigma, sigma_hi]; 0: keep sigma (closed-form / constant updates are the caller's) */
+    int32_t do_beta;     /* 1: root find starting at beta; 0: only the ESS of (sigma, beta) */
+    int32_t maxiter;     /* Brent: 500 (SciPy default) */
+    int32_t maxfev;      /* hybrd: 200 (n + 1) = 400 */
+    int32_t use_peers;   /* 1: merge every tuple over the connected peer mailboxes (all ranks launch the same call) */
+    double sigma;        /* current sigma = lower bound of the search = sigma_old of the incremental weights */
+    double sigma_hi;     /* sigma + lip_sigma log(1 / t_step), solver.py:549-552 */
+    double cvar_tgt;
+    double xatol;        /* Brent: 1e-5 */
+    double beta;         /* starting temperature */
+    double ess_tgt_n;    /* ess_tgt * N (global particle count) */
+    double xtol;         /* hybrd: 1.49012e-8 */
+    double factor;       /* hybrd: 100 */
+    double epsfcn;       /* hybrd: machine epsilon */
+} ree_adapt;
+/* g, e (e may be NULL): this rank's limit-state / energy values; ell: n doubles of scratch, on return the log-target
+ * vector for the new sigma; workspace as for the reductions.
+ * out16 (DEVICE): [0] sigma, [1] beta (a non-positive root keeps the old beta, solver.py:602-605), [2] ESS(sigma, beta),
+ *   [3] sigma status (0 found, 1 maxiter, 2 NaN, -1 a reduction had no finite entry = the exception path of
+ *   my_log_cvar, -2 not searched), [4] beta status (hybrd info 1..5, -1 empty reduction, -2 not searched),
+ *   [5] / [6] objective evaluations of the two searches, [7] grid-wide combinations, [8..11] the ESS tuple
+ *   [M, S1, S2, cnt], [12] / [13] hybrd's x and f(x), [14] / [15] max / min of ell on this rank.                      */
+int ree_cbree_adapt(const double* g, const double* e, int64_t n, const ree_adapt* p, double* ell, double* workspace,
+                    double* out16, void* stream);
+/* The scalar searches of ree_cbree_adapt as plain host routines over a C callback (same source, host build): SciPy's
+ * `_minimize_scalar_bounded` and MINPACK hybrd for one unknown.  flag / info as SciPy reports them.                   */
+typedef double (*ree_scalar_fn)(double x, void* user);
+int ree_scalar_brent(ree_scalar_fn f, void* user, double lo, double hi, double xatol, int maxiter, double* x_out,
+                     double* f_out, int* nfev, int* flag);
+int ree_scalar_hybr1(ree_scalar_fn f, void* user, double x0, double xtol, int maxfev, double factor, double epsfcn,
+                     double* x_out, double* f_out, int* nfev, int* info);
 
 /* ---- the CBREE step (sweep 1) ------------------------------------------------------------ */
 /* X'[.,i] = t*X[.,i] + m_noise + F z_i ; g' = lsf(X') (unless EXTERNAL) ; e' = energy(X') ;

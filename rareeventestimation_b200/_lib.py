@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libree_b200.so")
 TGT_KINDS = {"algebraic": 0, "tanh": 1, "arctan": 2, "erf": 3, "relu": 4, "sigmoid": 5}
 LSF_EXTERNAL, LSF_AFFINE, LSF_CONVEX, LSF_FUJITA_RACKWITZ, LSF_OSCILLATOR, LSF_DIFFUSION = range(6)
 NOISE_INJECT, NOISE_PHILOX = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class ReeError(RuntimeError):
@@ -36,6 +36,30 @@ class ReeLsf(C.Structure):
     ]
 
 
+class ReeAdapt(C.Structure):
+    """struct ree_adapt (include/ree_b200.h): the sigma / beta searches of one iteration."""
+
+    _fields_ = [
+        ("tgt_kind", C.c_int32),
+        ("do_sigma", C.c_int32),
+        ("do_beta", C.c_int32),
+        ("maxiter", C.c_int32),
+        ("maxfev", C.c_int32),
+        ("use_peers", C.c_int32),
+        ("sigma", C.c_double),
+        ("sigma_hi", C.c_double),
+        ("cvar_tgt", C.c_double),
+        ("xatol", C.c_double),
+        ("beta", C.c_double),
+        ("ess_tgt_n", C.c_double),
+        ("xtol", C.c_double),
+        ("factor", C.c_double),
+        ("epsfcn", C.c_double),
+    ]
+
+
+SCALAR_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _U64 = C.c_uint64
@@ -56,6 +80,9 @@ PROTOTYPES = {
     "ree_vmfn_fit_sums": (_INT, [_P, _I64, _INT, _I64, _P, _P, _P, _P, _P]),
     "ree_vmfn_sample": (_INT, [_P, _I64, _INT, _I64, _P, _DBL, _DBL, _DBL, _DBL, _U64, _U64, _I64, _P, _P, _P, _P]),
     "ree_vmfn_logpdf": (_INT, [_P, _I64, _INT, _I64, _P, _DBL, _DBL, _DBL, _DBL, _P, _P, _P, _P, _P, _LSFP, _P]),
+    "ree_cbree_adapt": (_INT, [_P, _P, _I64, C.POINTER(ReeAdapt), _P, _P, _P, _P]),
+    "ree_scalar_brent": (_INT, [SCALAR_FN, _P, _DBL, _DBL, _DBL, _INT, _P, _P, _P, _P]),
+    "ree_scalar_hybr1": (_INT, [SCALAR_FN, _P, _DBL, _DBL, _INT, _DBL, _DBL, _P, _P, _P, _P]),
     "ree_aos_to_soa": (_INT, [_P, _P, _I64, _INT, _I64, _P]),
     "ree_soa_to_aos": (_INT, [_P, _P, _I64, _INT, _I64, _P]),
     "ree_upload_ensemble": (_INT, [_P, _P, _I64, _INT, _I64, _P, _I64, _P]),

@@ -13,65 +13,36 @@
 // same order (the host control flow is identical on all ranks), so `seq` is a plain per-process counter.
 #include <string.h>
 
-#include "common.cuh"
-
-#define REE_PEER_MAX 16
-
-struct PeerSlot {  // 64 bytes
-    double v[4];
-    unsigned long long seq;
-    unsigned long long pad[3];
-};
-struct PeerBox {
-    PeerSlot slot[2][REE_PEER_MAX];
-};
+#include "peer.cuh"
 
 struct PeerState {
     int rank, world;
     PeerBox* local;                 // this rank's mailbox (cudaMalloc)
     PeerBox* box[REE_PEER_MAX];     // every rank's mailbox as mapped into this process (box[rank] == local)
-    unsigned long long seq;
     int* d_error;                   // device flag: a spin timed out
     unsigned char handle[REE_PEER_MAX][64];  // IPC handles already mapped (a second process group reuses the mappings)
+    PeerArgs args;
 };
 static PeerState g_peer[64];
 static bool g_peer_ready[64] = {false};
 
-struct PeerArgs {
-    PeerBox* box[REE_PEER_MAX];
-    int rank, world;
-    unsigned long long seq;
-    int* error;
-};
+const PeerArgs* ree_peer_args_current() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_peer_ready[dev]) return nullptr;
+    return &g_peer[dev].args;
+}
 
+// The exchange counter lives in the owner's mailbox (device memory): the persistent sigma / beta search performs a
+// data-dependent number of exchanges inside one kernel, so the host cannot number them.
 __global__ void __launch_bounds__(32) k_peer_exchange(double* out4, const PeerArgs a) {
     __shared__ double t[REE_PEER_MAX][4];
-    const int r = threadIdx.x;
-    const int par = (int)(a.seq & 1ull);
-    if (r < a.world) {
-        volatile PeerSlot* dst = &a.box[r]->slot[par][a.rank];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dst->v[k] = out4[k];
-        __threadfence_system();
-        dst->seq = a.seq;
-        __threadfence_system();
-        volatile PeerSlot* src = &a.box[a.rank]->slot[par][r];
-        unsigned long long spins = 0;
-        while (src->seq != a.seq) {
-            if (++spins > (1ull << 28)) {  // ~ seconds: a peer died or the call order diverged
-                *a.error = 1;
-                break;
-            }
-        }
-        __threadfence_system();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) t[r][k] = src->v[k];
-    }
-    __syncwarp();
-    if (r == 0) {
-        ExpSums acc{t[0][0], t[0][1], t[0][2], t[0][3]};
-        for (int q = 1; q < a.world; ++q) acc = expsums_merge(acc, ExpSums{t[q][0], t[q][1], t[q][2], t[q][3]});
+    PeerBox* own = a.box[a.rank];
+    const unsigned long long seq = own->seq + 1;
+    const ExpSums mine{out4[0], out4[1], out4[2], out4[3]};
+    const ExpSums acc = peer_exchange_warp(a, seq, mine, t);
+    if (threadIdx.x == 0) {
         out4[0] = acc.m; out4[1] = acc.s1; out4[2] = acc.s2; out4[3] = acc.cnt;
+        own->seq = seq;
     }
 }
 
@@ -102,7 +73,7 @@ extern "C" int ree_peer_create(int rank, int world, unsigned char* handle_out) {
         if (err != cudaSuccess) return ree_set_error((int)err, cudaGetErrorString(err));
     }
     g_peer_ready[dev] = false;
-    s.rank = rank; s.world = world; s.seq = 0;
+    s.rank = rank; s.world = world;
     cudaIpcMemHandle_t h;
     err = cudaIpcGetMemHandle(&h, s.local);
     if (err != cudaSuccess) return ree_set_error((int)err, cudaGetErrorString(err));
@@ -131,6 +102,9 @@ extern "C" int ree_peer_connect(const unsigned char* handles) {
         s.box[r] = (PeerBox*)p;
         memcpy(s.handle[r], handles + 64 * (size_t)r, 64);
     }
+    memset(&s.args, 0, sizeof(s.args));
+    for (int r = 0; r < s.world; ++r) s.args.box[r] = s.box[r];
+    s.args.rank = s.rank; s.args.world = s.world; s.args.error = s.d_error;
     g_peer_ready[dev] = true;
     return 0;
 }
@@ -146,11 +120,7 @@ extern "C" int ree_peer_combine_expsums(double* out4, void* stream) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_peer_ready[dev] || !out4)
         return ree_set_error(REE_E_BADARG, "ree_peer_combine_expsums: peers are not connected");
-    PeerState& s = g_peer[dev];
-    PeerArgs a{};
-    for (int r = 0; r < s.world; ++r) a.box[r] = s.box[r];
-    a.rank = s.rank; a.world = s.world; a.seq = ++s.seq; a.error = s.d_error;
-    k_peer_exchange<<<1, 32, 0, ree_stream(stream)>>>(out4, a);
+    k_peer_exchange<<<1, 32, 0, ree_stream(stream)>>>(out4, g_peer[dev].args);
     return ree_check_launch("ree_peer_combine_expsums");
 }
 

@@ -185,6 +185,8 @@ class Engine:
             self.reduce_cvar(ens, 2.0, 1.0, 0, out=out)   # algebraic kernel (sigma grows)
             self.reduce_cvar(ens, 1.0, 2.0, 0, out=out)   # generic kernel
             self.count_failed(ens)
+            self.adapt(ens, 0, 1.0, 1.5, 2.0, 1.0, True, 4.0)  # persistent search kernel, algebraic objective
+            self.adapt(ens, 2, 1.0, 1.5, 2.0, 1.0, True, 4.0)  # ... generic objective
             self.fetch(out)
 
     def __init__(self, device: torch.device):
@@ -369,6 +371,32 @@ class Engine:
                                          range2.data_ptr() if range2 is not None else None, ws.data_ptr(),
                                          out.data_ptr(), self.stream), "ree_reduce_scaled")
         return self.comm.combine_expsums_(out)
+
+    def peers_connected(self) -> bool:
+        """True if cross-rank merges can run inside kernels (single rank, or NVLink mailboxes connected)."""
+        comm = self.comm
+        if not comm.enabled:
+            return True
+        if comm.peer is None:
+            comm.peer = comm._connect_peers(self.device)
+        return bool(comm.peer)
+
+    def adapt(self, ens: Ensemble, tgt_kind: int, sigma: float, sigma_hi: Optional[float], cvar_tgt: float, beta: float,
+              do_beta: bool, ess_tgt_n: float) -> np.ndarray:
+        """sigma / beta searches of one iteration in one persistent kernel (``ree_cbree_adapt``): bounded Brent over
+        sigma in [sigma, sigma_hi] (skipped if ``sigma_hi`` is None), then the hybrd root find over beta (or only the ESS
+        of (sigma, beta)).  Returns the 16 result doubles on the host; needs :meth:`peers_connected`."""
+        p = _lib.ReeAdapt(tgt_kind, 1 if sigma_hi is not None else 0, 1 if do_beta else 0, 500, 400,
+                          1 if self.comm.enabled else 0, float(sigma),
+                          float(sigma_hi) if sigma_hi is not None else float(sigma), float(cvar_tgt), 1e-5, float(beta),
+                          float(ess_tgt_n), 1.49012e-08, 100.0, float(np.finfo(np.float64).eps))
+        ell = self.scratch("ell", ens.ld)
+        out = self.scratch("adapt_out", 16)
+        ws = self.workspace(ens.d)
+        check(self.lib.ree_cbree_adapt(ens.g.data_ptr(), ens.e.data_ptr() if ens.e is not None else None, ens.n,
+                                       C.byref(p), ell.data_ptr(), ws.data_ptr(), out.data_ptr(), self.stream),
+              "ree_cbree_adapt")
+        return self.fetch(out, 16)
 
     def vector_range(self, v: torch.Tensor, n: int, d: int) -> torch.Tensor:
         """Device [max, min] over the finite entries of this rank's part of an N-vector."""

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import logging
 import math
+import os
 import warnings
 from copy import deepcopy
 from numbers import Real
@@ -236,13 +237,16 @@ class CBREE(Solver):
 
     noise: "philox" (device Philox4x32-10 counters, seeded by ``seed``) or "numpy" (draw Z on the host
            from ``self.rng`` exactly like ``rng.multivariate_normal`` does, then inject -- parity mode).
+    search: "device" (the sigma / beta searches run inside one persistent kernel per iteration, ``ree_cbree_adapt``:
+           SciPy's bounded Brent and MINPACK's hybrd in the same arithmetic) or "scipy" (the reference's host
+           optimisers drive one device reduction per objective evaluation -- kept as the cross-check).
     """
 
     def __init__(self, stepsize_tolerance=0.5, t_step=-1, num_steps=100, tgt_fun="algebraic", observation_window=5,
                  seed=None, sigma_adaptivity="cvar", beta_adaptivity=True, cvar_tgt=2, sfp_tgt=1 / 3, ess_tgt=1 / 2,
                  lip_sigma=1, divergence_check=True, convergence_check=True, mixture_model="GM", resample=False,
                  verbose=False, save_history=False, return_other=False, return_caches=False, name=None,
-                 callback=None, *, noise="philox", quiet=False) -> None:
+                 callback=None, *, noise="philox", search=None, quiet=False) -> None:
         super().__init__()
         if t_step > 0:
             self.stepsize_adaptivity = False
@@ -291,6 +295,10 @@ class CBREE(Solver):
         self.callback = callback
         assert noise in ("philox", "numpy")
         self.noise = noise
+        if search is None:
+            search = os.environ.get("REE_SEARCH", "device")
+        assert search in ("device", "scipy")
+        self.search = search
 
     def __str__(self) -> str:
         return self.name if self.name is not None else "CBREE"
@@ -542,8 +550,54 @@ class CBREE(Solver):
         return self._eng.logtgt(dev.g, dev.e, dev.n, cache.sigma, self._tgt_kind(),
                                 out=self._eng.scratch("ell", dev.ld))
 
+    def _update_beta_and_sigma_device(self, cache: CBREECache) -> None:
+        """solver.py:505-523 with both searches inside one kernel (``ree_cbree_adapt``): one launch and one readback
+        per iteration instead of ~25 host-driven objective evaluations.  Outcomes, messages and failure paths are those
+        of :meth:`_update_sigma_cvar` / :meth:`_update_beta`."""
+        eng, dev = self._eng, cache._dev
+        sigma_hi = None
+        if self.sigma_adaptivity == "cvar":
+            try:
+                if self._sfp_now(cache) < self.sfp_tgt:
+                    self._update_sigma_sfp(cache)
+                else:
+                    sigma_hi = cache.sigma + self.lip_sigma * np.log(1 / cache.t_step)
+                    if not (math.isfinite(cache.sigma) and math.isfinite(sigma_hi)):
+                        raise ValueError("Optimization bounds must be finite scalars.")
+                    if cache.sigma > sigma_hi:
+                        raise ValueError("The lower bound exceeds the upper bound.")
+            except Exception as e:
+                sigma_hi = None
+                self._note_failure(cache, f"Failed to update sigma: {str(e)}")
+        if self.sigma_adaptivity == "sfp":
+            self._update_sigma_sfp(cache)
+        out = eng.adapt(dev, self._tgt_kind(), cache.sigma, sigma_hi, self.cvar_tgt, cache.beta,
+                        bool(self.beta_adaptivity), self.ess_tgt * cache._n_total)
+        cache._search = (int(out[5]), int(out[6]), int(out[3]), int(out[4]))  # evaluations and exit codes
+        if sigma_hi is not None:
+            if out[3] == -1:  # my_log_cvar on a vector without finite entries (utilities.py:92)
+                self._note_failure(cache, "Failed to update sigma: zero-size array to reduction operation maximum "
+                                          "which has no identity")
+            else:
+                cache.sigma = float(out[0])
+        if self.beta_adaptivity and out[4] == -1:  # my_softmax on a vector without finite entries (utilities.py:121)
+            self._note_failure(cache, "Failed to update beta: attempt to get argmax of an empty sequence")
+        elif self.beta_adaptivity:
+            cache.beta = float(out[1])
+        if not out[11] > 0:
+            raise ValueError("attempt to get argmax of an empty sequence")
+        cache.ess = float(out[2])
+
+    def _note_failure(self, cache: CBREECache, msg: str) -> None:
+        if self.verbose:
+            cache.msg += msg
+        else:
+            _log.info(f"Iteration {cache.iteration}: {msg}")
+
     def _update_beta_and_sigma(self, cache: CBREECache) -> None:
         """solver.py:505-523."""
+        if self.search == "device" and self._eng.peers_connected():
+            return self._update_beta_and_sigma_device(cache)
         if self.sigma_adaptivity == "cvar":
             self._update_sigma_cvar(cache)
         if self.sigma_adaptivity == "sfp":

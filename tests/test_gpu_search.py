@@ -1,0 +1,163 @@
+"""The persistent sigma / beta search kernel (``ree_cbree_adapt``) against the SciPy-driven host path.
+
+The reference adapts sigma with scipy's bounded Brent search (solver.py:538-556) and beta with MINPACK's hybrd
+(solver.py:591-605).  ``CBREE(search="scipy")`` drives exactly those SciPy routines over one device reduction per
+objective evaluation; ``search="device"`` (the default) runs the same algorithms inside one kernel.  Both see the same
+particles, so sigma, beta and the ESS must agree to 1e-12 (the reductions differ in summation order only) and the whole
+free-running trajectories to 1e-10."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cbree_oracle as co
+import lsf_oracle as lo
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ree():
+    import rareeventestimation_b200 as r
+
+    return r
+
+
+@pytest.fixture(scope="module")
+def eng(ree):
+    from rareeventestimation_b200.engine import Engine
+
+    return Engine.get()
+
+
+def _cache(ree, eng, X, g, e, sigma, beta, t_step):
+    import torch
+    from rareeventestimation_b200.solver import CBREECache
+
+    ens = eng.upload(X)
+    ens.g[: len(g)].copy_(torch.from_numpy(np.ascontiguousarray(g)))
+    ens.e[: len(e)].copy_(torch.from_numpy(np.ascontiguousarray(e)))
+    c = CBREECache(eng, ens, sigma=sigma, beta=beta, t_step=t_step)
+    c._n_total = float(len(g))
+    c.num_failed = float(np.sum(g <= 0))
+    return c
+
+
+def _solver(ree, eng, search, **kw):
+    s = ree.CBREE(quiet=True, search=search, **kw)
+    s._eng = eng
+    return s
+
+
+CASES = [  # (n, d, shift of g, sigma, beta, t_step, tgt_fun)
+    (2000, 4, 0.5, 0.0, 1.0, 0.9, "algebraic"),
+    (2000, 4, 0.5, 3.0, 0.3, 0.5, "algebraic"),
+    (100_003, 10, 1.5, 12.0, 0.05, 0.7, "algebraic"),
+    (300_000, 3, 0.2, 150.0, 0.8, 0.95, "algebraic"),
+    (5000, 6, 1.0, 1.0, 1.0, 0.6, "arctan"),
+    (5000, 6, 1.0, 2.0, 0.4, 0.6, "erf"),
+    (5000, 6, 0.3, 0.5, 1.0, 0.6, "sigmoid"),
+    (5000, 6, 0.3, 0.7, 1.0, 0.6, "relu"),
+    (7, 2, 0.0, 1.0, 1.0, 0.5, "algebraic"),
+]
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_device_search_equals_scipy_search(ree, eng, case):
+    n, d, shift, sigma, beta, t_step, tgt = CASES[case]
+    rng = np.random.default_rng(case)
+    X = rng.standard_normal((n, d)) * 1.2
+    g = lo.lsf_affine(X) * 0.4 + shift - 1.0
+    e = co.energy_fast(X)
+    res = {}
+    for search in ("scipy", "device"):
+        c = _cache(ree, eng, X, g, e, sigma, beta, t_step)
+        s = _solver(ree, eng, search, tgt_fun=tgt, sfp_tgt=0.0)  # sfp_tgt 0: always the Brent branch
+        s._update_beta_and_sigma(c)
+        res[search] = (c.sigma, c.beta, c.ess)
+        if search == "device":
+            nfev_sigma, nfev_beta, st_sigma, st_beta = c._search
+            assert st_sigma == 0 and st_beta >= 1
+            assert nfev_sigma >= 3 and nfev_beta >= 3
+    for a, b, what in zip(res["device"], res["scipy"], ("sigma", "beta", "ess")):
+        assert a == pytest.approx(b, rel=1e-12, abs=1e-300), (what, res)
+
+
+def test_device_search_constant_beta_and_sfp_sigma(ree, eng):
+    """do_sigma = 0 / do_beta = 0 variants: closed-form sigma (solver.py:564-580), fixed temperature."""
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((4000, 5))
+    g = lo.lsf_affine(X) + 1.0
+    e = co.energy_fast(X)
+    for kw in (dict(sigma_adaptivity="sfp"), dict(beta_adaptivity=2.0), dict(sigma_adaptivity=3.0),
+               dict(sigma_adaptivity=3.0, beta_adaptivity=0.5)):
+        res = {}
+        for search in ("scipy", "device"):
+            s = _solver(ree, eng, search, **kw)
+            c = _cache(ree, eng, X, g, e, s.sigma if s.sigma else 0.7, s.beta, 0.8)
+            s._update_beta_and_sigma(c)
+            res[search] = (c.sigma, c.beta, c.ess)
+        for a, b in zip(res["device"], res["scipy"]):
+            assert a == pytest.approx(b, rel=1e-12), (kw, res)
+
+
+def test_device_search_failure_paths(ree, eng):
+    """No finite entry: the reference's my_log_cvar / my_softmax raise inside the objectives; the searches keep sigma
+    and beta and the final ESS raises (solver.py:523)."""
+    n = 1000
+    X = np.zeros((n, 2))
+    g = np.full(n, np.nan)
+    e = np.zeros(n)
+    for search in ("scipy", "device"):
+        c = _cache(ree, eng, X, g, e, 1.0, 0.5, 0.8)
+        c.num_failed = float(n)  # force the Brent branch
+        s = _solver(ree, eng, search)
+        with pytest.raises(ValueError, match="empty sequence"):
+            s._update_beta_and_sigma(c)
+        assert c.sigma == 1.0 and c.beta == 0.5
+
+
+def test_device_search_is_deterministic_and_rearms(ree, eng):
+    """The control words of the persistent kernel are rearmed by the last CTA: back-to-back launches give identical
+    bits, and the one-shot reductions that share the workspace still work in between."""
+    rng = np.random.default_rng(11)
+    n = 250_000
+    X = rng.standard_normal((n, 3))
+    g = lo.lsf_affine(X) + 0.8
+    e = co.energy_fast(X)
+    c = _cache(ree, eng, X, g, e, 2.0, 0.2, 0.7)
+    outs = []
+    for _ in range(4):
+        outs.append(eng.adapt(c._dev, 0, 2.0, 2.0 + 0.36, 2.0, 0.2, True, 0.5 * n).copy())
+        t4 = eng.fetch(eng.reduce_ess(c._dev, 2.0, 0.2, 0))
+        assert t4[3] == n
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o, outs[0])
+    assert outs[0][7] == outs[0][5] + outs[0][6] + 1  # one grid combination per evaluation + the range of ell
+
+
+GOLDEN_RUNS = ["cbree_readme_d4", "cbree_osc_d6", "cbree_d4_sfp", "cbree_d4_erf_beta2", "cbree_linear_d2"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_RUNS)
+def test_whole_solves_agree_between_searches(ree, name):
+    from test_gpu_parity import golden_problem
+
+    t = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg = json.loads(str(t["config"]))
+    prob = golden_problem(ree, cfg)
+    traj = {}
+    for search in ("scipy", "device"):
+        solver = ree.CBREE(seed=cfg["solver_seed"], save_history=True, return_caches=True, noise="numpy", quiet=True,
+                           search=search, **cfg["opts"])
+        sol = solver.solve(prob)
+        caches = sol.other["cache_list"]
+        traj[search] = {k: np.array([getattr(c, k) for c in caches], dtype=np.float64)
+                        for k in ["sigma", "beta", "t_step", "cvar_is_weights", "ess", "estimate"]}
+        traj[search]["msg"] = sol.msg
+    assert traj["device"]["msg"] == traj["scipy"]["msg"] == str(t["msg"])
+    for k in ["sigma", "beta", "t_step", "cvar_is_weights", "ess", "estimate"]:
+        np.testing.assert_allclose(traj["device"][k], traj["scipy"][k], rtol=1e-10, atol=1e-300, err_msg=k)
+        np.testing.assert_allclose(traj["device"][k], t[k], rtol=1e-6, atol=1e-300, err_msg=k)
