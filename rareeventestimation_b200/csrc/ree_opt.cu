@@ -384,14 +384,14 @@ __global__ void __launch_bounds__(OPT_THREADS, 2) k_adapt(const AdaptArgs A) {
             const ExpSums blk = ess_partial(A, x, hi, lo, T, sh);
             const ExpSums t = grid_combine(A, blk, MERGE_PLAIN, true, k, seq_base, xk, sh);
             if (lead) {
+                if (nev == 0) t_first = t_acc = t;
                 if (!(t.cnt > 0.0)) {
                     sh.more = -1;
                 } else {
                     const int phase = hy.phase;
                     const double ess = t.s1 * t.s1 / t.s2;
                     const bool m = hy.tell(ess - A.p.ess_tgt_n);
-                    if (phase == ree_opt::Hybr1::P_INIT) t_first = t_acc = t;
-                    else if (phase == ree_opt::Hybr1::P_STEP && hy.x == x) t_acc = t;  // the trial point was accepted
+                    if (phase == ree_opt::Hybr1::P_STEP && hy.x == x) t_acc = t;  // the trial point was accepted
                     sh.more = m ? 1 : 0;
                     sh.x = hy.x_eval;
                 }

@@ -25,7 +25,7 @@ dev_ms, host_ms, calls = defaultdict(float), defaultdict(float), defaultdict(int
 events = []
 for name in ["cbree_step", "cbree_moments", "cbree_maha", "reduce_ess", "reduce_cvar", "reduce_scaled", "logtgt", "moments_chol",
              "chol_scaled", "ensemble_sums", "count_failed", "to_device", "alloc_ensemble", "empty", "lsf_eval", "energy",
-             "vmfn_fit_sums", "vmfn_sample", "vmfn_logpdf", "vector_range", "adapt", "fetch"]:
+             "vmfn_fit_sums", "vmfn_sample", "vmfn_logpdf", "vector_range", "adapt"]:
     fn = getattr(eng, name)
 
     def wrap(fn=fn, name=name):
