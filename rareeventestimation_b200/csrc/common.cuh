@@ -94,7 +94,7 @@ __device__ __forceinline__ ExpSums expsums_merge(const ExpSums& a, const ExpSums
         r.s1 = 0.0;
         r.s2 = 0.0;
     } else {
-        double fa = exp(a.m - r.m), fb = exp(b.m - r.m);
+        double fa = (a.m == r.m) ? 1.0 : exp(a.m - r.m), fb = (b.m == r.m) ? 1.0 : exp(b.m - r.m);  // exp(0) = 1: same bits
         r.s1 = a.s1 * fa + b.s1 * fb;
         r.s2 = a.s2 * fa * fa + b.s2 * fb * fb;
     }

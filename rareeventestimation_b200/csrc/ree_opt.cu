@@ -14,13 +14,14 @@
 // and writes sigma, beta, ESS and the search diagnostics.  g / ell are re-read ~25 times: 80 MB at N = 1e7, i.e. largely
 // from L2 (126 MB).  This translation unit is compiled with -fmad=false: the scalar searches must not be contracted.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "nvec_stream.cuh"
 #include "peer.cuh"
 #include "scalar_opt.cuh"
 
 #define REE_WS_HEADER 8
-#define OPT_THREADS 512
+#define OPT_THREADS 1024
 
 struct AdaptArgs {
     const double* g;
@@ -30,29 +31,41 @@ struct AdaptArgs {
     double* ws;
     double* out;
     ree_adapt p;
-    PeerArgs peer;
-    int has_peer;
+    PeerArgs peer;  // world == 1: a mailbox of this device alone (the publication path is the same)
 };
 
 enum { MERGE_PLAIN = 0, MERGE_EXPS = 1, MERGE_RANGE = 2 };
 
 struct OptShared {
     ExpSums es[32];
-    double red[32];
+    double red[3 * 32];
     double tab[64];
     double xch[REE_PEER_MAX][4];
-    double x;
+    double x, y;
     int more;
     int last;
 };
 
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned int atom_add_acq_rel_u32(unsigned int* p, unsigned int v) {
+    unsigned int old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_f64(double* p, double v) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
 __device__ __forceinline__ double block_max(double v, double* smem) {
@@ -70,54 +83,79 @@ __device__ __forceinline__ double block_max(double v, double* smem) {
     return m;
 }
 
-// Grid-wide combination of per-CTA partial tuples: the last CTA to arrive merges them in fixed order (run-to-run and
-// rank-to-rank identical bits), optionally exchanges the result with the other ranks, and publishes it; every CTA's
-// thread 0 returns the global tuple.  `k` counts the combinations of this launch (identical in all CTAs).
-//   ws header (unsigned words): [0] ticket of the one-shot reduction kernels, [2] arrivals, [4] published k, [6] exits
-__device__ __forceinline__ ExpSums grid_combine(const AdaptArgs& A, const ExpSums& blk, int mode, bool exchange, int& k,
-                                                unsigned long long seq_base, unsigned long long& xk, OptShared& sh) {
+// three plain sums in one pass (two CTA barriers instead of six); results valid in thread 0; fixed tree
+__device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double* smem /* >= 96 */) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    c = warp_sum(c);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) {
+        smem[warp] = a;
+        smem[32 + warp] = b;
+        smem[64 + warp] = c;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        a = warp_sum(lane < nw ? smem[lane] : 0.0);
+        b = warp_sum(lane < nw ? smem[32 + lane] : 0.0);
+        c = warp_sum(lane < nw ? smem[64 + lane] : 0.0);
+    }
+    __syncthreads();
+}
+
+// Grid-wide (and cross-rank) combination of per-CTA partial tuples -- the epilogue of every objective reduction.
+//   1. thread 0 of every CTA stores its partial and arrives (one acq_rel atomic, no fences);
+//   2. the last CTA to arrive merges the partials in fixed order and PUBLISHES the rank's tuple with a sequence number
+//      into slot [seq & 1][rank] of every rank's mailbox (NVLink stores; with one rank: this device's own mailbox);
+//   3. warp 0 of EVERY CTA polls its own rank's mailbox until all ranks' slots carry `seq` and merges them in rank order.
+// One hop from the last arrival to every CTA of every rank; identical bits everywhere (fixed orders), so every CTA
+// advances the scalar search identically.  `k` counts the combinations of this launch (identical in all CTAs); a rank
+// publishes k + 1 only after all its CTAs have read combination k, which keeps the two slot parities safe (ree_peer.cu).
+//   ws header (unsigned words): [0] ticket of the one-shot reduction kernels, [2] arrivals, [6] exits
+__device__ __forceinline__ ExpSums grid_combine(const AdaptArgs& A, const ExpSums& blk, int mode, int& k,
+                                                unsigned long long seq_base, OptShared& sh) {
     const unsigned int G = gridDim.x;
     double* part = A.ws + REE_WS_HEADER + (size_t)(k & 1) * 4 * G;
-    double* res = A.ws + REE_WS_HEADER + 8 * (size_t)G + (size_t)(k & 1) * 4;
     unsigned int* ctl = reinterpret_cast<unsigned int*>(A.ws);
+    const unsigned long long seq = seq_base + (unsigned long long)k + 1ull;
+    const int par = (int)(seq & 1ull);
+    const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         double* p = part + 4 * (size_t)blockIdx.x;
-        p[0] = blk.m; p[1] = blk.s1; p[2] = blk.s2; p[3] = blk.cnt;
-        __threadfence();
-        const unsigned int old = atomicAdd(ctl + 2, 1u);
+        reinterpret_cast<double2*>(p)[0] = make_double2(blk.m, blk.s1);
+        reinterpret_cast<double2*>(p)[1] = make_double2(blk.s2, blk.cnt);
+        const unsigned int old = atom_add_acq_rel_u32(ctl + 2, 1u);
         sh.last = (old == (unsigned int)(k + 1) * G - 1u) ? 1 : 0;
     }
     __syncthreads();
-    const bool do_exchange = exchange && A.has_peer;
     if (sh.last) {
-        __threadfence();
         ExpSums v;
         if (mode == MERGE_EXPS) {
             v = expsums_empty();
             for (unsigned int b = threadIdx.x; b < G; b += blockDim.x) {
-                const volatile double* p = part + 4 * (size_t)b;
-                v = expsums_merge(v, ExpSums{p[0], p[1], p[2], p[3]});
+                const double* p = part + 4 * (size_t)b;
+                v = expsums_merge(v, ExpSums{ld_relaxed_f64(p), ld_relaxed_f64(p + 1), ld_relaxed_f64(p + 2),
+                                             ld_relaxed_f64(p + 3)});
             }
             v = expsums_block_reduce(v, sh.es);
         } else if (mode == MERGE_PLAIN) {  // all non-empty partials carry the same shift: plain sums
             double m = -CUDART_INF, s1 = 0.0, s2 = 0.0, c = 0.0;
             for (unsigned int b = threadIdx.x; b < G; b += blockDim.x) {
-                const volatile double* p = part + 4 * (size_t)b;
-                const double pm = p[0];
+                const double* p = part + 4 * (size_t)b;
+                const double pm = ld_relaxed_f64(p);
                 m = pm > m ? pm : m;
-                s1 += p[1];
-                s2 += p[2];
-                c += p[3];
+                s1 += ld_relaxed_f64(p + 1);
+                s2 += ld_relaxed_f64(p + 2);
+                c += ld_relaxed_f64(p + 3);
             }
             v.m = block_max(m, sh.red);
-            v.s1 = block_sum(s1, sh.red);
-            v.s2 = block_sum(s2, sh.red);
-            v.cnt = block_sum(c, sh.red);
+            block_sum3(s1, s2, c, sh.red);
+            v.s1 = s1; v.s2 = s2; v.cnt = c;
         } else {  // [max, min]
             double hi = -CUDART_INF, nlo = -CUDART_INF;
             for (unsigned int b = threadIdx.x; b < G; b += blockDim.x) {
-                const volatile double* p = part + 4 * (size_t)b;
-                const double a = p[0], c = -p[1];
+                const double* p = part + 4 * (size_t)b;
+                const double a = ld_relaxed_f64(p), c = -ld_relaxed_f64(p + 1);
                 hi = a > hi ? a : hi;
                 nlo = c > nlo ? c : nlo;
             }
@@ -126,23 +164,47 @@ __device__ __forceinline__ ExpSums grid_combine(const AdaptArgs& A, const ExpSum
             v.s2 = 0.0;
             v.cnt = 0.0;
         }
-        if (do_exchange && threadIdx.x < 32) v = peer_exchange_warp(A.peer, seq_base + xk + 1, v, sh.xch);
-        if (threadIdx.x == 0) {
-            volatile double* r = res;
-            r[0] = v.m; r[1] = v.s1; r[2] = v.s2; r[3] = v.cnt;
-            __threadfence();
-            st_release_u32(ctl + 4, (unsigned int)(k + 1));
+        if (threadIdx.x < 32) {  // publish: lane r stores into rank r's mailbox
+            const double v0 = __shfl_sync(0xffffffffu, v.m, 0), v1 = __shfl_sync(0xffffffffu, v.s1, 0);
+            const double v2 = __shfl_sync(0xffffffffu, v.s2, 0), v3 = __shfl_sync(0xffffffffu, v.cnt, 0);
+            if (lane < A.peer.world) {
+                PeerSlot* dst = &A.peer.box[lane]->slot[par][A.peer.rank];
+                st_relaxed_f64(&dst->v[0], v0);
+                st_relaxed_f64(&dst->v[1], v1);
+                st_relaxed_f64(&dst->v[2], v2);
+                st_relaxed_f64(&dst->v[3], v3);
+                st_release_sys_u64(&dst->seq, seq);
+            }
         }
     }
     ExpSums out = expsums_empty();
-    if (threadIdx.x == 0) {
-        while (ld_acquire_u32(ctl + 4) < (unsigned int)(k + 1)) {
+    if (threadIdx.x < 32) {
+        if (lane < A.peer.world) {
+            const PeerSlot* src = &A.peer.box[A.peer.rank]->slot[par][lane];
+            unsigned long long spins = 0;
+            while (ld_acquire_sys_u64(&src->seq) != seq) {
+                if (A.peer.world > 1 && ++spins > REE_PEER_SPIN_LIMIT) {  // a peer died or the call order diverged
+                    *A.peer.error = 1;
+                    break;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sh.xch[lane][q] = ld_relaxed_f64(&src->v[q]);
         }
-        const volatile double* r = res;
-        out = ExpSums{r[0], r[1], r[2], r[3]};
+        __syncwarp();
+        if (lane == 0) {
+            if (mode == MERGE_RANGE) {  // the range of ell stays rank-local (the exchange only keeps the ranks in step)
+                const int r = A.peer.rank;
+                out = ExpSums{sh.xch[r][0], sh.xch[r][1], 0.0, 0.0};
+            } else {
+                out = ExpSums{sh.xch[0][0], sh.xch[0][1], sh.xch[0][2], sh.xch[0][3]};
+                for (int q = 1; q < A.peer.world; ++q)
+                    out = expsums_merge(out, ExpSums{sh.xch[q][0], sh.xch[q][1], sh.xch[q][2], sh.xch[q][3]});
+            }
+        }
+        __syncwarp();
     }
     k += 1;
-    if (do_exchange) xk += 1;
     return out;
 }
 
@@ -196,9 +258,8 @@ __device__ __forceinline__ ExpSums cvar_alg_partial(const AdaptArgs& A, double s
                  for (int k = 0; k < 4; ++k) one(q.v[k]);
              },
              [&](int64_t, double gi) { one(gi); });
-    s1 = block_sum(s1, sh.red);
-    s2 = block_sum(s2, sh.red);
-    const double cn = block_sum((double)cnt, sh.red);
+    double cn = (double)cnt;
+    block_sum3(s1, s2, cn, sh.red);
     return ExpSums{cn > 0.0 ? 0.0 : -CUDART_INF, s1, s2, cn};
 }
 
@@ -242,9 +303,8 @@ __device__ __forceinline__ ExpSums ess_partial(const AdaptArgs& A, double beta, 
                  for (int k = 0; k < 4; ++k) one(lq.v[k]);
              },
              [&](int64_t, double li) { one(li); });
-    s1 = block_sum(s1, sh.red);
-    s2 = block_sum(s2, sh.red);
-    const double cn = block_sum((double)cnt, sh.red);
+    double cn = (double)cnt;
+    block_sum3(s1, s2, cn, sh.red);
     return ExpSums{cn > 0.0 ? M : -CUDART_INF, s1, s2, cn};
 }
 
@@ -301,15 +361,17 @@ __device__ __forceinline__ double cvar_of(const ExpSums& t) {
 //          6 beta evaluations, 7 grid combinations, 8..11 the ESS tuple [M, S1, S2, cnt] at (sigma, beta),
 //          12 hybrd's root before the positivity test, 13 objective there, 14 / 15 range of ell
 template <bool ALG>
-__global__ void __launch_bounds__(OPT_THREADS, 2) k_adapt(const AdaptArgs A) {
+__global__ void __launch_bounds__(OPT_THREADS, 1) k_adapt(const AdaptArgs A) {
     __shared__ OptShared sh;
     __shared__ ree_opt::BrentBounded br;  // the searches' state: touched by thread 0 only, kept out of the registers
     __shared__ ree_opt::Hybr1 hy;
     const uint32_t T = load_exp_table(sh.tab);
     int k = 0;
-    unsigned long long xk = 0, seq_base = 0;
-    if (A.has_peer && threadIdx.x == 0) seq_base = A.peer.box[A.peer.rank]->seq;
-    if (A.has_peer) seq_base = __shfl_sync(0xffffffffu, seq_base, 0);  // warp 0 runs the exchanges
+    unsigned long long seq_base = 0;  // combinations this mailbox has seen before this launch (warp 0 needs it)
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) seq_base = A.peer.box[A.peer.rank]->seq;
+        seq_base = __shfl_sync(0xffffffffu, seq_base, 0);
+    }
     const bool lead = threadIdx.x == 0;
 
     // ---- A. sigma ------------------------------------------------------------------------------------------------
@@ -323,7 +385,7 @@ __global__ void __launch_bounds__(OPT_THREADS, 2) k_adapt(const AdaptArgs A) {
         __syncthreads();
         for (;;) {
             const ExpSums blk = ALG ? cvar_alg_partial(A, x, A.p.sigma, sh) : cvar_generic_partial(A, x, A.p.sigma, T, sh);
-            const ExpSums t = grid_combine(A, blk, ALG ? MERGE_PLAIN : MERGE_EXPS, true, k, seq_base, xk, sh);
+            const ExpSums t = grid_combine(A, blk, ALG ? MERGE_PLAIN : MERGE_EXPS, k, seq_base, sh);
             if (lead) {
                 if (!(t.cnt > 0.0)) {
                     sh.more = -1;
@@ -333,11 +395,11 @@ __global__ void __launch_bounds__(OPT_THREADS, 2) k_adapt(const AdaptArgs A) {
                     sh.x = br.x;
                 }
             }
-            __syncthreads();
+            __syncthreads();  // (the next write to sh.more / sh.x comes after the barriers of the next reduction)
             const int more = sh.more;
             x = sh.x;
-            __syncthreads();
             if (more <= 0) {
+                __syncthreads();
                 if (lead) {
                     sig_status = more < 0 ? -1 : br.flag;
                     sig_nfev = br.num;
@@ -355,14 +417,14 @@ __global__ void __launch_bounds__(OPT_THREADS, 2) k_adapt(const AdaptArgs A) {
     double hi, lo;
     {
         const ExpSums blk = ell_partial(A, sigma, sh);
-        const ExpSums t = grid_combine(A, blk, MERGE_RANGE, false, k, seq_base, xk, sh);
+        const ExpSums t = grid_combine(A, blk, MERGE_RANGE, k, seq_base, sh);
         if (lead) {
             sh.x = t.m;
-            sh.red[0] = t.s1;
+            sh.y = t.s1;
         }
         __syncthreads();
         hi = sh.x;
-        lo = sh.red[0];
+        lo = sh.y;
         __syncthreads();
     }
 
@@ -382,7 +444,7 @@ __global__ void __launch_bounds__(OPT_THREADS, 2) k_adapt(const AdaptArgs A) {
         int nev = 0;
         while (more) {
             const ExpSums blk = ess_partial(A, x, hi, lo, T, sh);
-            const ExpSums t = grid_combine(A, blk, MERGE_PLAIN, true, k, seq_base, xk, sh);
+            const ExpSums t = grid_combine(A, blk, MERGE_PLAIN, k, seq_base, sh);
             if (lead) {
                 if (nev == 0) t_first = t_acc = t;
                 if (!(t.cnt > 0.0)) {
@@ -400,8 +462,8 @@ __global__ void __launch_bounds__(OPT_THREADS, 2) k_adapt(const AdaptArgs A) {
             __syncthreads();
             const int mm = sh.more;
             x = sh.x;
-            __syncthreads();
             if (mm <= 0) {
+                __syncthreads();
                 if (lead) {
                     beta_status = mm < 0 ? -1 : hy.info;
                     beta_nfev = nev;
@@ -419,7 +481,7 @@ __global__ void __launch_bounds__(OPT_THREADS, 2) k_adapt(const AdaptArgs A) {
         }
     } else {
         const ExpSums blk = ess_partial(A, beta, hi, lo, T, sh);
-        const ExpSums t = grid_combine(A, blk, MERGE_PLAIN, true, k, seq_base, xk, sh);
+        const ExpSums t = grid_combine(A, blk, MERGE_PLAIN, k, seq_base, sh);
         if (lead) t_acc = t;
     }
 
@@ -445,9 +507,8 @@ __global__ void __launch_bounds__(OPT_THREADS, 2) k_adapt(const AdaptArgs A) {
         const unsigned int old = atomicAdd(ctl + 6, 1u);
         if (old == gridDim.x - 1) {
             ctl[2] = 0u;
-            ctl[4] = 0u;
             ctl[6] = 0u;
-            if (A.has_peer) A.peer.box[A.peer.rank]->seq = seq_base + xk;
+            A.peer.box[A.peer.rank]->seq = seq_base + (unsigned long long)k;
             __threadfence();
         }
     }
@@ -455,6 +516,8 @@ __global__ void __launch_bounds__(OPT_THREADS, 2) k_adapt(const AdaptArgs A) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 static int g_opt_ctas[64][2] = {{0}};
+static PeerArgs g_local_box[64];  // single-rank publication mailbox of each device (world = 1)
+static bool g_local_ready[64] = {false};
 
 static int opt_max_ctas(int alg) {
     int dev = 0;
@@ -465,12 +528,37 @@ static int opt_max_ctas(int alg) {
         cudaError_t err = alg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_adapt<true>, OPT_THREADS, 0)
                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_adapt<false>, OPT_THREADS, 0);
         if (err != cudaSuccess || per < 1 || sms < 1) return 0;
-        if (per > 2) per = 2;
-        int ctas = per * sms;
+        int ctas = sms;  // one CTA per SM: the fewest arrivals per combination at full thread occupancy
+        if (const char* env = getenv("REE_ADAPT_CTAS")) {  // experiments (tools/adapt_bench.py)
+            const int v = atoi(env);
+            if (v >= 1 && v <= sms * per) ctas = v;
+        }
         const int cap = 2 * ree_grid_ctas();  // the small-partials region of the workspace holds 16 G doubles
         g_opt_ctas[dev][alg] = ctas > cap ? cap : ctas;
     }
     return g_opt_ctas[dev][alg];
+}
+
+static const PeerArgs* local_mailbox() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!g_local_ready[dev]) {
+        PeerArgs a{};
+        cudaError_t err = cudaMalloc((void**)&a.box[0], sizeof(PeerBox));
+        if (err == cudaSuccess) err = cudaMemset(a.box[0], 0, sizeof(PeerBox));
+        if (err == cudaSuccess) err = cudaMalloc((void**)&a.error, sizeof(int));
+        if (err == cudaSuccess) err = cudaMemset(a.error, 0, sizeof(int));
+        if (err == cudaSuccess) err = cudaDeviceSynchronize();
+        if (err != cudaSuccess) {
+            ree_set_error((int)err, cudaGetErrorString(err));
+            return nullptr;
+        }
+        a.rank = 0;
+        a.world = 1;
+        g_local_box[dev] = a;
+        g_local_ready[dev] = true;
+    }
+    return &g_local_box[dev];
 }
 
 extern "C" int ree_cbree_adapt(const double* g, const double* e, int64_t n, const ree_adapt* p, double* ell,
@@ -486,9 +574,11 @@ extern "C" int ree_cbree_adapt(const double* g, const double* e, int64_t n, cons
     const int ctas = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     AdaptArgs a{};
     a.g = g; a.e = e; a.n = n; a.ell = ell; a.ws = workspace; a.out = out16; a.p = *p;
-    const PeerArgs* peer = ree_peer_args_current();
-    a.has_peer = (peer && p->use_peers) ? 1 : 0;
-    if (a.has_peer) a.peer = *peer;
+    const PeerArgs* peer = p->use_peers ? ree_peer_args_current() : local_mailbox();
+    if (!peer)
+        return ree_set_error(REE_E_BADARG, p->use_peers ? "ree_cbree_adapt: use_peers without connected peer mailboxes"
+                                                         : "ree_cbree_adapt: no mailbox");
+    a.peer = *peer;
     void* args[] = {&a};
     cudaError_t err = alg ? cudaLaunchCooperativeKernel((void*)k_adapt<true>, dim3(ctas), dim3(OPT_THREADS), args, 0,
                                                         ree_stream(stream))
