@@ -5,15 +5,17 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one CBREE iteration (solver.py:413-437 of the reference): step-size controller, sigma (Brent) and
-beta (hybr) adaptation with device objective sweeps, the Euler-Maruyama sweep and the Mahalanobis / IS / weighted
-moments sweep, convergence bookkeeping.  Workload: affine LSF, d=100, N=1e7 particles PER GPU (weak scaling),
-fp64, synthetic standard-normal particles (Philox, rank-invariant counters).  Inputs (8 GB per ensemble) are far
-larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
+beta (hybr) adaptation (one persistent search kernel), the Euler-Maruyama sweep and the Gram / Mahalanobis / IS
+sweeps, convergence bookkeeping.  Workload: affine LSF, d=100, N=1e7 particles IN TOTAL (strong scaling: the ranks
+share them; `weak_value` is the same step with 1e7 particles per GPU; --scaling weak makes that the headline), fp64,
+synthetic standard-normal particles (Philox, rank-invariant counters).  Inputs (8 GB per ensemble, >= 1 GB per rank)
+are far larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = the same metric through
 CBREE(...).solve(problem) with the sample in pinned HOST memory (H2D of the sample and D2H of the results inside
 the timed region); `roofline` = dominant sweep against the measured HBM peak (plus the fp64 pipe fraction that
-actually binds at d=100); `cpu_baseline` = the NumPy oracle port of the reference on this box's host cores.
+actually binds at d=100); `cpu_baseline` = the reference's own CBREE (oracle/_ref; the NumPy oracle port if that copy
+is absent) on this box's host cores.
 """
 import argparse
 import json
@@ -36,7 +38,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=10_000_000, help="particles per GPU")
+    ap.add_argument("--n", type=int, default=10_000_000,
+                    help="particles: the TOTAL over all GPUs with --scaling strong, per GPU with --scaling weak")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): N total fixed at --n (BASELINE: 'near-linear 1->8 GPU scaling at N=10^7'); "
+                         "weak: --n particles per GPU.  Identical at --gpus 1.")
+    ap.add_argument("--no-weak", action="store_true", help="strong runs on >1 GPU: skip the extra weak-scaling leg")
     ap.add_argument("--d", type=int, default=100)
     ap.add_argument("--ref-n", type=int, default=100_000, help="particles of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
@@ -47,9 +54,44 @@ def parse():
 
 
 # --------------------------------------------------------------------------- #
-# CPU arm: the oracle port of the reference's CBREE (the reference itself cannot travel to the GPU box)
+# CPU arm: the reference's own CBREE (oracle/_ref, the git-ignored copy oracle/make_ref.sh makes; it ships with gpurun),
+# else the NumPy oracle port of it.  The one place outside tests/ and smoke() that executes anything under oracle/.
 # --------------------------------------------------------------------------- #
-def cpu_cbree(n, d, steps, warmup):
+def cpu_cbree_reference(n, d, steps, warmup):
+    """Time `steps` iterations of the UNMODIFIED reference `CBREE.solve` (solver.py:365-503) after `warmup` untimed ones,
+    through its public API: the per-iteration `callback(cache, solver)` hook (solver.py:439-446) takes the time stamps.
+    Returns (p-it/s, seconds) or None if no copy of the reference is reachable."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+
+    import ref_loader
+
+    if not ref_loader.reference_available():
+        return None
+    ref = ref_loader.load_reference()
+    warmup = max(1, warmup)
+    prob = ref.toy.make_linear_problem(d)
+    prob.set_sample(np.random.default_rng(1).standard_normal((n, d)))  # (ERANataf.random takes 10 s per 1e8 values)
+    stamps = []
+
+    def callback(cache, solver):
+        stamps.append(time.perf_counter())
+        return cache
+
+    import contextlib
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()):  # the constructor prints "adaptive: True" (solver.py:267)
+        solver = ref.solver.CBREE(seed=2, num_steps=warmup + steps - 1, convergence_check=False,
+                                  divergence_check=False, callback=callback)
+        sol = solver.solve(prob)
+    if len(stamps) < warmup + steps:
+        raise RuntimeError(f"reference CBREE stopped after {len(stamps)} iterations: {sol.msg}")
+    dt = stamps[warmup + steps - 1] - stamps[warmup - 1]
+    return n * steps / dt, dt
+
+
+def cpu_cbree_port(n, d, steps, warmup):
     """Time `steps` CBREE iterations of the NumPy port after `warmup` untimed ones.  Returns (p-it/s, seconds)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
@@ -84,6 +126,34 @@ def cpu_cbree(n, d, steps, warmup):
     return n * steps / dt, dt
 
 
+def cpu_cbree(n, d, steps, warmup):
+    """(p-it/s, seconds, kind, description): the real reference when oracle/_ref (or /root/reference) is there."""
+    use_all_host_threads()
+    try:
+        out = cpu_cbree_reference(n, d, steps, warmup)
+    except Exception as e:  # say why the port ran instead
+        out, why = None, f"; reference failed: {type(e).__name__}: {e}"
+    else:
+        why = "; oracle/_ref absent (run oracle/make_ref.sh where /root/reference exists)"
+    if out is not None:
+        return out[0], out[1], "reference", "rareeventestimation.solver.CBREE.solve (unmodified reference, oracle/_ref)"
+    v, dt = cpu_cbree_port(n, d, steps, warmup)
+    return v, dt, "port", "oracle/cbree_oracle.py (NumPy/SciPy port)" + why
+
+
+def use_all_host_threads():
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm uses all the host threads it can get
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.pop(k, None)
+    try:
+        import numpy  # noqa: F401  (loads the BLAS the limits below apply to)
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -97,26 +167,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm uses all the host threads it can get
-    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
-        os.environ.pop(k, None)
-    try:
-        import numpy  # noqa: F401  (loads the BLAS the limits below apply to)
-        from threadpoolctl import threadpool_limits
-
-        threadpool_limits(limits=os.cpu_count() or 1)
-    except Exception:
-        pass
-    val, dt = cpu_cbree(args.ref_n, args.d, args.steps, args.warmup)
+    val, dt, kind, what = cpu_cbree(args.ref_n, args.d, args.steps, args.warmup)
     cores = blas_threads()
-    sample = f"CBREE affine d={args.d}, N={args.ref_n} particles, {args.steps} iterations, NumPy/SciPy oracle port"
+    sample = (f"CBREE affine d={args.d}, N={args.ref_n} particles, {args.steps} iterations after {max(1, args.warmup)} "
+              f"warm-up, {what} ({dt:.1f} s)")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"CBREE affine LSF d={args.d} fp64 (bounded CPU sample N={args.ref_n})",
-                   "particles": args.ref_n, "d": args.d},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": f"CBREE affine LSF d={args.d} fp64 (bounded CPU sample N={args.ref_n} of BASELINE "
+                               f"configs[1]; the rate is per particle-iteration)",
+                   "particles": args.ref_n, "d": args.d, "host_cpus": os.cpu_count()},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -191,8 +254,10 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     eng = Engine.get(dev, Comm())
-    n_local, d, K, W = args.n, args.d, args.steps, args.warmup
-    n_total = n_local * world
+    d, K, W = args.d, args.steps, args.warmup
+    strong = args.scaling == "strong"
+    n_total = args.n if strong else args.n * world
+    n_local = eng.comm.shard(n_total)[1] - eng.comm.shard(n_total)[0]
 
     def barrier():
         if world > 1:
@@ -231,10 +296,6 @@ def run_b200(args):
         warm.sample = DeviceSample(8192 * world, d, seed=1)
         ree.CBREE(num_steps=16, **kw).solve(warm)
         del warm
-    prob = ree.make_linear_problem(d)
-    prob.sample = DeviceSample(n_total, d, seed=0x5EED)
-    solver = ree.CBREE(num_steps=10**9, **kw)
-    cache_list = solver.start(prob)
     # The sampler is started BEFORE the warm-up steps: launching nvidia-smi (NVML initialisation, device enumeration)
     # stalls CUDA calls of other processes for tens of milliseconds -- inside the timed region that was a sporadic
     # +20..100 ms.  Once it runs, its 200 ms polls are cheap; they cover the warm-up and the timed steps (same load).
@@ -242,29 +303,45 @@ def run_b200(args):
     if rank == 0 and os.environ.get("REE_BENCH_NO_CLOCKS") != "1":  # (hook used to measure the sampler's own cost)
         clocks.start()
         time.sleep(1.0)
-    for _ in range(W):
-        solver.advance(cache_list)
-    for v in marks.values():
-        v.clear()
     import gc
 
-    gc.collect()
-    gc.disable()  # like timeit: no cyclic-GC pause inside the timed regions (re-enabled before the CPU baseline)
-    barrier()
-    launches0 = lib.ree_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(K):
-        solver.advance(cache_list)
-    ev1.record()
-    barrier()
-    launches = lib.ree_launch_count() - launches0
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    def measure(n_tot):
+        """W untimed + K timed CBREE iterations on n_tot particles (all ranks).  Returns a dict."""
+        prob = ree.make_linear_problem(d)
+        prob.sample = DeviceSample(n_tot, d, seed=0x5EED)
+        solver = ree.CBREE(num_steps=10**9, **kw)
+        cache_list = solver.start(prob)
+        for _ in range(W):
+            solver.advance(cache_list)
+        for v in marks.values():
+            v.clear()
+        gc.collect()
+        gc.disable()  # like timeit: no cyclic-GC pause inside the timed regions (re-enabled before the CPU baseline)
+        barrier()
+        launches0 = lib.ree_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(K):
+            solver.advance(cache_list)
+        ev1.record()
+        barrier()
+        gc.enable()
+        out = {"launches": lib.ree_launch_count() - launches0, "ms": max_over_ranks(ev0.elapsed_time(ev1)),
+               "sweep_ms": {k: (sum(a.elapsed_time(b) for a, b in v) / max(1, len(v))) for k, v in marks.items()},
+               "sigma": cache_list[-1].sigma, "beta": cache_list[-1].beta}
+        out["value"] = n_tot * K / (out["ms"] * 1e-3)
+        return out  # the HBM blocks go back to the engine's free list / the allocator's cache
+
+    weak = None
+    if strong and world > 1 and not args.no_weak:  # second field: the same step with --n particles PER GPU
+        weak = measure(args.n * world)
+        eng.drop_pool()
+        torch.cuda.empty_cache()
+    m = measure(n_total)
+    ms, launches, sweep_ms, value = m["ms"], m["launches"], m["sweep_ms"], m["value"]
+    sigma_now, beta_now = m["sigma"], m["beta"]
     clk = clocks.stop() if rank == 0 else None
-    value = n_total * K / (ms * 1e-3)
-    sweep_ms = {k: (sum(a.elapsed_time(b) for a, b in v) / max(1, len(v))) for k, v in marks.items()}
-    sigma_now, beta_now = cache_list[-1].sigma, cache_list[-1].beta
-    del cache_list, solver  # the HBM blocks stay in the allocator's cache for the end-to-end leg below
+    gc.disable()
 
     # ---- roofline of the dominant sweep (per launch, this rank) -------------------------------
     peaks = {}
@@ -274,11 +351,30 @@ def run_b200(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    fp64_peak = None
-    try:
-        fp64_peak = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))
-    except Exception:
-        pass
+    fp64_peak, fp64_src = None, None
+    if rank == 0 and world == 1 and os.path.exists(os.path.join(ROOT, "tools", "fp64_peak")):
+        # the fp64 roofline denominator measured in this very run (dependent-free DFMA / DMMA chains, < 1 s), with the
+        # SM clock sampled while it runs
+        try:
+            probe_clk = ClockSampler(local)
+            probe_clk.start()
+            time.sleep(0.5)
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local)))
+            txt = ""
+            for _ in range(3):  # ~0.25 s each: long enough for the 200 ms clock samples to see the load
+                txt = subprocess.run([os.path.join(ROOT, "tools", "fp64_peak")], capture_output=True, text=True,
+                                     timeout=120, env=env).stdout
+            fp64_peak = json.loads(txt.strip().splitlines()[-1])
+            fp64_peak["clocks"] = probe_clk.stop()
+            fp64_src = "tools/fp64_peak run inside this bench.py invocation"
+        except Exception:
+            fp64_peak = None
+    if fp64_peak is None:
+        try:
+            fp64_peak = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))
+            fp64_src = "profiles/fp64_peak.json (tools/fp64_peak.cu on this pool, an earlier run)"
+        except Exception:
+            pass
     # Algorithmic bytes / flops per particle of the three kernels of an iteration:
     #   step     read X, write X', g', e'                     | triangular F z: d(d+1) flop
     #   moments  read X', g', a                               | two symmetric-half Grams of (y, 1): 2 (d+1)(d+2) flop
@@ -312,8 +408,9 @@ def run_b200(args):
         # d = 100: 16.8 flop/B against a machine balance of 5.7 -> the fp64 tensor pipe (DMMA) binds, not HBM
         roofline = {"bound": "tensor", "kernel": names[dom], "achieved": ach_tf, "peak": fp64_pk, "unit": "TFLOP/s",
                     "frac": ach_tf / fp64_pk, "traffic": traffic,
-                    "peak_source": "fp64 DMMA (mma.sync.m8n8k4.f64) measured on this pool by tools/fp64_peak.cu -> "
-                                   "profiles/fp64_peak.json; tcgen05 has no f64 kind, MEASURED_PEAKS.json only has bf16",
+                    "peak_source": f"fp64 DMMA (mma.sync.m8n8k4.f64) measured by tools/fp64_peak.cu: {fp64_src}; "
+                                   "tcgen05 has no f64 kind, MEASURED_PEAKS.json only has bf16",
+                    "fp64_probe": fp64_peak,
                     "ms_per_launch": sweep_ms[dom],
                     "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
                             "peak_source": peak_src},
@@ -363,7 +460,10 @@ def run_b200(args):
                "d2h_bytes_per_step": (last_g.nbytes + 8 * len(sol.prob_fail_hist)) / n_steps,
                "steps": n_steps, "seconds": ms2 * 1e-3, "prob_fail": pf, "msg": sol.msg,
                "phases_ms": {"start_incl_h2d": 1e3 * (t_ph[1] - t_ph[0]), "iterations": 1e3 * (t_ph[2] - t_ph[1]),
-                             "finish_incl_d2h": 1e3 * (t_ph[3] - t_ph[2])}}
+                             "finish_incl_d2h": 1e3 * (t_ph[3] - t_ph[2])},
+               "note": "CBREE.solve(problem) written out as its three public phases start / advance* / finish (the "
+                       "body of solve) on a pinned HOST sample; D2H = lsf_eval_hist[-1] + prob_fail_hist.  The (S, N, d) "
+                       "Solution.ensemble_hist is NOT copied: it stays in HBM behind LazyHistory until accessed."}
         del sol, solver2, host, cl2
         torch.cuda.empty_cache()
 
@@ -371,23 +471,27 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         steps_cpu = 8
-        v, dt = cpu_cbree(args.ref_n, d, steps_cpu, 1)
-        cpu = {"value": v, "unit": UNIT, "cores": blas_threads(), "kind": "port",
-               "sample": f"CBREE affine d={d}, N={args.ref_n}, {steps_cpu} iterations of oracle/cbree_oracle.py "
-                         f"({dt:.1f} s)"}
+        v, dt, kind, what = cpu_cbree(args.ref_n, d, steps_cpu, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": blas_threads(), "kind": kind,
+               "sample": f"CBREE affine d={d}, N={args.ref_n}, {steps_cpu} iterations of {what} ({dt:.1f} s)"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": f"CBREE affine LSF d={d}, N={n_local} particles per GPU, fp64 (BASELINE configs[1])",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if (strong and world > 1) else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"CBREE affine LSF d={d}, N={n_total} particles in total, {n_local} per GPU, fp64 "
+                                   f"(BASELINE configs[1])",
                        "particles_per_gpu": n_local, "particles_total": n_total, "d": d, "tgt_fun": "algebraic",
                        "noise": "philox", "sharding": f"particles x{world}",
                        "l2": "inputs (8*N*d bytes per ensemble) exceed L2; no flush",
                        "sigma_at_end": sigma_now, "beta_at_end": beta_now},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
+        if weak is not None:  # the same step at --n particles per GPU (N grows with the GPU count)
+            line["weak_value"] = weak["value"]
+            line["weak"] = {"value": weak["value"], "ms_per_step": weak["ms"] / K, "particles_per_gpu": args.n,
+                            "particles_total": args.n * world, "gpu_launches": int(weak["launches"])}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

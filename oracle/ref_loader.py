@@ -1,19 +1,32 @@
 """TEST INFRASTRUCTURE ONLY -- loader for the *live* reference package.
 
 Imports the unmodified reference modules from ``/root/reference/src`` (build
-container only; the path does not exist on the GPU box) without executing the
+container) or from ``oracle/_ref/src`` (the git-ignored copy ``oracle/make_ref.sh``
+makes; it travels to the GPU box with gpurun) without executing the
 reference's ``__init__`` (which pulls plotly / skfem).
 Used by ``tests/golden/make_golden.py`` to generate the committed golden
-fixtures and by the ``needs_reference`` tests that pin ``oracle/`` against the
-reference itself.  Nothing in ``rareeventestimation_b200`` may import this.
+fixtures, by the ``needs_reference`` tests that pin ``oracle/`` against the
+reference itself, and by ``bench.py --impl reference`` / its ``cpu_baseline`` leg
+to time the reference's own CBREE.  Nothing in ``rareeventestimation_b200`` may
+import this.
 """
 import importlib
 import os
 import sys
 import types
 
-REF_SRC = os.environ.get("REE_REFERENCE_SRC", "/root/reference/src")
 _PKG = "rareeventestimation"
+
+
+def _find_reference_src() -> str:
+    here = os.path.dirname(os.path.abspath(__file__))
+    for cand in (os.environ.get("REE_REFERENCE_SRC"), "/root/reference/src", os.path.join(here, "_ref", "src")):
+        if cand and os.path.isdir(os.path.join(cand, _PKG)):
+            return cand
+    return "/root/reference/src"
+
+
+REF_SRC = _find_reference_src()
 
 
 def reference_available() -> bool:
