@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define REE_ABI_VERSION 7
+#define REE_ABI_VERSION 8
 
 /* argument errors */
 #define REE_E_BADARG (-1)
@@ -88,6 +88,9 @@ int64_t ree_launch_count(void);
  *   0  modular kernels (need the optional `w` scratch vector of ree_cbree_maha)           -- d > 103
  * Path 2 dimensions are also served by the path 1 calling sequence.                                    */
 int ree_fused_path(int d);
+/* Largest supported dimension (256): beyond it the d x d factorisations and the modular Gram have no kernel.  The host
+ * side raises before any work (the reference itself accepts any d; toy_problems.py:95-101 goes up to d = 200). */
+int ree_max_dim(void);
 /* number of CTAs every reduction kernel uses on the current device (partials per launch) */
 int ree_num_ctas(void);
 /* bytes of scratch a call with dimension d may need (partials of the d x d sums).  The workspace
@@ -229,14 +232,17 @@ int ree_cbree_moments(const double* x, int64_t n, int d, int64_t ld, const doubl
 
 /* ---- small dense algebra (single CTA) ---------------------------------------------------- */
 /* From raw shifted sums (after any cross-rank allreduce) compute
- *   mean[d], cov[d*d] (ddof given), L = chol(cov) (lower, row-major), Linv = L^-1, stats[0] = log det cov,
- *   stats[1] = info (0 ok, k>0: pivot k not positive / matrix numerically singular by SciPy's test),
- *   stats[2] = min pivot, stats[3] = max diag.
- * replaces average/cov (solver.py:670-671) + the factorisation inside multivariate_normal.logpdf (672-674). */
+ *   mean[d], cov[d*d] (ddof given), L = chol(cov) (lower, row-major), Linv = L^-1, and EIGHT statistics:
+ *   stats[0] = log det cov, stats[1] = info (0 ok, k>0: pivot k not positive), stats[2] = min pivot,
+ *   stats[3] = max diag, stats[4] = |Linv|_F^2 = trace(cov^-1) (0 without Linv), stats[5] = |cov|_inf, stats[6..7] = 0.
+ *   (min pivot >= lambda_min >= 1 / stats[4] and max diag <= lambda_max <= stats[5]: the host decides SciPy's
+ *    singularity test lambda_min <= 1e6 eps lambda_max from them and only needs eigenvalues inside the gap.)
+ * replaces average/cov (solver.py:670-671) + the factorisation inside multivariate_normal.logpdf (672-674).
+ * d <= 160: the matrix lives in shared memory; 160 < d <= ree_max_dim(): in a per-device global scratch. */
 int ree_moments_chol(const double* sums, const double* shift, int d, int ddof, int weighted, double* mean,
-                     double* cov, double* L, double* Linv, double* stats4, void* stream);
-/* L = chol(scale * C) for the noise covariance (solver.py:666-667), stats as above (no Linv). */
-int ree_chol_scaled(const double* C, int d, double scale, double* L, double* stats4, void* stream);
+                     double* cov, double* L, double* Linv, double* stats8, void* stream);
+/* L = chol(scale * C) for the noise covariance (solver.py:666-667), stats[0..3] as above, stats[4..7] = 0. */
+int ree_chol_scaled(const double* C, int d, double scale, double* L, double* stats8, void* stream);
 
 /* ---- IS density + weighted moments (sweep 2) ---------------------------------------------- */
 /* For every particle: q = |Linv (x - mean)|^2, logq = -(d log 2pi + logdet + q)/2   (solver.py:672-674)

@@ -12,6 +12,7 @@ from .solution import Solution  # noqa: F401
 from .mixture import MixtureModel, VMFNMixture  # noqa: F401
 from .solver import CBREE, CBREECache, Solver, flatten_cache_list, get_slope  # noqa: F401
 from .baselines import CMC, SIS  # noqa: F401
+from .utilities import gaussian_logpdf, importance_sampling, my_log_cvar, my_softmax  # noqa: F401
 from .evaluation import (  # noqa: F401
     add_evaluations, aggregate_df, do_multiple_solves, load_data, study_cbree_observation_window,
 )

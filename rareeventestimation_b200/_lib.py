@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libree_b200.so")
 TGT_KINDS = {"algebraic": 0, "tanh": 1, "arctan": 2, "erf": 3, "relu": 4, "sigmoid": 5}
 LSF_EXTERNAL, LSF_AFFINE, LSF_CONVEX, LSF_FUJITA_RACKWITZ, LSF_OSCILLATOR, LSF_DIFFUSION = range(6)
 NOISE_INJECT, NOISE_PHILOX = 0, 1
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class ReeError(RuntimeError):
@@ -74,6 +74,7 @@ PROTOTYPES = {
     "ree_num_ctas": (_INT, []),
     "ree_launch_count": (_I64, []),
     "ree_fused_path": (_INT, [_INT]),
+    "ree_max_dim": (_INT, []),
     "ree_workspace_bytes": (_I64, [_INT]),
     "ree_fetch_small": (_INT, [_P, _INT, _P, _P]),
     "ree_download_vector": (_INT, [_P, _P, _I64, _P]),

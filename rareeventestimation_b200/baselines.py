@@ -14,7 +14,7 @@ from scipy import optimize
 from ._lib import check
 from .engine import Engine, Ensemble, _pad
 from .lsf import DeviceLSF
-from .problem import DeviceSample, Problem
+from .problem import DeviceSample, Problem, is_standard_normal_problem
 from .solution import Solution
 from .solver import Solver
 
@@ -101,7 +101,9 @@ class CMC(Solver):
     def solve(self, prob: Problem) -> Solution:
         eng = Engine.get()
         d = prob.sample.shape[-1]
-        if self.noise == "numpy":
+        if self.noise == "numpy" or not is_standard_normal_problem(prob):
+            # the reference draws every batch through the problem's own sampler (solver.py:1248): the device stream
+            # is N(0, I) and only stands in for it on the standard normal space
             return self._solve_reference_stream(prob, eng, d)
         n = self.num_runs
         lo, hi = eng.comm.shard(n)
@@ -180,6 +182,10 @@ class SIS(Solver):
                                       "SIS-GM / SIS-vMFNM are out of scope (SURVEY.md section 2, rows 12-13)")
         assert hasattr(prob, "eranataf_dist"), \
             "For sequential importance sampling, prob needs to have an ERANataf distribution."
+        if not is_standard_normal_problem(prob):
+            raise NotImplementedError("SIS on the engine works on the standard normal space (NormalProblem); the U2X map "
+                                      "of a general ERANataf distribution (transform_lsf, solver.py:1144) is host-side "
+                                      "ERADist code that is out of scope (SURVEY.md section 2, row 10)")
         eng = Engine.get()
         comm = eng.comm
         lib = eng.lib

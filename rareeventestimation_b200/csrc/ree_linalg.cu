@@ -1,8 +1,10 @@
 // Small dense algebra on the d x d consensus statistics: moments from raw sums, Cholesky, inverse
-// of the factor.  One CTA per call; the matrix lives in shared memory (d <= REE_MAX_D).
+// of the factor.  One CTA per call; the matrix lives in shared memory for d <= REE_MAX_D_SMEM and in a per-device
+// global scratch (L1 / L2 resident, same code: CTA barriers order global accesses inside a CTA too) up to REE_MAX_D.
 #include "common.cuh"
 
-#define REE_MAX_D 160
+#define REE_MAX_D_SMEM 160
+#define REE_MAX_D 256
 #define REE_LA_THREADS 256
 
 // in-place lower Cholesky of A (row-major, leading dimension lda) in shared memory.
@@ -93,19 +95,33 @@ __device__ void chol_smem(double* A, int d, int lda, bool psd, double* s_stat /*
     __syncthreads();
 }
 
+__device__ __forceinline__ double block_max_la(double v, double* smem /* >= 32 */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    double m = 0.0;
+    for (int w = 0; w < nw; ++w) m = fmax(m, smem[w]);
+    __syncthreads();
+    return m;
+}
+
 // mean / cov from shifted raw sums, then chol(cov) and its inverse.
 // sums = [S1 (d) | S2 (d*d) | a | b]; unweighted: n = b ; weighted: W = a (sum of weights).
 __global__ void __launch_bounds__(REE_LA_THREADS) k_moments_chol(const double* __restrict__ sums,
                                                                  const double* __restrict__ shift, int d, int ddof,
                                                                  int weighted, double* __restrict__ mean,
                                                                  double* __restrict__ cov, double* __restrict__ L,
-                                                                 double* __restrict__ Linv, double* __restrict__ stats4) {
+                                                                 double* __restrict__ Linv, double* __restrict__ stats4,
+                                                                 double* gscratch) {
     extern __shared__ double sm[];
     const int lda = d + 1;
-    double* A = sm;                 // d x lda
-    double* ybar = A + d * lda;     // d
+    double* A = gscratch ? gscratch : sm;            // d x lda
+    double* ybar = gscratch ? sm : A + d * lda;     // d
     double* s_stat = ybar + d;      // 4
     double* pivlog = s_stat + 4;    // d
+    __shared__ double red[32];
     const int tid = threadIdx.x, nt = blockDim.x;
     const double tot = weighted ? sums[d + d * d] : sums[d + d * d + 1];
     for (int j = tid; j < d; j += nt) {
@@ -132,11 +148,25 @@ __global__ void __launch_bounds__(REE_LA_THREADS) k_moments_chol(const double* _
         int j = idx / d, k = idx - j * d;
         L[idx] = (k <= j) ? A[j * lda + k] : 0.0;
     }
-    if (tid == 0) {
-        stats4[0] = s_stat[0];
-        stats4[1] = s_stat[1];
-        stats4[2] = s_stat[2];
-        stats4[3] = s_stat[3];
+    // ||cov||_inf (largest absolute row sum, from the global copy written above): an upper bound of lambda_max
+    {
+        double rs = 0.0;
+        for (int j = tid; j < d; j += nt) {
+            double acc = 0.0;
+            for (int k = 0; k < d; ++k) acc += fabs(cov[j * d + k]);
+            rs = fmax(rs, acc);
+        }
+        __syncthreads();
+        rs = block_max_la(rs, red);
+        if (tid == 0) {
+            stats4[0] = s_stat[0];
+            stats4[1] = s_stat[1];
+            stats4[2] = s_stat[2];
+            stats4[3] = s_stat[3];
+            stats4[4] = 0.0;
+            stats4[5] = rs;
+            stats4[6] = stats4[7] = 0.0;
+        }
     }
     if (!Linv || s_stat[1] != 0.0) return;
     // inverse of the lower factor, one column per thread: solve L x = e_c by forward substitution (same arithmetic as
@@ -144,16 +174,21 @@ __global__ void __launch_bounds__(REE_LA_THREADS) k_moments_chol(const double* _
     // triangle plus the padding column of A has exactly d(d+1)/2 free slots, x_j goes to A[c][j+1] (row c: contiguous
     // for the thread, rows d+1 apart across threads: conflict-free) -- no global-memory round trip per term.
     __syncthreads();
+    double fro = 0.0;  // |Linv|_F^2 = trace(cov^-1) >= 1 / lambda_min
     for (int c = tid; c < d; c += nt) {
         double* x = A + c * lda + 1;  // x[j], j >= c
         for (int j = c; j < d; ++j) {
             double s = (j == c) ? 1.0 : 0.0;
             const double* Lj = A + j * lda;
             for (int k = c; k < j; ++k) s = fma(-Lj[k], x[k], s);
-            x[j] = s / Lj[j];
+            const double v = s / Lj[j];
+            x[j] = v;
+            fro = fma(v, v, fro);
         }
     }
     __syncthreads();
+    fro = block_sum(fro, red);
+    if (tid == 0) stats4[4] = fro;
     for (int idx = tid; idx < d * d; idx += nt) {
         int j = idx / d, c = idx - j * d;
         if (c <= j) Linv[idx] = A[c * lda + j + 1];
@@ -161,11 +196,12 @@ __global__ void __launch_bounds__(REE_LA_THREADS) k_moments_chol(const double* _
 }
 
 __global__ void __launch_bounds__(REE_LA_THREADS) k_chol_scaled(const double* __restrict__ C, int d, double scale,
-                                                                double* __restrict__ L, double* __restrict__ stats4) {
+                                                                double* __restrict__ L, double* __restrict__ stats4,
+                                                                double* gscratch) {
     extern __shared__ double sm[];
     const int lda = d + 1;
-    double* A = sm;
-    double* s_stat = A + d * lda;
+    double* A = gscratch ? gscratch : sm;
+    double* s_stat = gscratch ? sm : A + d * lda;
     double* pivlog = s_stat + 4;
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int idx = tid; idx < d * d; idx += nt) {
@@ -185,26 +221,56 @@ __global__ void __launch_bounds__(REE_LA_THREADS) k_chol_scaled(const double* __
         stats4[1] = s_stat[1];
         stats4[2] = s_stat[2];
         stats4[3] = s_stat[3];
+        stats4[4] = stats4[5] = stats4[6] = stats4[7] = 0.0;
     }
 }
+
+// d x (d+1) scratch of the current device for REE_MAX_D_SMEM < d <= REE_MAX_D (allocated once; calls on one device are
+// stream-ordered by the engine: one solve at a time per device)
+static double* la_scratch() {
+    static double* buf[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!buf[dev] && cudaMalloc((void**)&buf[dev], sizeof(double) * REE_MAX_D * (REE_MAX_D + 1)) != cudaSuccess) {
+        buf[dev] = nullptr;
+        ree_set_error((int)cudaErrorMemoryAllocation, "linalg scratch: cudaMalloc failed");
+    }
+    return buf[dev];
+}
+
+static void la_attrs() {  // once per device: opt in to the large dynamic shared-memory size
+    static bool done[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    const int mx = (int)(((size_t)REE_MAX_D_SMEM * (REE_MAX_D_SMEM + 1) + 2 * REE_MAX_D + 4) * sizeof(double));
+    cudaFuncSetAttribute(k_moments_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_chol_scaled, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    done[dev] = true;
+}
+
+extern "C" int ree_max_dim(void) { return REE_MAX_D; }
 
 extern "C" int ree_moments_chol(const double* sums, const double* shift, int d, int ddof, int weighted, double* mean,
                                 double* cov, double* L, double* Linv, double* stats4, void* stream) {
     if (!sums || !mean || !cov || d < 1 || (L && !stats4))
         return ree_set_error(REE_E_BADARG, "ree_moments_chol: bad argument");
-    if (d > REE_MAX_D) return ree_set_error(REE_E_UNSUPPORTED, "ree_moments_chol: d > 160 not supported");
-    size_t smem = ((size_t)d * (d + 1) + 2 * d + 4) * sizeof(double);
-    cudaFuncSetAttribute(k_moments_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (d > REE_MAX_D) return ree_set_error(REE_E_UNSUPPORTED, "ree_moments_chol: d > 256 not supported");
+    double* gs = nullptr;
+    if (d > REE_MAX_D_SMEM && !(gs = la_scratch())) return (int)cudaErrorMemoryAllocation;
+    size_t smem = ((gs ? 0 : (size_t)d * (d + 1)) + 2 * d + 4) * sizeof(double);
+    la_attrs();
     k_moments_chol<<<1, REE_LA_THREADS, smem, ree_stream(stream)>>>(sums, shift, d, ddof, weighted, mean, cov, L, Linv,
-                                                                    stats4);
+                                                                    stats4, gs);
     return ree_check_launch("ree_moments_chol");
 }
 
 extern "C" int ree_chol_scaled(const double* C, int d, double scale, double* L, double* stats4, void* stream) {
     if (!C || !L || d < 1) return ree_set_error(REE_E_BADARG, "ree_chol_scaled: bad argument");
-    if (d > REE_MAX_D) return ree_set_error(REE_E_UNSUPPORTED, "ree_chol_scaled: d > 160 not supported");
-    size_t smem = ((size_t)d * (d + 1) + d + 4) * sizeof(double);
-    cudaFuncSetAttribute(k_chol_scaled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_chol_scaled<<<1, REE_LA_THREADS, smem, ree_stream(stream)>>>(C, d, scale, L, stats4);
+    if (d > REE_MAX_D) return ree_set_error(REE_E_UNSUPPORTED, "ree_chol_scaled: d > 256 not supported");
+    double* gs = nullptr;
+    if (d > REE_MAX_D_SMEM && !(gs = la_scratch())) return (int)cudaErrorMemoryAllocation;
+    size_t smem = ((gs ? 0 : (size_t)d * (d + 1)) + d + 4) * sizeof(double);
+    la_attrs();
+    k_chol_scaled<<<1, REE_LA_THREADS, smem, ree_stream(stream)>>>(C, d, scale, L, stats4, gs);
     return ree_check_launch("ree_chol_scaled");
 }

@@ -41,8 +41,9 @@ int ree_split_moments(const double* x, int64_t n, int d, int64_t ld, const doubl
                       const double* wmax, const double* shift, double* ws_big, double* ws_small, double* sums_u,
                       double* sums_w, cudaStream_t st);
 
-#define TP 128  // particles per CTA tile in the contraction kernels
-#define JB 4    // output dims per register block
+#define TP_WIDE 128  // particles per CTA tile in the contraction kernels (d <= 200: the tile fits 200 KB)
+#define TP_NARROW 64 // ... for 200 < d <= 256
+#define JB 4         // output dims per register block
 
 // workspace layout (doubles): [0,8) ticket header | [8, 8+4*G) small partials | [WS_BIG, ...) big partials
 #define REE_WS_HEADER 8
@@ -79,7 +80,7 @@ struct StepArgs {
     double* is4;
 };
 
-template <int MODE>
+template <int MODE, int TP>
 __global__ void __launch_bounds__(TP) k_contract(StepArgs a) {
     extern __shared__ double tile[];  // [d][TP]
     __shared__ ExpSums sh[32];
@@ -192,6 +193,8 @@ __global__ void __launch_bounds__(TP) k_contract(StepArgs a) {
 #define GP 32  // particles per shared-memory tile
 #define GT 256
 
+// blockIdx.y selects a slab of GT*MAXO entries of S2 (d > 160: d*d entries do not fit one CTA's registers); slab 0
+// also owns S1 and the scalars.  Every slab stages the same tiles.
 template <int MAXO>
 __global__ void __launch_bounds__(GT) k_gram(const double* __restrict__ x, int64_t n, int d, int64_t ld,
                                              const double* __restrict__ shift, const double* __restrict__ w,
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(GT) k_gram(const double* __restrict__ x, int64
 #pragma unroll
     for (int r = 0; r < MAXO; ++r) {
         acc[r] = 0.0;
-        int o = tid + r * GT;
+        int o = (int)blockIdx.y * GT * MAXO + tid + r * GT;
         int j = o / d, k = o - j * d;
         bool valid = o < d * d;
         ojk[r] = valid ? ((unsigned)(j * lds) | ((unsigned)(k * lds) << 16)) : 0u;
@@ -226,7 +229,8 @@ __global__ void __launch_bounds__(GT) k_gram(const double* __restrict__ x, int64
             int64_t i = base + tid;
             double wi = (i < n) ? (w ? w[i] : 1.0) : 0.0;
             wsm[tid] = wi;
-            if (w) {
+            if (blockIdx.y != 0) {  // the scalars belong to slab 0
+            } else if (w) {
                 sa += wi;
                 sb += wi * wi;
             } else if (i < n) {
@@ -241,21 +245,21 @@ __global__ void __launch_bounds__(GT) k_gram(const double* __restrict__ x, int64
             for (int r = 0; r < MAXO; ++r)
                 acc[r] = fma(wp, ys[(ojk[r] & 0xffffu) + p] * ys[(ojk[r] >> 16) + p], acc[r]);
         }
-        if (tid < d) {
+        if (blockIdx.y == 0 && tid < d) {  // (d <= GT: one row per thread)
             for (int p = 0; p < GP; ++p) s1 = fma(wsm[p], ys[tid * lds + p], s1);
         }
     }
     const size_t len = (size_t)d + (size_t)d * d + 2;
     double* out = partials + len * blockIdx.x;
-    if (tid < d) out[tid] = s1;
+    if (blockIdx.y == 0 && tid < d) out[tid] = s1;
 #pragma unroll
     for (int r = 0; r < MAXO; ++r) {
-        int o = tid + r * GT;
+        int o = (int)blockIdx.y * GT * MAXO + tid + r * GT;
         if (o < d * d) out[d + o] = acc[r];
     }
     sa = block_sum(sa, red);
     sb = block_sum(sb, red);
-    if (tid == 0) {
+    if (tid == 0 && blockIdx.y == 0) {
         out[d + d * d] = sa;
         out[d + d * d + 1] = sb;
     }
@@ -280,10 +284,13 @@ static int launch_gram(const double* x, int64_t n, int d, int64_t ld, const doub
     if (ntiles < grid) grid = (int)(ntiles < 1 ? 1 : ntiles);
     size_t smem = ((size_t)d * (GP + 1) + GP) * sizeof(double);
     int maxo = (d * d + GT - 1) / GT;
+    if (d > GT) return ree_set_error(REE_E_UNSUPPORTED, "gram: d > 256 not supported");
 #define LAUNCH_GRAM(M)                                                                                  \
     do {                                                                                                \
+        const int slabs = (maxo + M - 1) / M;                                                           \
+        if (grid * slabs > 2 * ree_grid_ctas()) grid = 2 * ree_grid_ctas() / slabs;                     \
         cudaFuncSetAttribute(k_gram<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-        k_gram<M><<<grid, GT, smem, st>>>(x, n, d, ld, shift, w, g, partials);                          \
+        k_gram<M><<<dim3(grid, slabs), GT, smem, st>>>(x, n, d, ld, shift, w, g, partials);             \
     } while (0)
     if (maxo <= 1) LAUNCH_GRAM(1);
     else if (maxo <= 4) LAUNCH_GRAM(4);
@@ -291,7 +298,7 @@ static int launch_gram(const double* x, int64_t n, int d, int64_t ld, const doub
     else if (maxo <= 40) LAUNCH_GRAM(40);
     else if (maxo <= 64) LAUNCH_GRAM(64);
     else if (maxo <= 100) LAUNCH_GRAM(100);
-    else return ree_set_error(REE_E_UNSUPPORTED, "gram: d > 160 not supported");
+    else LAUNCH_GRAM(64);  // 160 < d <= 256: up to four slabs of 64 * 256 entries
 #undef LAUNCH_GRAM
     int rc = ree_check_launch("k_gram");
     if (rc) return rc;
@@ -299,10 +306,28 @@ static int launch_gram(const double* x, int64_t n, int d, int64_t ld, const doub
     return ree_check_launch("k_reduce_partials");
 }
 
-static int contract_grid(int64_t n) {
-    int64_t want = (n + TP - 1) / TP;
-    int cap = ree_grid_ctas();
-    return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+template <int MODE, int TP>
+static int launch_contract_tp(const StepArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)a.d * TP * sizeof(double);
+    if (smem > 200 * 1024) return ree_set_error(REE_E_UNSUPPORTED, "modular contraction: d too large (d <= 256)");
+    int64_t want = (a.n + TP - 1) / TP;
+    const int cap = ree_grid_ctas();
+    const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    static bool attr_done[64] = {false};  // the opt-in is per function and device, not per launch
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+        cudaFuncSetAttribute(k_contract<MODE, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_done[dev] = true;
+    }
+    k_contract<MODE, TP><<<grid, TP, smem, st>>>(a);
+    return ree_check_launch(MODE == 0 ? "ree_cbree_step(transform)" : "ree_cbree_maha(contract)");
+}
+
+template <int MODE>
+static int launch_contract(const StepArgs& a, cudaStream_t st) {
+    if ((size_t)a.d * TP_WIDE * sizeof(double) <= 200 * 1024) return launch_contract_tp<MODE, TP_WIDE>(a, st);
+    return launch_contract_tp<MODE, TP_NARROW>(a, st);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -352,14 +377,10 @@ extern "C" int ree_cbree_step(const double* x, double* x_new, int64_t n, int d, 
     if (lsf && lsf->kind != REE_LSF_EXTERNAL && !g_new) return ree_set_error(REE_E_BADARG, "ree_cbree_step: g_new is NULL");
     if (!sums && noise_mode == REE_NOISE_INJECT && d > 103) {
         // parity-mode (dense) factor beyond the DMMA transform's shared-memory budget: modular transform, no Gram
-        size_t smem = (size_t)d * TP * sizeof(double);
-        if (smem > 200 * 1024) return ree_set_error(REE_E_UNSUPPORTED, "ree_cbree_step: d too large");
         StepArgs a{};
         a.x = x; a.x_new = x_new; a.n = n; a.ld = ld; a.d = d; a.t = t; a.m_noise = m_noise; a.A = F; a.z = z;
         a.seed = seed; a.draw = draw; a.first = first_particle; a.e_new = e_new;
-        cudaFuncSetAttribute(k_contract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_contract<0><<<contract_grid(n), TP, smem, st>>>(a);
-        int rc = ree_check_launch("ree_cbree_step(transform)");
+        int rc = launch_contract<0>(a, st);
         if (rc) return rc;
         if (lsf && lsf->kind != REE_LSF_EXTERNAL) return ree_lsf_launch(lsf, x_new, n, ld, g_new, st);
         return 0;
@@ -408,15 +429,11 @@ extern "C" int ree_cbree_step(const double* x, double* x_new, int64_t n, int d, 
         }
         return 0;
     }
-    size_t smem = (size_t)d * TP * sizeof(double);
-    if (smem > 200 * 1024) return ree_set_error(REE_E_UNSUPPORTED, "ree_cbree_step: d too large");
     StepArgs a{};
     a.x = x; a.x_new = x_new; a.n = n; a.ld = ld; a.d = d; a.t = t; a.m_noise = m_noise; a.A = F;
     a.z = (noise_mode == REE_NOISE_INJECT) ? z : nullptr;
     a.seed = seed; a.draw = draw; a.first = first_particle; a.e_new = e_new;
-    cudaFuncSetAttribute(k_contract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_contract<0><<<contract_grid(n), TP, smem, st>>>(a);
-    int rc = ree_check_launch("ree_cbree_step(transform)");
+    int rc = launch_contract<0>(a, st);
     if (rc) return rc;
     const double* g_for_count = nullptr;
     if (lsf && lsf->kind != REE_LSF_EXTERNAL) {
@@ -448,15 +465,11 @@ extern "C" int ree_cbree_maha(const double* x, int64_t n, int d, int64_t ld, con
         return ree_mma_maha(x, n, d, ld, g, e, mean, Linv, logdet, sigma, beta, tgt_kind, wmax, logq, w,
                             workspace + ws_big_offset(), workspace + REE_WS_HEADER, sums, is4, st);
     if (!w) return ree_set_error(REE_E_BADARG, "ree_cbree_maha: this dimension needs the weight scratch vector w");
-    size_t smem = (size_t)d * TP * sizeof(double);
-    if (smem > 200 * 1024) return ree_set_error(REE_E_UNSUPPORTED, "ree_cbree_maha: d too large");
     StepArgs a{};
     a.x = x; a.n = n; a.ld = ld; a.d = d; a.A = Linv; a.g = g; a.e = e; a.mean = mean; a.logdet = logdet;
     a.wmax = wmax; a.sigma = sigma; a.beta = beta; a.tgt_kind = tgt_kind; a.logq = logq; a.w = w;
     a.ws = workspace; a.is4 = is4;
-    cudaFuncSetAttribute(k_contract<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_contract<1><<<contract_grid(n), TP, smem, st>>>(a);
-    int rc = ree_check_launch("ree_cbree_maha(contract)");
+    int rc = launch_contract<1>(a, st);
     if (rc) return rc;
     return launch_gram(x, n, d, ld, mean, w, nullptr, workspace, sums, st);
 }

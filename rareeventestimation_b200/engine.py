@@ -164,8 +164,19 @@ class Engine:
         if eng is None:
             eng = cls._instances[key] = Engine(torch.device("cuda", key))
             eng.comm = Comm(enabled=False)
+            eng._comm_given = False
             eng._load_nvector_kernels()
-        eng.comm = comm if comm is not None else Comm()
+        if comm is not None:  # an explicit communicator / group stays until another one is passed
+            eng.comm, eng._comm_given = comm, True
+        elif not eng._comm_given:
+            # default: follow torch.distributed's state.  The communicator is only rebuilt when that state changed, so
+            # callers inside a solve (DeviceLSF / StandardNormalEnergy / VMFNMixture on host arrays, user callbacks)
+            # never drop the connected peer mailboxes or trigger a collective re-connection on one rank only.
+            import torch.distributed as dist
+
+            live = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            if live != eng.comm.enabled or (live and eng.comm.world != dist.get_world_size()):
+                eng.comm = Comm()
         return eng
 
     def _load_nvector_kernels(self):

@@ -125,6 +125,9 @@ class Problem:
         if isinstance(arg, (int, np.integer)):
             assert hasattr(self, "sample_gen"), "Problem has no sample generator. Provide a sample as a ndarray!"
             if device:
+                if not is_standard_normal_problem(self):
+                    raise ValueError("set_sample(device=True) draws N(0, I) on the device: only for problems on the "
+                                     "standard normal space (NormalProblem); this problem has its own sample_gen")
                 d = self.sample.shape[-1]
                 self.sample = DeviceSample(int(arg), d, 0 if seed is None else int(seed))
             else:
@@ -148,6 +151,12 @@ class NormalProblem(Problem):
 
         super().__init__(lsf, StandardNormalEnergy(), sample_gen(sample_size), sample_gen=sample_gen,
                          prob_fail_true=prob_fail_true, mpp=mpp, eranataf_dist=dist, hints=hints, name=name)
+
+
+def is_standard_normal_problem(prob) -> bool:
+    """True if ``prob`` lives on the standard normal space: its sampler draws N(0, I), its energy is
+    -log N(x; 0, I) and SIS needs no U2X transform (solver.py:1144 ``transform_lsf=not isinstance(prob, NormalProblem)``)."""
+    return isinstance(prob, NormalProblem) or bool(getattr(prob.e_fun, "is_standard_normal", False))
 
 
 class Vectorizer:

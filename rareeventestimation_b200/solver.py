@@ -148,10 +148,21 @@ class CBREECache:
         new = CBREECache.__new__(CBREECache)
         for k, v in self.__dict__.items():
             if k in ("_engine", "_dev", "_stats"):
-                new.__dict__[k] = v  # device buffers are immutable once a cache is finished
+                new.__dict__[k] = v  # device buffers are shared copy-on-write (see own_device_buffers)
             else:
                 new.__dict__[k] = deepcopy(v, memo)
+        self._dev_shared = new._dev_shared = True
         return new
+
+    def own_device_buffers(self) -> None:
+        """Called before anything writes into ``_dev`` in place (the vMFNM redraw of the final importance sampling):
+        a cache that shares its HBM buffers with a deep copy gets private ones first."""
+        if getattr(self, "_dev_shared", False) and self._dev is not None:
+            old = self._dev
+            self._dev = Ensemble(old.X.clone(), old.n, old.d, old.ld, old.first,
+                                 old.g.clone() if old.g is not None else None,
+                                 old.e.clone() if old.e is not None else None)
+            self._dev_shared = False
 
 
 def flatten_cache_list(cache_list: list, attrs=None, lazy_bytes=64 << 20) -> dict:
@@ -315,6 +326,10 @@ class CBREE(Solver):
             raise NotImplementedError(f"mixture_model={self.mixture_model!r}: CBREE knows 'GM' and 'vMFNM' (solver.py:186)")
         self._eng = Engine.get()
         self._prob = prob
+        d_max = int(self._eng.lib.ree_max_dim())
+        if prob.sample is not None and int(prob.sample.shape[-1]) > d_max:
+            raise ValueError(f"rareeventestimation_b200 supports d <= {d_max}; the sample has d = "
+                             f"{int(prob.sample.shape[-1])} (the d x d factorisations run in one CTA)")
         lsf = prob.lsf
         self._dev_lsf_obj = lsf if isinstance(lsf, DeviceLSF) else None
         self._device_energy = getattr(prob.e_fun, "is_standard_normal", False)
@@ -377,13 +392,13 @@ class CBREE(Solver):
         d = dev.d
         kind = self._tgt_kind()
         slen = d + d * d + 2
-        # packed result buffer: [mean d | cov d*d | m_w d | C_w d*d | stats 4 | is4 4 | ess4 4 | sums_u tail 2 | sums_w tail 2]
-        res = eng.empty(2 * d + 2 * d * d + 16)
+        # packed result buffer: [mean d | cov d*d | m_w d | C_w d*d | stats 8 | is4 4 | ess4 4 | sums_u tail 2 | sums_w tail 2]
+        res = eng.empty(2 * d + 2 * d * d + 20)
         mean, cov = res[0:d], res[d:d + d * d]
         m_w, C_w = res[d + d * d:2 * d + d * d], res[2 * d + d * d:2 * d + 2 * d * d]
         o = 2 * d + 2 * d * d
-        stats, is4, ess4 = res[o:o + 4], res[o + 4:o + 8], res[o + 8:o + 12]
-        tails = res[o + 12:o + 16]
+        stats, is4, ess4 = res[o:o + 8], res[o + 8:o + 12], res[o + 12:o + 16]
+        tails = res[o + 16:o + 20]
         L, Linv = eng.empty(d * d), eng.empty(d * d)
         if eng.path(d) == 2 and sums_ready is None:
             # split path: log-weights + softmax shift, both Grams in one pass, factorisation, Mahalanobis / IS pass
@@ -422,11 +437,12 @@ class CBREE(Solver):
         cache.ens_cov = host[d:d + d * d].reshape(d, d).copy()
         cache.weighted_mean = host[d + d * d:2 * d + d * d].copy()
         cache.weighted_cov = host[2 * d + d * d:o].reshape(d, d).copy()
-        st, i4, e4, tl = host[o:o + 4], host[o + 4:o + 8], host[o + 8:o + 12], host[o + 12:o + 16]
+        st, i4, e4, tl = host[o:o + 8], host[o + 8:o + 12], host[o + 12:o + 16], host[o + 16:o + 20]
         cache._stats = dict(C_w=C_w)  # view into `res`; the O(N) scratch (w, L, Linv) is released here
         cache._vmfn_density = model is not None
         cache._chol_info = int(st[1])
         cache._min_pivot, cache._max_diag = float(st[2]), float(st[3])
+        cache._tr_inv, cache._norm_inf = float(st[4]), float(st[5])
         cache.num_failed = float(tl[0])
         n_tot = float(tl[1])
         cache._is4 = i4.copy()
@@ -440,22 +456,78 @@ class CBREE(Solver):
         """cvar_is_weights (solver.py:683-686) and the IS estimate (843-846) from the sweep-2 sums."""
         self._check_density(cache)
         cache.cvar_is_weights = cvar_from(cache._is4)
-        cache.estimate = self._estimate_of(cache)
+        cache.estimate = self._estimate_of(cache, in_loop=True)
 
-    def _estimate_of(self, cache: CBREECache) -> float:
+    def _estimate_of(self, cache: CBREECache, in_loop=False) -> float:
+        if not in_loop and not getattr(self, "_device_energy", True) and cache._dev is not None:
+            return self._estimate_standard_target(cache)  # (inside the loop the reference computes no estimate at all)
         R, s1 = float(cache._is4[0]), float(cache._is4[1])
         if s1 == 0.0 or not math.isfinite(R):
             return 0.0
         return math.exp(R) * s1 / cache._n_total
 
+    def _estimate_standard_target(self, cache: CBREECache) -> float:
+        """The final estimate always uses the standard normal density as target (``gaussian_logpdf``, solver.py:843),
+        whatever ``prob.e_fun`` is; cvar_is_weights uses ``e_fun`` (solver.py:683-686).  With a user-supplied energy
+        the two differ, and the estimate is redone with |x|^2/2 + d/2 log 2pi: density of the fit (or of the fitted
+        model) per particle on the device, the mean of the IS weights on the host (user-energy problems are bridged
+        through the host anyway)."""
+        eng, dev = self._eng, cache._dev
+        d, kind = dev.d, self._tgt_kind()
+        logq = eng.empty(dev.ld)
+        model = self._fitted_model(cache)
+        if model is not None and hasattr(model, "logpdf_device"):
+            model.logpdf_device(eng, dev, logq=logq)
+            lq = eng.download_vector(logq, dev.n)
+        elif model is not None:
+            lq = np.asarray(model.logpdf(cache.ensemble), dtype=np.float64).reshape(-1)
+        else:
+            slen = d + d * d + 2
+            sums_u, sums_w = eng.empty(slen), eng.empty(slen)
+            eng.ensemble_sums(dev, None, sums_u)
+            mean, cov, L, Linv, stats = eng.empty(d), eng.empty(d * d), eng.empty(d * d), eng.empty(d * d), eng.empty(8)
+            eng.moments_chol(sums_u, None, d, 1, False, mean, cov, L, Linv, stats)
+            is4, ess4 = eng.empty(4), eng.empty(4)
+            if eng.path(d) == 2:
+                eng.cbree_maha(dev, mean, Linv, stats[0:1], cache.sigma, cache.beta, kind, None, None, is4, logq=logq)
+            else:
+                eng.reduce_ess(dev, cache.sigma, cache.beta, kind, out=ess4)
+                eng.cbree_maha(dev, mean, Linv, stats[0:1], cache.sigma, cache.beta, kind, ess4[0:1], sums_w, is4,
+                               logq=logq)
+            lq = eng.download_vector(logq, dev.n)
+        e_std = eng.download_vector(eng.energy(dev), dev.n)
+        g = eng.download_vector(dev.g, dev.n)
+        with np.errstate(all="ignore"):
+            part = np.sum(np.exp(-e_std - lq) * (g <= 0))  # utilities.py:43-45
+        part = eng.comm.allreduce_sum_(eng.to_device(np.array([part]))).item() if eng.comm.enabled else float(part)
+        return part / cache._n_total
+
+    _PSD_MSG = "When `allow_singular is False`, the input matrix must be symmetric positive definite."
+
     def _check_density(self, cache: CBREECache):
-        """SciPy's multivariate_normal refuses (numerically) singular covariances (SURVEY.md 7.2);
-        the factorisation reports the same condition through its pivots."""
+        """SciPy's multivariate_normal refuses numerically singular covariances: its ``_PSD`` raises
+        LinAlgError if an eigenvalue is <= eps = 1e6 * eps_f64 * max|lambda| and ValueError if one is < -eps.  The
+        factorisation brackets both extreme eigenvalues (min pivot >= lambda_min >= 1 / trace(cov^-1), max diag <=
+        lambda_max <= |cov|_inf): singular for sure if min pivot <= thr * max diag, regular for sure if
+        1 / trace(cov^-1) > thr * |cov|_inf; only in between are the eigenvalues themselves computed (host, d x d)."""
         if getattr(cache, "_vmfn_density", False):
             return  # no Gaussian fit behind this cache's importance density
-        if cache._chol_info != 0 or not (cache._min_pivot > 2.220446049250313e-10 * cache._max_diag):
-            raise np.linalg.LinAlgError(
-                "When `allow_singular is False`, the input matrix must be symmetric positive definite.")
+        thr = 1e6 * np.finfo(np.float64).eps
+        if cache._chol_info == 0 and cache._min_pivot > thr * cache._max_diag:
+            tr_inv = getattr(cache, "_tr_inv", 0.0)
+            if tr_inv > 0.0 and math.isfinite(tr_inv) and 1.0 / tr_inv > thr * cache._norm_inf:
+                return
+        elif cache._chol_info == 0 and math.isfinite(cache._min_pivot) and cache._min_pivot > 0:
+            raise np.linalg.LinAlgError(self._PSD_MSG)  # positive definite in fp64, singular by SciPy's threshold
+        cov = np.asarray(cache.ens_cov, dtype=np.float64)
+        if not np.isfinite(cov).all():
+            raise ValueError("array must not contain infs or NaNs")  # scipy _PSD -> eigh(check_finite=True)
+        s = np.linalg.eigvalsh(cov)
+        eps = thr * np.max(np.abs(s))
+        if np.min(s) < -eps:
+            raise ValueError("The input matrix must be symmetric positive semidefinite.")
+        if np.any(s <= eps):
+            raise np.linalg.LinAlgError(self._PSD_MSG)
 
     def _compute_weights_check(self, cache: CBREECache):
         if not np.isfinite(cache.weighted_cov).all():  # solver.py:637-638
@@ -641,7 +713,7 @@ class CBREE(Solver):
             eng.cbree_step(src, dst, t, m_noise_d, F, step_desc, shift_u, sums, z=zdev)
         else:
             F = eng.empty(d * d)
-            fstats = eng.empty(4)
+            fstats = eng.empty(8)
             eng.chol_scaled(cache._stats["C_w"] if not cache._cw_dirty else eng.to_device(cache.weighted_cov), d,
                             scale, F, fstats)
             self._step_draws += 1
@@ -781,9 +853,14 @@ class CBREE(Solver):
         produced; they are recomputed only if a callback replaced N-sized fields."""
         if cache.sync_to_device():
             self._refresh(cache)
+        model = self._fitted_model(cache)
+        if model is not None and not getattr(cache, "_vmfn_density", False) and cache._dev is not None:
+            # a callback installed a fitted model without touching the N-sized fields: its density replaces the fit
+            self._model_is_stats(cache, model)
         if self.mixture_model == "vMFNM" and not cache.mixture_model.fitted and cache._dev is not None:
             # solver.py:828-836: fit the model to the cache's ensemble, replace the ensemble by a sample of the model,
             # re-evaluate the limit state there; the estimate uses the model's density
+            cache.own_device_buffers()
             cache.mixture_model = self._vmfn_redraw(cache._dev)
             cache._host.pop("ensemble", None)
             cache._host.pop("lsf_evals", None)
@@ -798,9 +875,38 @@ class CBREE(Solver):
         self._check_density(cache)
         cache.estimate = self._estimate_of(cache)
 
+    def _fitted_model(self, cache: CBREECache):
+        """The cache's mixture model if it is fitted (then its density is the importance density, solver.py:825-826:
+        the `callback_vmfnm` pattern of dimension_study.py:12-25), else None."""
+        model = cache.mixture_model
+        return model if getattr(model, "fitted", False) else None
+
+    def _model_is_stats(self, cache: CBREECache, model) -> None:
+        """IS statistics of a cache under a fitted model's density: [max r, sum 1[g<=0] exp(r-max), sum (..)^2, #finite r],
+        r = -e - log q (solver.py:683-686, 843-846).  Engine models evaluate on the device; any other object with the
+        reference's ``logpdf(sample)`` interface is *user* code and goes through the host bridge like a Python LSF."""
+        eng, dev = self._eng, cache._dev
+        if hasattr(model, "logpdf_device"):
+            is4 = eng.empty(4)
+            model.logpdf_device(eng, dev, is4=is4)
+            cache._is4 = eng.fetch(is4)
+        else:
+            r = -np.asarray(cache.e_fun_evals) - np.asarray(model.logpdf(cache.ensemble), dtype=np.float64).reshape(-1)
+            fin = np.isfinite(r)
+            mult = (np.asarray(cache.lsf_evals) <= 0)[fin].astype(np.float64)
+            top = np.max(r[fin]) if fin.any() else -math.inf
+            w = np.exp(r[fin] - top) * mult
+            cache._is4 = np.array([top, w.sum(), (w * w).sum(), float(fin.sum())])
+        cache._vmfn_density = True
+
     def _refresh(self, cache: CBREECache):
         sig, bet = cache.sigma, cache.beta
-        self._post_ensemble(cache)
+        model = self._fitted_model(cache)
+        if model is not None:
+            model._is4_dev = None  # (statistics of an earlier redraw do not describe the replaced ensemble)
+        self._post_ensemble(cache, model=model if hasattr(model, "logpdf_device") else None)
+        if model is not None and not hasattr(model, "logpdf_device"):
+            self._model_is_stats(cache, model)
         cache.sigma, cache.beta = sig, bet
 
     def _compute_weighted_estimates(self, cache_list: list) -> None:
@@ -819,9 +925,12 @@ class CBREE(Solver):
     # ------------------------------------------------------------------ #
     # main loop
     # ------------------------------------------------------------------ #
-    def start(self, prob: Problem) -> list:
+    def start(self, prob: Problem, recycle: bool = False) -> list:
         """Everything ``solve`` does before its loop (solver.py:375-409): upload / evaluate the initial ensemble,
-        initial weights, initial step size.  Returns the cache list."""
+        initial weights, initial step size.  Returns the cache list.  ``recycle=True`` is the caller's promise not to
+        keep references to caches that left the observation window: their HBM buffers are then reused by later steps
+        (what ``solve`` does with its private list)."""
+        self._owns_cache_list = bool(recycle)
         self._setup(prob)
         dev = self._initial_ensemble(prob)
         if not self.save_history:  # the window's HBM buffers, allocated once and recycled by _retire
@@ -870,11 +979,10 @@ class CBREE(Solver):
         return True
 
     def _retire(self, cache: CBREECache):
-        """A cache left the observation window: its HBM buffers go back to the engine's free list unless somebody
-        else (a callback, the caller) still holds the cache."""
-        import sys
-
-        if sys.getrefcount(cache) <= 3 and not self.callback:  # this frame's arg + local + getrefcount's own
+        """A cache left the observation window.  Its HBM buffers are recycled only inside :meth:`solve` -- there the
+        cache list never leaves the solver before it is pruned (no callback, no ``return_caches``); users of the
+        ``start`` / ``advance`` API hold the list themselves, so nothing they may still reference is reused."""
+        if getattr(self, "_owns_cache_list", False) and not self.callback and not self.return_caches:
             dev, cache._dev = cache._dev, None
             self._eng.release(dev)
 
@@ -887,17 +995,25 @@ class CBREE(Solver):
 
     def solve(self, prob: Problem) -> Solution:
         """Estimate the rare event of `prob` (solver.py:365-503)."""
-        cache_list = self.start(prob)
-        while not cache_list[-1].converged and cache_list[-1].iteration <= self.num_steps:
-            if not self.advance(cache_list):
-                break
-        return self.finish(cache_list)
+        try:  # the list below is private to this call: retired caches' buffers are recycled
+            cache_list = self.start(prob, recycle=True)
+            while not cache_list[-1].converged and cache_list[-1].iteration <= self.num_steps:
+                if not self.advance(cache_list):
+                    break
+            return self.finish(cache_list)
+        finally:
+            self._owns_cache_list = False
 
     def _refresh_after_callback(self, cache: CBREECache):
         """A callback replaced the ensemble / evaluations: redo the moments the next step needs.  The
         reference keeps the *old* weighted mean/cov in that case (solver.py:441, 693), so do we."""
         m_w, C_w, cv = cache.weighted_mean, cache.weighted_cov, cache.cvar_is_weights
-        self._post_ensemble(cache)
+        model = self._fitted_model(cache)
+        if model is not None:
+            model._is4_dev = None  # (statistics of an earlier redraw do not describe the callback's ensemble)
+        self._post_ensemble(cache, model=model if hasattr(model, "logpdf_device") else None)
+        if model is not None and not hasattr(model, "logpdf_device"):
+            self._model_is_stats(cache, model)
         cache.weighted_mean, cache.weighted_cov, cache.cvar_is_weights = m_w, C_w, cv
         cache._cw_dirty = True
 

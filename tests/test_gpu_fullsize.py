@@ -109,7 +109,7 @@ def test_full_size_properties(eng):
     # (eigenvalues of F F^T >= 0.5 => variance >= 0.86 ... the ratio p/q has finite variance), so mean(p/q) = 1 + O(N^-1/2)
     so = _sums(eng, out)
     slen = D + D * D + 2
-    mean_d, cov_d, L, Linv, stats = eng.empty(D), eng.empty(D * D), eng.empty(D * D), eng.empty(D * D), eng.empty(4)
+    mean_d, cov_d, L, Linv, stats = eng.empty(D), eng.empty(D * D), eng.empty(D * D), eng.empty(D * D), eng.empty(8)
     sums_dev = eng.to_device(so)
     eng.moments_chol(sums_dev, None, D, 1, False, mean_d, cov_d, L, Linv, stats)
     assert stats.cpu().numpy()[1] == 0

@@ -242,8 +242,34 @@ class ReplayRng:
         return self.Z
 
 
+# d = 152, 200, 256: modular SIMT kernels (k_contract / k_gram, csrc/ree_step.cu) -- toy_problems.py:95-101 goes up to 200;
+# 200 < d runs the narrow contraction tile and the global-memory factorisation (d > 160), 256 is the largest dimension
 CASES = [("affine", 4, 2000), ("oscillator", 6, 3000), ("affine", 100, 1500), ("convex", 2, 1000),
-         ("affine", 37, 1111), ("affine", 64, 1200), ("affine", 103, 900)]
+         ("affine", 37, 1111), ("affine", 64, 1200), ("affine", 103, 900), ("affine", 150, 700), ("affine", 152, 600),
+         ("affine", 200, 700), ("affine", 256, 600)]
+
+
+def device_weights(eng, solver, dev, sigma, beta):
+    """Normalised per-particle weights as the device computed them (solver.py:629-632): from the log-weight vector the
+    split path's Gram kernel consumes (ree_reduce_ess, a_out) and -- on the fused / small-d / modular paths -- from the
+    weight vector the Mahalanobis sweep itself wrote (ree_cbree_maha, w)."""
+    n, d, kind = dev.n, dev.d, solver._tgt_kind()
+    ess4, a = eng.empty(4), eng.empty(dev.ld)
+    eng.reduce_ess(dev, sigma, beta, kind, out=ess4, a_out=a)
+    t4 = ess4.cpu().numpy()
+    av = a[:n].cpu().numpy()
+    with np.errstate(all="ignore"):
+        out = [np.where(np.isfinite(av), np.exp(av - t4[0]), 0.0) / t4[1]]
+    if eng.path(d) != 2:
+        slen = d + d * d + 2
+        sums_u, sums_w = eng.empty(slen), eng.empty(slen)
+        eng.ensemble_sums(dev, None, sums_u)
+        mean, cov, L, Linv, stats = eng.empty(d), eng.empty(d * d), eng.empty(d * d), eng.empty(d * d), eng.empty(8)
+        eng.moments_chol(sums_u, None, d, 1, False, mean, cov, L, Linv, stats)
+        w, is4 = eng.empty(dev.ld), eng.empty(4)
+        eng.cbree_maha(dev, mean, Linv, stats[0:1], sigma, beta, kind, ess4[0:1], sums_w, is4, w=w)
+        out.append(w[:n].cpu().numpy() / t4[1])
+    return out
 
 
 def make_problem(ree, kind, d):
@@ -303,7 +329,13 @@ def test_teacher_forced_steps(ree, eng, kind, d, n):
         want_est = co.is_estimate(-nx.e, nx.logq, nx.g)
         assert new.estimate == pytest.approx(want_est, rel=1e-9, abs=1e-300)
         assert new.num_failed == np.sum(nx.g <= 0)
-        # weights themselves (unnormalised on the device): compare after normalisation
+        # the weights themselves (unnormalised on the device): compared after normalisation, every weight relative to
+        # the largest one and the non-negligible ones also relative to themselves
+        for w_dev in device_weights(eng, solver, new._dev, st.sigma, st.beta):
+            rel_close(w_dev, nx.weights, what=f"weights it{k}")
+            big = nx.weights > 1e-30 * nx.weights.max()
+            np.testing.assert_allclose(w_dev[big], nx.weights[big], rtol=1e-9)
+            assert abs(w_dev.sum() - 1) < 1e-12
         checked += 1
     assert checked >= 3
 

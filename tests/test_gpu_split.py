@@ -98,7 +98,7 @@ def test_split_moments_and_maha_match_numpy(eng, n, d):
     # factorise + Mahalanobis / IS pass
     if n <= d:
         return
-    mean, cov, L, Linv, stats = eng.empty(d), eng.empty(d * d), eng.empty(d * d), eng.empty(d * d), eng.empty(4)
+    mean, cov, L, Linv, stats = eng.empty(d), eng.empty(d * d), eng.empty(d * d), eng.empty(d * d), eng.empty(8)
     eng.moments_chol(eng.to_device(su), shift, d, 1, False, mean, cov, L, Linv, stats)
     np.testing.assert_allclose(cov.cpu().numpy().reshape(d, d), np.cov(X, rowvar=False), rtol=0, atol=1e-11)
     is4, logq = eng.empty(4), eng.empty(ens.ld)

@@ -21,7 +21,7 @@ def cbree_iterations(prob, n, d, steps=6, warm=2, **kw):
     prob.sample = DeviceSample(n, d, seed=0x5EED)
     solver = ree.CBREE(seed=1, convergence_check=False, divergence_check=False, quiet=True, num_steps=10**9, **kw)
     t0 = time.perf_counter()
-    cl = solver.start(prob)
+    cl = solver.start(prob, recycle=True)
     torch.cuda.synchronize()
     t_start = time.perf_counter() - t0
     for _ in range(warm):

@@ -41,7 +41,7 @@ for rep in range(2):
     print(f"rep {rep}")
     torch.cuda.synchronize()
     t00 = t0 = time.perf_counter()
-    cl = solver.start(prob)
+    cl = solver.start(prob, recycle=True)
     t0 = tick("start (upload, g/e, weights, h0)", t0)
     for i in range(args.steps):
         solver.advance(cl)

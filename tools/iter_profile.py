@@ -51,7 +51,7 @@ else:
 prob.sample = DeviceSample(args.n, args.d, seed=0x5EED)
 extra = dict(resample=True, mixture_model="vMFNM") if args.resample else {}
 solver = ree.CBREE(seed=1, convergence_check=False, divergence_check=False, quiet=True, num_steps=10**9, **extra)
-cl = solver.start(prob)
+cl = solver.start(prob, recycle=True)
 for _ in range(3):
     solver.advance(cl)
 torch.cuda.synchronize()

@@ -27,7 +27,7 @@ eng.lsf_eval(lsf, X, out=X.g)
 eng.energy(X, out=X.e)
 slen = d + d * d + 2
 sums, sums_w = eng.empty(slen), eng.empty(slen)
-mean, cov, L, Linv, stats = eng.empty(d), eng.empty(d * d), eng.empty(d * d), eng.empty(d * d), eng.empty(4)
+mean, cov, L, Linv, stats = eng.empty(d), eng.empty(d * d), eng.empty(d * d), eng.empty(d * d), eng.empty(8)
 ess4, is4 = eng.empty(4), eng.empty(4)
 m_noise = eng.zeros(d)
 F = eng.empty(d * d)
