@@ -285,24 +285,42 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k
 
 // ---------------------------------------------------------------------------------------
 // Table-driven, branch-free fp64 Box-Muller.
-// DMMA and DFMA share one fp64 pipe on B200 (tools/fp64_pipe_share.cu), so every fp64 instruction spent on noise is
-// taken from the tensor work: the transcendental parts use small tables (bm_tables.cuh, 4 KB) + short polynomials
-// (~38 fp64 instructions per pair instead of ~190 for log/sqrt/sincospi of libdevice).  The uniforms are 53-bit
-// integers, so all arguments are normal numbers in fixed ranges: no special cases, no slow paths.
-// Accuracy (vs long double, 3e6 inputs): ln <= 4.2 ulp, sqrt <= 1.5 ulp, sin/cos <= 1.1e-16 absolute.
+// DMMA and DFMA share one fp64 pipe on B200 (tools/fp64_pipe_share.cu), and under a saturating DMMA stream every
+// DEPENDENT fp64 instruction of another warp costs ~28 cycles (tools/fp64_mix.cu): what counts is the number of fp64
+// instructions on the critical path of a pair.  27 fp64 instructions per pair, no int<->fp conversions:
+//   radius^2  w = -2 ln u1: exponent / mantissa of the 53-bit integer by shifts (no I2F), table of (1/m_i, -2 ln m_i)
+//             on 128ths of [1, 2], table of k * 2 ln 2, degree-5 polynomial of -2 log1p(r), |r| <= 2^-8     (7)
+//   radius    MUFU.RSQ64H seed + one cubic correction                                                          (5)
+//   angle     theta from the integer remainder by the 2^52 magic-number trick inside one FMA, Taylor polynomials on
+//             |theta| <= pi/128, rotation of the table entry already scaled by the radius                      (15)
+// The uniforms are 53-bit integers, so all arguments are normal numbers in fixed ranges: no special cases, no slow
+// paths.  Accuracy against long double: |dz| <= 4e-15 absolute (tests/test_gpu_parity.py compares with NumPy).
 // ---------------------------------------------------------------------------------------
 #include "bm_tables.cuh"
 
-struct BmTableGlobal {  // tables read through the read-only path (modular kernels)
+#define BM_TWO_LN2 1.3862943611198906
+#define BM_SMEM_DOUBLES (BM_TABLE_DOUBLES + 54 + 2)  // staged tables: log (x -2) | trig | k * 2 ln 2, k = 0..53 | pad
+
+// copy the tables into shared memory in the form the pair generator reads them (all threads of the CTA call it)
+__device__ __forceinline__ void bm_stage_tables(double* dst, int tid, int nthreads) {
+    for (int idx = tid; idx < BM_TABLE_DOUBLES; idx += nthreads) {
+        const double v = BM_TABLE[idx];
+        dst[idx] = (idx < 258 && (idx & 1)) ? -2.0 * v : v;  // T_i -> -2 T_i (exact)
+    }
+    for (int k = tid; k < 56; k += nthreads) dst[BM_TABLE_DOUBLES + k] = k < 54 ? (double)k * BM_TWO_LN2 : 0.0;
+}
+
+struct BmTableGlobal {  // tables read through the read-only path (modular kernels); same values as the staged form
     __device__ __forceinline__ double2 log_entry(int i) const {
-        return make_double2(__ldg(BM_TABLE + 2 * i), __ldg(BM_TABLE + 2 * i + 1));
+        return make_double2(__ldg(BM_TABLE + 2 * i), -2.0 * __ldg(BM_TABLE + 2 * i + 1));
     }
     __device__ __forceinline__ double2 trig_entry(int j) const {
         return make_double2(__ldg(BM_TABLE + 258 + 2 * j), __ldg(BM_TABLE + 258 + 2 * j + 1));
     }
+    __device__ __forceinline__ double e_entry(int k) const { return (double)k * BM_TWO_LN2; }
 };
 
-struct BmTableShared {  // tables staged in shared memory (fused sweep kernel); addr = 32-bit shared address
+struct BmTableShared {  // tables staged in shared memory by bm_stage_tables; addr = 32-bit shared address
     uint32_t addr;
     __device__ __forceinline__ double2 log_entry(int i) const {
         double2 v;
@@ -314,61 +332,66 @@ struct BmTableShared {  // tables staged in shared memory (fused sweep kernel); 
         asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr + 2064u + 16u * (uint32_t)j));
         return v;
     }
+    __device__ __forceinline__ double e_entry(int k) const {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr + 4112u + 8u * (uint32_t)k));
+        return v;
+    }
 };
 
 template <class Tab>
 __device__ __forceinline__ double bm_neg2log(uint64_t k53, const Tab& tab) {
-    // -2*ln(u), u = (k53+1)*2^-53 in (0,1]:  x = k53+1 = 2^e * m, m in [1,2), i = round((m-1)*128),
-    // m = (1/inv_i)(1 + r) with r = m*inv_i - 1 (one fma, |r| <= 2^-8)  =>  ln m = T_i + log1p(r)
-    const double x = (double)(long long)(k53 + 1);  // exact, in [1, 2^53]
-    const long long bits = __double_as_longlong(x);
-    const long long mant = bits & 0x000fffffffffffffLL;
+    // w = -2 ln(u), u = x * 2^-53, x = min(k53 + 1, 2^53 - 1) in [1, 2^53):  x = 2^e * m, m in [1, 2),
+    // i = round((m - 1) * 128), m = m_i (1 + r) with r = m / m_i - 1 (one fma, |r| <= 2^-8):
+    //   w = (53 - e) 2 ln 2 - 2 ln m_i - 2 log1p(r);  for i >= BM_LOG_I0 the table holds ln(m_i / 2) and e counts one more
+    //   (keeps w = -2 log1p(r) exact in the last octave, where the other two terms would cancel).
+    const uint64_t x = k53 + (k53 != 0x1fffffffffffffULL ? 1ULL : 0ULL);
+    const int lz = __clzll((long long)x);             // 63 - e
+    const uint64_t mant = ((x << lz) >> 11) & 0x000fffffffffffffULL;
     const int i = (int)(((mant >> 44) + 1) >> 1);
-    const int e = (int)(bits >> 52) - (1023 + 53) + (i >= BM_LOG_I0 ? 1 : 0);
-    const double m = __longlong_as_double(mant | 0x3ff0000000000000LL);
-    const double2 t = tab.log_entry(i);
+    const int ke = lz - 10 - (i >= BM_LOG_I0 ? 1 : 0);  // 53 - e (- 1)
+    const double m = __longlong_as_double((long long)(mant | 0x3ff0000000000000ULL));
+    const double2 t = tab.log_entry(i);                 // (1 / m_i, -2 ln m_i [+ 2 ln 2])
+    const double base = tab.e_entry(ke) + t.y;
     const double r = fma(m, t.x, -1.0);
-    double p = -1.0 / 6.0;
-    p = fma(p, r, 0.2);
-    p = fma(p, r, -0.25);
-    p = fma(p, r, 1.0 / 3.0);
-    p = fma(p, r, -0.5);
-    p = fma(p, r, 1.0);
-    p = p * r;
-    const double ed = (double)e;
-    const double ln_u = fma(ed, 0.6931471803691238, fma(ed, 1.9082149292705877e-10, t.y + p));
-    return -2.0 * ln_u;
+    double q = fma(r, -0.4, 0.5);                       // -2 log1p(r) = r (-2 + r (1 + r (-2/3 + r (1/2 - 2/5 r))))
+    q = fma(q, r, -2.0 / 3.0);
+    q = fma(q, r, 1.0);
+    q = fma(q, r, -2.0);
+    return fma(q, r, base);
 }
 
 __device__ __forceinline__ double bm_sqrt(double w) {
-    // sqrt(w), w in [0, 74]
-    const float wf = fmaxf((float)w, 1e-30f);
-    const double rs = (double)rsqrtf(wf);
-    double r = w * rs;
-    const double h = 0.5 * rs;
-    r = fma(h, fma(-r, r, w), r);
-    r = fma(h, fma(-r, r, w), r);
-    return r;
+    // sqrt(w), w in [2.2e-16, 74]: hardware seed of 1/sqrt(w) (~2^-21) + one cubic correction (-> ~2^-60)
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(w));
+    const double t = w * y0;
+    const double e = fma(-t, y0, 1.0);
+    return fma(t * e, fma(e, 0.375, 0.5), t);
 }
 
+// (r cos alpha, r sin alpha), alpha = 2 pi b53 2^-53: j = nearest 128th of the circle, theta = alpha - 2 pi j / 128 in
+// [-pi/128, pi/128], angle addition with short Taylor polynomials on the table entry scaled by r
 template <class Tab>
-__device__ __forceinline__ void bm_sincos2pi(uint64_t b53, const Tab& tab, double& sn, double& cs) {
-    // sin / cos of alpha = 2*pi*b53*2^-53: j = nearest 128th of the circle, theta = alpha - 2 pi j/128 in
-    // [-pi/128, pi/128], angle addition with short Taylor polynomials
+__device__ __forceinline__ void bm_rotate(uint64_t b53, double r, const Tab& tab, double& zc, double& zs) {
     const long long j = (long long)((b53 + (1ULL << 45)) >> 46);
-    const long long rem = (long long)b53 - (j << 46);
-    const double th = (double)rem * (6.283185307179586476925286766559 * 1.1102230246251565e-16);  // 2 pi 2^-53
+    const long long rem = (long long)b53 - (j << 46);   // |rem| <= 2^45
+    // theta = rem * 2 pi 2^-53 in ONE fma: (2^52 + 2^51 + rem) as a double is exact, the subtraction happens inside
+    const double dm = __longlong_as_double(0x4338000000000000LL + rem);
+    const double C = 6.283185307179586476925286766559 * 1.1102230246251565e-16;  // 2 pi 2^-53
+    const double th = fma(dm, C, -6755399441055744.0 * C);
     const double t2 = th * th;
     double ps = fma(t2, -1.0 / 5040.0, 1.0 / 120.0);
     ps = fma(ps, t2, -1.0 / 6.0);
-    ps = fma(ps, t2, 1.0);
-    ps = ps * th;                       // sin(theta)
+    ps = ps * t2;
+    const double sn = fma(th, ps, th);                  // sin(theta)
     double pc = fma(t2, -1.0 / 720.0, 1.0 / 24.0);
     pc = fma(pc, t2, -0.5);
-    pc = pc * t2;                       // cos(theta) - 1
-    const double2 sc = tab.trig_entry((int)(j & 127));
-    sn = sc.x + fma(sc.y, ps, sc.x * pc);
-    cs = sc.y + fma(-sc.x, ps, sc.y * pc);
+    pc = pc * t2;                                       // cos(theta) - 1
+    const double2 sc = tab.trig_entry((int)(j & 127));  // (sin, cos) of 2 pi j / 128
+    const double a = r * sc.x, b = r * sc.y;
+    zs = fma(b, sn, fma(a, pc, a));
+    zc = fma(-a, sn, fma(b, pc, b));
 }
 
 // two standard normals for (particle, pair, draw)
@@ -380,11 +403,7 @@ __device__ __forceinline__ void philox_normal_pair(uint64_t seed, uint64_t parti
     // u1 = (a53+1)*2^-53 in (0,1] ; u2 = b53*2^-53 in [0,1)
     const uint64_t a53 = (((uint64_t)c[0] << 32) | c[1]) >> 11;
     const uint64_t b53 = (((uint64_t)c[2] << 32) | c[3]) >> 11;
-    const double r = bm_sqrt(bm_neg2log(a53, tab));
-    double sn, cs;
-    bm_sincos2pi(b53, tab, sn, cs);
-    z0 = r * cs;
-    z1 = r * sn;
+    bm_rotate(b53, bm_sqrt(bm_neg2log(a53, tab)), tab, z0, z1);
 }
 
 __device__ __forceinline__ void philox_normal_pair(uint64_t seed, uint64_t particle, uint32_t pair, uint64_t draw,

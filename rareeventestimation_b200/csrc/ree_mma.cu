@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_sweep(const MmaArgs a) {
     }
     for (int idx = tid; idx < 2 * ROWS * S; idx += MT) Ys[idx] = 0.0;
     if (SWEEP == 1)
-        for (int idx = tid; idx < BM_TABLE_DOUBLES; idx += MT) bm[idx] = BM_TABLE[idx];
+        bm_stage_tables(bm, tid, MT);
 
     constexpr int WG = NW / KS;
     const int grp = warp / WG, wi = warp % WG;
@@ -489,7 +489,7 @@ template <int SWEEP, int NTB, int NW, int MAXM, int KS, bool EXACT, bool TRI>
 static int launch_k(const MmaArgs& a, int grid, cudaStream_t st) {
     constexpr int P = NW * 8, S = P + 8, ROWS = 8 * NTB;
     constexpr size_t smem = ((size_t)lf_doubles<NTB, TRI>() + 2 * ROWS * S + 3 * 8 * NTB +
-                             (SWEEP == 1 ? BM_TABLE_DOUBLES + 2 : 0)) * sizeof(double);
+                             (SWEEP == 1 ? BM_SMEM_DOUBLES : 0)) * sizeof(double);
     static_assert(smem <= 227 * 1024, "shared memory budget");
     auto kern = k_sweep<SWEEP, NTB, NW, MAXM, KS, EXACT, TRI>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -126,14 +126,14 @@ __global__ void __launch_bounds__(SM_T, SG_CTAS) k_small_step_g(const SmallArgs 
     __shared__ double sF[D * D], sm[D], ss[D], sc[D];
     __shared__ double tiles[(SM_T / 32) * 8 * SG_S];
     __shared__ double stage[(SM_T / 32) * 64];
-    __shared__ double bm[BM_TABLE_DOUBLES];
+    __shared__ double bm[BM_SMEM_DOUBLES];
     for (int k = threadIdx.x; k < D * D; k += SM_T) sF[k] = a.F[k];
     if (threadIdx.x < D) {
         sm[threadIdx.x] = a.m_noise[threadIdx.x];
         ss[threadIdx.x] = a.shift ? a.shift[threadIdx.x] : 0.0;
         sc[threadIdx.x] = (a.lsf_kind == REE_LSF_AFFINE && a.coef) ? a.coef[threadIdx.x] : 0.0;
     }
-    for (int k = threadIdx.x; k < BM_TABLE_DOUBLES; k += SM_T) bm[k] = BM_TABLE[k];
+    bm_stage_tables(bm, threadIdx.x, SM_T);
     __syncthreads();
     BmTableShared tab;
     tab.addr = smem_u32(bm);

@@ -39,6 +39,7 @@ struct XfArgs {
     const double* logdet;
     double* logq;
     double* small;  // per-CTA ExpSums
+    int debug;      // REE_XF_DEBUG (timing experiments only): 1 = producers skip the noise generation, 2 = consumers skip the DMMAs
 };
 
 struct GenStage {  // rows 8q+lc and 8q+4+lc of the warp's staging block at particle column lr, minus the row mean
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_xform(const XfArgs a) {
     }
     for (int idx = tid; idx < NW * STG; idx += MT) stg[idx] = 0.0;
     if (MODE == 1 && !a.z)
-        for (int idx = tid; idx < BM_TABLE_DOUBLES; idx += MT) bm[idx] = BM_TABLE[idx];
+        bm_stage_tables(bm, tid, MT);
     __syncthreads();
 
     const uint32_t lf_lane = smem_u32(Lf) + lane * 8;
@@ -229,6 +230,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_xform(const XfArgs a) {
 // id computes exactly the consumer lane's fragment values (Philox counter = (particle lr, pair 4q + lc)), so both sides
 // use conflict-free 16-byte accesses at lane * 16.  full/empty mbarriers per buffer, one elected arrival per warp.
 // ---------------------------------------------------------------------------------------
+// predicated 16-byte global store: one instruction under a predicate, never a branch around it
+__device__ __forceinline__ void stg128_if(double* p, double x0, double x1, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.global.v2.f64 [%0], {%1, %2};\n\t}" ::"l"(p),
+        "d"(x0), "d"(x1), "r"((uint32_t)pred)
+        : "memory");
+}
+
 struct GenNoise {  // B fragments of k-pair q from the consumer's noise buffer
     uint32_t addr;  // buffer + lane * 16
     __device__ __forceinline__ void operator()(int q, double& b0, double& b1) const {
@@ -242,7 +251,9 @@ struct GenNoise {  // B fragments of k-pair q from the consumer's noise buffer
 // behind the 16-cycle DMMAs of the shared pipe, so one producer per consumer is latency-bound at ~2.4 consumer tile
 // times.  With NPC > 1 the CTA has more than 512 threads; setmaxnreg moves registers from the producers (RP) to the
 // consumers (RC), whose 2 * NTB accumulators + fragment prefetch do not fit the launch-time allocation.
-template <int NTB, int NC, int NPC, bool EXACT, int PGB, int RC, int RP>
+// CONS: 2 = accumulators start as t x + m, epilogue rows dealt out over the next tile's k-pair steps; 1 = same start,
+// epilogue after the tile's own DMMAs (no second accumulator set); tuning hook REE_XF_VARIANT
+template <int NTB, int NC, int NPC, bool EXACT, int PGB, int RC, int RP, int CONS>
 __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArgs a) {
     constexpr int MT = (1 + NPC) * NC * 32;
     constexpr int ROWS = 8 * NTB;
@@ -265,7 +276,7 @@ __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArg
         vc[j] = (j < d) ? (a.lsf_mode == 1 ? a.coef[j] : 1.0) : 0.0;
     }
     for (int idx = tid; idx < NC * STG; idx += MT) stg[idx] = 0.0;
-    for (int idx = tid; idx < BM_TABLE_DOUBLES; idx += MT) bm[idx] = BM_TABLE[idx];
+    bm_stage_tables(bm, tid, MT);
     if (tid < NC * 4) mbar_init(smem_u32(&bars[0][0][0]) + 8u * (uint32_t)tid, (tid & 1) ? 1 : NPC);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -288,6 +299,7 @@ __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArg
             mbar_wait(bar_c + 16u * b + 8u, ph ^ 1u);  // buffer b is free (passes at once the first two times)
             const uint64_t particle = (uint64_t)(a.first + wt * 8 + lr);
             constexpr int NQ = (NTB + NPC - 1) / NPC;  // k-pairs q = h + NPC * i, i < NQ
+            if (a.debug != 1)
 #pragma unroll
             for (int i0 = 0; i0 < NQ; i0 += PGB) {
                 double z0[PGB], z1[PGB];
@@ -311,11 +323,17 @@ __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArg
     }
 
     // ---------------- consumer: F z on the tensor pipe, update, g', e' ----------------
+    // Tile k's accumulators START as t x + m_noise (one DFMA per element while the warp waits for its noise), the
+    // DMMAs add F z on top, and what is left of the epilogue -- store, |x'|^2, coef . x' -- is dealt out one row tile per
+    // k-pair step of tile k+1: the warp never leaves its DMMA stream for a burst of fp64 instructions that each queue
+    // behind the other warps' 16-cycle DMMAs (the old epilogue was 39 % of a consumer's time, profiles/r2_xform_ws_*).
     if constexpr (RC > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RC));
     const uint32_t lf_lane = smem_u32(Lf) + lane * 8;
     const uint32_t stg_w = smem_u32(stg + warp * STG);
     const uint32_t own = stg_w + (uint32_t)(lr * 64 + lc * 16);  // rows 8mt+lr, columns 2lc, 2lc+1
+    const uint32_t vm_lane = smem_u32(vm) + (uint32_t)lr * 8u, vc_lane = smem_u32(vc) + (uint32_t)lr * 8u;
     const double e_const = (double)d * REE_LOG_2PI;
+    const double tt = a.t;
     auto prefetch = [&](int64_t wt) {
         const double* src = a.x + wt * 8 + 2 * lc;
 #pragma unroll
@@ -324,42 +342,24 @@ __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArg
             if (row < d) cp_async16(own + (uint32_t)(mt * 512), src + (int64_t)row * a.ld);
         }
     };
-    int64_t wt = (int64_t)blockIdx.x * NC + warp;
-    if (wt < nwt) prefetch(wt);
-    int k = 0;
-    for (; wt < nwt; wt += stride, ++k) {
-        const int64_t ip = wt * 8 + 2 * lc;
-        const uint32_t b = (uint32_t)k & 1u, ph = ((uint32_t)k >> 1) & 1u;
-        double c2[NTB][2];
+    double cprev[NTB][2];  // finished tile whose rows are written out during the next tile's DMMAs
 #pragma unroll
-        for (int mt = 0; mt < NTB; ++mt) c2[mt][0] = c2[mt][1] = 0.0;
-        mbar_wait(bar_c + 16u * b, ph);
-        GenNoise gen;
-        gen.addr = nz_c + b * (uint32_t)(NZ * 8);
-        transform_tiles<NTB, true, EXACT, 3>(lf_lane, ntd, gen, c2);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_c + 16u * b + 8u);  // every fragment of the buffer has been read
-        cp_async_wait_all();  // own elements only: no warp barrier needed
-        double se0 = 0.0, se1 = 0.0, sg0 = 0.0, sg1 = 0.0;
-#pragma unroll
-        for (int mt = 0; mt < NTB; ++mt) {
-            if (EXACT || mt < ntd) {
-                const int row = 8 * mt + lr;
-                if (row < d) {
-                    const double2 xv = lds128(own + (uint32_t)(mt * 512));
-                    const double mrow = vm[row], crow = vc[row];
-                    double2 xn;  // t*X + (m_noise + Z F^T): grouping of solver.py:667
-                    xn.x = __dadd_rn(__dmul_rn(a.t, xv.x), __dadd_rn(mrow, c2[mt][0]));
-                    xn.y = __dadd_rn(__dmul_rn(a.t, xv.y), __dadd_rn(mrow, c2[mt][1]));
-                    *reinterpret_cast<double2*>(a.x_new + (int64_t)row * a.ld + ip) = xn;
-                    se0 = fma(xn.x, xn.x, se0);
-                    se1 = fma(xn.y, xn.y, se1);
-                    sg0 = fma(crow, xn.x, sg0);
-                    sg1 = fma(crow, xn.y, sg1);
-                }
-            }
-        }
-        if (wt + stride < nwt) prefetch(wt + stride);
+    for (int mt = 0; mt < NTB; ++mt) cprev[mt][0] = cprev[mt][1] = 0.0;
+    double se0 = 0.0, se1 = 0.0, sg0 = 0.0, sg1 = 0.0;
+    int64_t ip_prev = 0;
+    // straight-line code (a predicated store, no branch): the DMMA stream of the next tile must stay one basic block so
+    // that the fragment loads of k-pair q+1 are scheduled above the DMMAs of k-pair q
+    auto epi_row = [&](int mt, bool live) {
+        const int row = 8 * mt + lr;
+        const double crow = lds64(vc_lane + (uint32_t)(mt * 64));  // (0 for rows >= d)
+        const double x0 = cprev[mt][0], x1 = cprev[mt][1];         // (0 for rows >= d)
+        stg128_if(a.x_new + (int64_t)row * a.ld + ip_prev, x0, x1, live && row < d);
+        se0 = fma(x0, x0, se0);
+        se1 = fma(x1, x1, se1);
+        sg0 = fma(crow, x0, sg0);
+        sg1 = fma(crow, x1, sg1);
+    };
+    auto epi_finish = [&]() {
 #pragma unroll
         for (int o = 4; o < 32; o <<= 1) {
             se0 += __shfl_xor_sync(0xffffffffu, se0, o);
@@ -370,16 +370,79 @@ __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArg
         if (lr == 0) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                if (ip + h < a.n) {
+                if (ip_prev + h < a.n) {
                     const double s = h ? se1 : se0, gsum = h ? sg1 : sg0;
-                    if (a.e_new) a.e_new[ip + h] = 0.5 * (e_const + s);
+                    if (a.e_new) a.e_new[ip_prev + h] = 0.5 * (e_const + s);
                     if (a.lsf_mode)
-                        a.g_new[ip + h] = (a.lsf_mode == 1)
-                                              ? __dadd_rn(gsum, a.offset)
-                                              : __dadd_rn(__ddiv_rn(-gsum, __dsqrt_rn((double)d)), a.offset);
+                        a.g_new[ip_prev + h] = (a.lsf_mode == 1)
+                                                   ? __dadd_rn(gsum, a.offset)
+                                                   : __dadd_rn(__ddiv_rn(-gsum, __dsqrt_rn((double)d)), a.offset);
                 }
             }
         }
+        se0 = se1 = sg0 = sg1 = 0.0;
+    };
+    int64_t wt = (int64_t)blockIdx.x * NC + warp;
+    if (wt < nwt) prefetch(wt);
+    int k = 0;
+    for (; wt < nwt; wt += stride, ++k) {
+        const uint32_t b = (uint32_t)k & 1u, ph = ((uint32_t)k >> 1) & 1u;
+        double c2[NTB][2];
+        cp_async_wait_all();  // own elements only: no warp barrier needed
+#pragma unroll
+        for (int mt = 0; mt < NTB; ++mt) {
+            const int row = 8 * mt + lr;
+            c2[mt][0] = c2[mt][1] = 0.0;
+            if ((EXACT || mt < ntd) && row < d) {
+                const double2 xv = lds128(own + (uint32_t)(mt * 512));
+                const double mrow = lds64(vm_lane + (uint32_t)(mt * 64));
+                c2[mt][0] = fma(tt, xv.x, mrow);
+                c2[mt][1] = fma(tt, xv.y, mrow);
+            }
+        }
+        if (wt + stride < nwt) prefetch(wt + stride);  // (this lane's reads of the block precede its refill)
+        mbar_wait(bar_c + 16u * b, ph);
+        const uint32_t nzb = nz_c + b * (uint32_t)(NZ * 8);
+        const bool have_prev = CONS == 2 && k > 0;
+        double2 bq = lds128(nzb);
+        if (a.debug != 2)
+#pragma unroll
+        for (int q = 0; q < NTB; ++q) {
+            if (EXACT || q < ntd) {
+                double2 bn = bq;
+                if (q + 1 < NTB && (EXACT || q + 1 < ntd)) bn = lds128(nzb + (uint32_t)((q + 1) * 512));
+#pragma unroll
+                for (int mt = q; mt < NTB; ++mt)
+                    if (EXACT || mt < ntd)
+                        dmma(c2[mt][0], c2[mt][1], lds64(lf_lane + lf_tile<NTB, true>(mt, 2 * q) * 256), bq.x);
+#pragma unroll
+                for (int mt = q; mt < NTB; ++mt)
+                    if (EXACT || mt < ntd)
+                        dmma(c2[mt][0], c2[mt][1], lds64(lf_lane + lf_tile<NTB, true>(mt, 2 * q + 1) * 256), bq.y);
+                bq = bn;
+            }
+            if constexpr (CONS == 2) epi_row(q, have_prev);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_c + 16u * b + 8u);  // every fragment of the buffer has been read
+        if (have_prev) epi_finish();
+        se0 = se1 = sg0 = sg1 = 0.0;
+#pragma unroll
+        for (int mt = 0; mt < NTB; ++mt) {
+            cprev[mt][0] = c2[mt][0];
+            cprev[mt][1] = c2[mt][1];
+        }
+        ip_prev = wt * 8 + 2 * lc;
+        if constexpr (CONS == 1) {
+#pragma unroll
+            for (int mt = 0; mt < NTB; ++mt) epi_row(mt, true);
+            epi_finish();
+        }
+    }
+    if (CONS == 2 && k > 0) {
+#pragma unroll
+        for (int mt = 0; mt < NTB; ++mt) epi_row(mt, true);
+        epi_finish();
     }
 }
 
@@ -748,7 +811,7 @@ bool ree_split_supported(int d) {
 template <int MODE, int NTB, int NW, bool EXACT, bool TRI, int PGB = 2>
 static int launch_xf(const XfArgs& a, int grid, cudaStream_t st) {
     constexpr size_t smem = ((size_t)lf_doubles<NTB, TRI>() + (size_t)NW * 8 * NTB * 8 + 2 * 8 * NTB +
-                             (MODE == 1 ? BM_TABLE_DOUBLES + 2 : 0)) * sizeof(double);
+                             (MODE == 1 ? BM_SMEM_DOUBLES : 0)) * sizeof(double);
     static_assert(smem <= 227 * 1024, "shared memory budget");
     auto kern = k_xform<MODE, NTB, NW, EXACT, TRI, PGB>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -765,14 +828,14 @@ static int xf_ws() {
     return v;
 }
 
-template <int NTB, int NC, int NPC, bool EXACT, int PGB, int RC, int RP>
+template <int NTB, int NC, int NPC, bool EXACT, int PGB, int RC, int RP, int CONS = 2>
 static int launch_xf_ws(const XfArgs& a, int grid, cudaStream_t st) {
     constexpr size_t smem = ((size_t)lf_doubles<NTB, true>() + (size_t)NC * 3 * NTB * 64 + 2 * 8 * NTB +
-                             BM_TABLE_DOUBLES + 2) * sizeof(double);
+                             BM_SMEM_DOUBLES) * sizeof(double);
     static_assert(smem <= 227 * 1024, "shared memory budget");
     static_assert(RC == 0 || (NC * RC + NC * NPC * RP) * 32 <= 65536 / ((1 + NPC) * NC * 32) / 8 * 8 * (1 + NPC) * NC * 32,
                   "register pool");
-    auto kern = k_xform_ws<NTB, NC, NPC, EXACT, PGB, RC, RP>;
+    auto kern = k_xform_ws<NTB, NC, NPC, EXACT, PGB, RC, RP, CONS>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, (1 + NPC) * NC * 32, smem, st>>>(a);
     return ree_check_launch("k_xform_ws");
@@ -787,11 +850,15 @@ static int launch_xf_ws_variants(const XfArgs& a, cudaStream_t st) {
     if ((a.d + 7) / 8 == NTB) {
         // tuning hooks: 1 = four Philox chains per producer batch, 2 = two producers per consumer
         // with setmaxnreg 120 / 56 (measured slower: the extra DFMA streams take pipe slots from the consumers)
-        if (v == 1) return launch_xf_ws<NTB, NC, 1, true, 4, 0, 0>(a, grid, st);
-        if (v == 2) return launch_xf_ws<NTB, NC, 2, true, 2, 120, 56>(a, grid, st);
-        return launch_xf_ws<NTB, NC, 1, true, 2, 0, 0>(a, grid, st);
+        // measured at N = 1e7, d = 100 (profiles/r2_xform_variants.txt): 0: 7.39 ms; 3 (next tile's DMMAs carry the
+        // epilogue, setmaxnreg 152 / 104): 8.10; 1 (same, 176 / 80): 8.98 -- every register taken from the producers
+        // costs more than the leaner consumer gains
+        if (v == 1) return launch_xf_ws<NTB, NC, 1, true, 2, 176, 80, 2>(a, grid, st);
+        if (v == 2) return launch_xf_ws<NTB, NC, 2, true, 2, 120, 56, 1>(a, grid, st);
+        if (v == 3) return launch_xf_ws<NTB, NC, 1, true, 2, 152, 104, 2>(a, grid, st);
+        return launch_xf_ws<NTB, NC, 1, true, 2, 0, 0, 1>(a, grid, st);
     }
-    return launch_xf_ws<NTB, NC, 1, false, 2, 0, 0>(a, grid, st);
+    return launch_xf_ws<NTB, NC, 1, false, 2, 0, 0, 1>(a, grid, st);
 }
 
 template <int MODE, int NTB, int NW, bool TRI>
@@ -805,6 +872,14 @@ static int launch_xf_bucket(const SplitCfg& c, const XfArgs& a, cudaStream_t st)
     const int sms = ree_grid_ctas() / 2;  // persistent: one CTA per SM
     const int64_t nwt = (a.n + 7) / 8;
     if constexpr (MODE == 1 && TRI) {
+        if (!a.z && c.ntb == 13 && (a.d + 7) / 8 == 13 && xf_variant() >= 7) {  // experiments: phased, unspecialised
+            const int v = xf_variant();
+            if (v == 7) { const int64_t w = (nwt + 11) / 12; return launch_xf<1, 13, 12, true, true, 13>(a, (int)(w < sms ? w : sms), st); }
+            if (v == 8) { const int64_t w = (nwt + 11) / 12; return launch_xf<1, 13, 12, true, true, 7>(a, (int)(w < sms ? w : sms), st); }
+            if (v == 9) { const int64_t w = (nwt + 15) / 16; return launch_xf<1, 13, 16, true, true, 13>(a, (int)(w < sms ? w : sms), st); }
+            if (v == 10) { const int64_t w = (nwt + 7) / 8; return launch_xf<1, 13, 8, true, true, 13>(a, (int)(w < sms ? w : sms), st); }
+            if (v == 11) { const int64_t w = (nwt + 11) / 12; return launch_xf<1, 13, 12, true, true, 4>(a, (int)(w < sms ? w : sms), st); }
+        }
         if (!a.z && xf_ws()) {  // Philox noise: producer / consumer warps
             if (c.ntb == 7) return launch_xf_ws_variants<7, 8>(a, st);
             if (c.ntb == 13) return launch_xf_ws_variants<13, 8>(a, st);
@@ -861,6 +936,14 @@ int ree_split_step(const double* x, double* x_new, int64_t n, int d, int64_t ld,
     a.x = x; a.n = n; a.ld = ld; a.d = d; a.A = F; a.x_new = x_new; a.t = t; a.m_noise = m_noise; a.z = z;
     a.seed = seed; a.draw = draw; a.first = first; a.lsf_mode = lsf_mode; a.coef = coef; a.offset = offset;
     a.g_new = g_new; a.e_new = e_new;
+    {
+        static int dbg = -1;
+        if (dbg < 0) {
+            const char* e = getenv("REE_XF_DEBUG");
+            dbg = e ? atoi(e) : 0;
+        }
+        a.debug = dbg;
+    }
     return tri ? launch_xf_bucket<1, true>(c, a, st) : launch_xf_bucket<1, false>(c, a, st);
 }
 
