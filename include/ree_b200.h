@@ -267,6 +267,10 @@ int ree_cbree_maha(const double* x, int64_t n, int d, int64_t ld, const double* 
  * ree_peer_connect(handles[world][64]).  All ranks must call ree_peer_combine_expsums in the same order.           */
 int ree_peer_create(int rank, int world, unsigned char* handle_out64);
 int ree_peer_connect(const unsigned char* handles);
+/* The same for ONE process that drives several devices with one host thread each (CBREE(devices=N)): after every thread
+ * has called ree_peer_create on its device (host barrier), each calls this with the device ordinal of every rank; the
+ * mailboxes are reached through cudaDeviceEnablePeerAccess instead of CUDA IPC. */
+int ree_peer_connect_local(const int* devices);
 int ree_peer_ready(void);
 int ree_peer_combine_expsums(double* out4, void* stream);
 int ree_peer_check(void);

@@ -98,6 +98,7 @@ PROTOTYPES = {
     "ree_vector_range": (_INT, [_P, _I64, _P, _P, _P]),
     "ree_peer_create": (_INT, [_INT, _INT, _P]),
     "ree_peer_connect": (_INT, [_P]),
+    "ree_peer_connect_local": (_INT, [C.POINTER(C.c_int)]),
     "ree_peer_ready": (_INT, []),
     "ree_peer_combine_expsums": (_INT, [_P, _P]),
     "ree_peer_check": (_INT, []),

@@ -195,10 +195,7 @@ class SIS(Solver):
             raise RuntimeError("N*p and 1/p must be positive integers. Adjust N and p accordingly")
         seed = int(np.random.SeedSequence(self.seed).generate_state(1)[0]) if self.seed is not None else \
             int(np.random.SeedSequence().generate_state(1)[0])
-        if comm.enabled:  # one seed for all ranks (the unseeded case draws from OS entropy per process)
-            box = [seed]
-            comm.dist.broadcast_object_list(box, src=0, group=comm.group)
-            seed = box[0]
+        seed = comm.broadcast_object(seed)  # one seed for all ranks (the unseeded case draws from OS entropy per process)
         nchain, lenchain, burn = int(N * p), int(round(1 / p)), int(self.burn_in)
         tar = float(self.cvar_tgt)
         max_it = 100
@@ -261,9 +258,7 @@ class SIS(Solver):
             # how many of the nchain seeds each rank contributes: multinomial in the ranks' weight sums
             wsum = (w[:pop.n].sum() if pop.n > 0 else eng.zeros(1).sum()).reshape(1)
             if comm.enabled:
-                parts = torch.empty(comm.world, dtype=wsum.dtype, device=wsum.device)
-                comm.dist.all_gather_into_tensor(parts, wsum, group=comm.group)
-                pw = parts.cpu().numpy()
+                pw = comm.all_gather_vec(wsum).cpu().numpy()
                 counts = split_rng.multinomial(nchain, pw / pw.sum())
                 my_chains, chain0 = int(counts[comm.rank]), int(counts[:comm.rank].sum())
             else:

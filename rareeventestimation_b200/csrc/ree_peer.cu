@@ -109,6 +109,40 @@ extern "C" int ree_peer_connect(const unsigned char* handles) {
     return 0;
 }
 
+// One process driving several devices (one host thread per device): the peers' mailboxes are plain device pointers of
+// this process, reached through peer access -- no IPC.  Every device's thread: ree_peer_create (the handle is not
+// used), a host barrier, ree_peer_connect_local(devices[world]), a host barrier.
+extern "C" int ree_peer_connect_local(const int* devices) {
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess || dev < 0 || dev >= 64 || !g_peer[dev].local || !devices)
+        return ree_set_error(REE_E_BADARG, "ree_peer_connect_local: ree_peer_create first");
+    PeerState& s = g_peer[dev];
+    for (int r = 0; r < s.world; ++r) {
+        const int od = devices[r];
+        if (od < 0 || od >= 64 || !g_peer[od].local)
+            return ree_set_error(REE_E_BADARG, "ree_peer_connect_local: a device of the group has no mailbox yet");
+        if (od != dev) {
+            int can = 0;
+            err = cudaDeviceCanAccessPeer(&can, dev, od);
+            if (err != cudaSuccess || !can) return ree_set_error(REE_E_UNSUPPORTED, "ree_peer_connect_local: no peer access");
+            err = cudaDeviceEnablePeerAccess(od, 0);
+            if (err == cudaErrorPeerAccessAlreadyEnabled) {
+                (void)cudaGetLastError();
+            } else if (err != cudaSuccess) {
+                return ree_set_error((int)err, cudaGetErrorString(err));
+            }
+        }
+        s.box[r] = g_peer[od].local;
+        memset(s.handle[r], 0, 64);
+    }
+    memset(&s.args, 0, sizeof(s.args));
+    for (int r = 0; r < s.world; ++r) s.args.box[r] = s.box[r];
+    s.args.rank = s.rank; s.args.world = s.world; s.args.error = s.d_error;
+    g_peer_ready[dev] = true;
+    return 0;
+}
+
 extern "C" int ree_peer_ready(void) {
     int dev = 0;
     return (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && g_peer_ready[dev]) ? 1 : 0;

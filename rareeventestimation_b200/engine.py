@@ -108,11 +108,119 @@ class Comm:
         if self.peer:
             check(_lib.load().ree_peer_check(), "ree_peer_check")
 
+    def broadcast_object(self, obj, src: int = 0):
+        """The object rank `src` passes, on every rank."""
+        if not self.enabled:
+            return obj
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=src, group=self.group)
+        return box[0]
+
+    def all_gather_vec(self, t: torch.Tensor) -> torch.Tensor:
+        """Concatenation over the ranks (rank order) of equally sized device vectors."""
+        if not self.enabled:
+            return t.clone()
+        out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
     def shard(self, n_global: int):
         """Contiguous slice [lo, hi) of this rank."""
         base, rem = divmod(int(n_global), self.world)
         lo = self.rank * base + min(self.rank, rem)
         return lo, lo + base + (1 if self.rank < rem else 0)
+
+
+class ThreadGroup:
+    """Shared state of one process that drives `devices` with one host thread each (``CBREE(devices=N)``)."""
+
+    def __init__(self, devices):
+        import threading
+
+        self.devices = [int(x) for x in devices]
+        self.world = len(self.devices)
+        self.barrier = threading.Barrier(self.world)
+        self.slots = [None] * self.world
+        self.failed = None
+
+
+class ThreadComm(Comm):
+    """The communicator of one thread of a :class:`ThreadGroup`: same interface as :class:`Comm` (one process per GPU
+    under torchrun), no torch.distributed.  The 4-tuple merges run in the same NVLink mailbox kernels (peer access
+    instead of CUDA IPC); the d x d sums are added in rank order from peer-to-peer copies, so every rank holds
+    identical bits."""
+
+    def __init__(self, tgroup: ThreadGroup, rank: int):
+        self.dist = None
+        self.group = None
+        self.tgroup = tgroup
+        self.enabled = tgroup.world > 1
+        self.rank, self.world = int(rank), tgroup.world
+        self.peer = None
+
+    def _sync_point(self):
+        try:
+            self.tgroup.barrier.wait(timeout=600)
+        except Exception:
+            raise ReeError("a device thread of this solve failed or stalled (see the first exception)") from None
+
+    def _connect_peers(self, device) -> bool:
+        lib = _lib.load()
+        buf = (C.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            check(lib.ree_peer_create(self.rank, self.world, buf), "ree_peer_create")
+            self._sync_point()
+            devs = (C.c_int * self.world)(*self.tgroup.devices)
+            check(lib.ree_peer_connect_local(devs), "ree_peer_connect_local")
+            self._sync_point()
+        return True
+
+    def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+        if not self.enabled:
+            return t
+        g = self.tgroup
+        torch.cuda.current_stream(t.device).synchronize()  # this rank's contribution is final
+        g.slots[self.rank] = t
+        self._sync_point()
+        acc = None
+        for r in range(self.world):  # rank order on every rank: identical bits
+            part = g.slots[r] if r == self.rank else g.slots[r].to(t.device)
+            acc = part.clone() if acc is None else acc.add_(part)
+        torch.cuda.current_stream(t.device).synchronize()  # all peer reads are done ...
+        self._sync_point()                                  # ... on every rank, before anybody's buffer changes
+        t.copy_(acc)
+        return t
+
+    def combine_expsums_(self, out4: torch.Tensor) -> torch.Tensor:
+        if self.enabled:
+            if self.peer is None:
+                self.peer = self._connect_peers(out4.device)
+            stream = C.c_void_p(torch.cuda.current_stream(out4.device).cuda_stream)
+            check(_lib.load().ree_peer_combine_expsums(out4.data_ptr(), stream), "ree_peer_combine_expsums")
+        return out4
+
+    def broadcast_object(self, obj, src: int = 0):
+        if not self.enabled:
+            return obj
+        g = self.tgroup
+        if self.rank == src:
+            g.slots[src] = obj
+        self._sync_point()
+        out = g.slots[src]
+        self._sync_point()
+        return out
+
+    def all_gather_vec(self, t: torch.Tensor) -> torch.Tensor:
+        if not self.enabled:
+            return t.clone()
+        g = self.tgroup
+        torch.cuda.current_stream(t.device).synchronize()
+        g.slots[self.rank] = t
+        self._sync_point()
+        out = torch.cat([g.slots[r] if r == self.rank else g.slots[r].to(t.device) for r in range(self.world)])
+        torch.cuda.current_stream(t.device).synchronize()
+        self._sync_point()
+        return out
 
 
 # --------------------------------------------------------------------------- #
@@ -208,6 +316,7 @@ class Engine:
         self._pool = {}
         self._scratch = {}
         self._staging = None
+        self._pin_ring, self._pin_next, self._pin_down, self._side = None, 0, None, None
         self._fetch_buf = np.empty(64, dtype=np.float64)
         with torch.cuda.device(self.device):
             self.num_ctas = self.lib.ree_num_ctas()
@@ -242,6 +351,40 @@ class Engine:
     def to_device(self, arr) -> torch.Tensor:
         a = np.ascontiguousarray(np.asarray(arr, dtype=np.float64))
         return torch.from_numpy(a).to(self.device, non_blocking=False)
+
+    # small host <-> device traffic of the iteration loop goes through pinned memory: a pageable cudaMemcpy stalls the
+    # host until the stream has drained AND costs ~50 us of driver staging per call
+    _RING, _RING_DOUBLES = 16, 4096
+
+    def to_device_small(self, arr) -> torch.Tensor:
+        """Stream-ordered upload of a small fp64 vector (<= 4096 values) from a ring of pinned buffers; a slot is reused
+        after 16 uploads (every iteration of a solve ends in a synchronising readback long before that)."""
+        a = np.asarray(arr, dtype=np.float64).reshape(-1)
+        if a.size > self._RING_DOUBLES:
+            return self.to_device(a)
+        if self._pin_ring is None:
+            self._pin_ring = [torch.empty(self._RING_DOUBLES, dtype=F64, pin_memory=True) for _ in range(self._RING)]
+            self._pin_next = 0
+        slot = self._pin_ring[self._pin_next]
+        self._pin_next = (self._pin_next + 1) % self._RING
+        slot.numpy()[: a.size] = a
+        out = torch.empty(a.size, dtype=F64, device=self.device)
+        out.copy_(slot[: a.size], non_blocking=True)
+        return out
+
+    def to_host(self, t: torch.Tensor) -> np.ndarray:
+        """Synchronising readback of a device vector through a pinned buffer (a view that the next call overwrites)."""
+        n = t.numel()
+        if self._pin_down is None or self._pin_down.numel() < n:
+            self._pin_down = torch.empty(max(n, 1 << 16), dtype=F64, pin_memory=True)
+        self._pin_down[:n].copy_(t.reshape(-1), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._pin_down[:n].numpy()
+
+    def side_stream(self) -> "torch.cuda.Stream":
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
 
     # -- ensemble I/O ---------------------------------------------------------- #
     def alloc_ensemble(self, n: int, d: int, first: int = 0, with_vectors=True) -> Ensemble:

@@ -16,6 +16,7 @@ from numbers import Real
 from typing import Optional
 
 import numpy as np
+import torch
 from scipy.optimize import minimize_scalar, root
 
 from . import _lib
@@ -187,12 +188,53 @@ def get_slope(y) -> float:
     y = np.atleast_1d(np.asarray(y, dtype=np.float64))
     if not np.all(np.isfinite(y)):
         return math.nan
-    try:
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            return np.polyfit(np.arange(len(y)), y, deg=1, full=True)[0][0]
-    except Exception:
+    n = y.shape[0]
+    if n < 2:  # polyfit of a single point fails (LAPACK error) and the reference returns nan for any failure
         return math.nan
+    # closed form of polyfit(arange(n), y, 1)[0] (the reference's call, two 100 us SVD-based fits per iteration)
+    x = np.arange(n, dtype=np.float64) - 0.5 * (n - 1)
+    return float(np.dot(x, y - y.mean()) / np.dot(x, x))
+
+
+class ConcatHistory:
+    """History over all particles of a solve that was sharded over several devices of one process: the (S, N_r[, d])
+    histories of the ranks side by side along the particle axis, materialised on access."""
+
+    def __init__(self, parts):
+        self._parts = list(parts)
+        first = self._parts[0]
+        n = sum(int(p.shape[1]) for p in self._parts)
+        self.shape = (int(first.shape[0]), n) + tuple(first.shape[2:])
+        self.ndim = len(self.shape)
+        self.dtype = np.dtype(np.float64)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __array__(self, dtype=None, copy=None):
+        return np.concatenate([np.asarray(p).reshape((self.shape[0], -1) + self.shape[2:]) for p in self._parts], axis=1)
+
+    def __getitem__(self, idx):
+        if isinstance(idx, (int, np.integer)):
+            return np.concatenate([np.asarray(p[idx]) for p in self._parts], axis=0)
+        if isinstance(idx, tuple) and isinstance(idx[0], (int, np.integer)):
+            return np.concatenate([np.asarray(p[idx[0]]) for p in self._parts], axis=0)[idx[1:]]
+        return np.asarray(self)[idx]
+
+
+def _merge_sharded_solutions(sols):
+    """Rank 0's Solution (all scalar histories are identical on every rank) over the particles of all ranks."""
+    out = sols[0]
+
+    def two_d(h, want_ndim):  # a single retained cache comes back without its leading axis
+        return h if h.ndim == want_ndim else np.asarray(h)[None, ...]
+
+    out.ensemble_hist = ConcatHistory([two_d(s.ensemble_hist, 3) for s in sols])
+    out.lsf_eval_hist = ConcatHistory([two_d(s.lsf_eval_hist, 2) for s in sols])
+    out.N = out.ensemble_hist.shape[1]
+    if isinstance(out.other, dict) and "cache_list" in out.other:
+        out.other["cache_list_per_device"] = [s.other["cache_list"] for s in sols]
+    return out
 
 
 class Solver:
@@ -251,13 +293,16 @@ class CBREE(Solver):
     search: "device" (the sigma / beta searches run inside one persistent kernel per iteration, ``ree_cbree_adapt``:
            SciPy's bounded Brent and MINPACK's hybrd in the same arithmetic) or "scipy" (the reference's host
            optimisers drive one device reduction per objective evaluation -- kept as the cross-check).
+    devices: None (the current device; under torchrun one rank per GPU), an int N (devices 0..N-1) or a list of device
+           ordinals: ``solve`` then shards the particles over these devices of THIS process (one host thread per
+           device, NVLink mailboxes through peer access) and returns one Solution over all particles.
     """
 
     def __init__(self, stepsize_tolerance=0.5, t_step=-1, num_steps=100, tgt_fun="algebraic", observation_window=5,
                  seed=None, sigma_adaptivity="cvar", beta_adaptivity=True, cvar_tgt=2, sfp_tgt=1 / 3, ess_tgt=1 / 2,
                  lip_sigma=1, divergence_check=True, convergence_check=True, mixture_model="GM", resample=False,
                  verbose=False, save_history=False, return_other=False, return_caches=False, name=None,
-                 callback=None, *, noise="philox", search=None, quiet=False) -> None:
+                 callback=None, *, noise="philox", search=None, quiet=False, devices=None) -> None:
         super().__init__()
         if t_step > 0:
             self.stepsize_adaptivity = False
@@ -310,6 +355,7 @@ class CBREE(Solver):
             search = os.environ.get("REE_SEARCH", "device")
         assert search in ("device", "scipy")
         self.search = search
+        self.devices = devices
 
     def __str__(self) -> str:
         return self.name if self.name is not None else "CBREE"
@@ -431,14 +477,32 @@ class CBREE(Solver):
                 model.logpdf_device(eng, dev, is4=is4)
         tails[0:2].copy_(sums_u[d + d * d:])
         tails[2:4].copy_(sums_w[d + d * d:])
-        host = res.cpu().numpy()  # the one synchronising D2H of the iteration
-        eng.comm.check_peers()
+        # factor of the weighted covariance for the NEXT step's noise, on a side stream: it overlaps the readback below,
+        # the host's bookkeeping and the sigma / beta search instead of sitting between the search and sweep 1
+        # (chol(scale C) = sqrt(scale) chol(C); the scale is only known after the search)
+        F0 = F0_event = None
+        if self.noise == "philox":
+            side, main = eng.side_stream(), torch.cuda.current_stream(eng.device)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                F0, f0stats = eng.empty(d * d), eng.empty(8)
+                eng.chol_scaled(C_w, d, 1.0, F0, f0stats)
+                F0_event = torch.cuda.Event()
+                F0_event.record(side)
+            res.record_stream(side)
+            F0.record_stream(main)
+        host = eng.to_host(res)  # the one synchronising D2H of the iteration (pinned)
+        self._peer_checks = getattr(self, "_peer_checks", 0) + 1
+        if self._peer_checks % 16 == 1:  # (a 4-byte synchronising copy of the time-out flag: not every iteration)
+            eng.comm.check_peers()
         cache.ens_mean = host[0:d].copy()
         cache.ens_cov = host[d:d + d * d].reshape(d, d).copy()
         cache.weighted_mean = host[d + d * d:2 * d + d * d].copy()
         cache.weighted_cov = host[2 * d + d * d:o].reshape(d, d).copy()
         st, i4, e4, tl = host[o:o + 8], host[o + 8:o + 12], host[o + 12:o + 16], host[o + 16:o + 20]
-        cache._stats = dict(C_w=C_w)  # view into `res`; the O(N) scratch (w, L, Linv) is released here
+        cache._stats = dict(C_w=C_w, F0=F0, F0_event=F0_event)  # views into `res`; the O(N) scratch is released here
         cache._vmfn_density = model is not None
         cache._chol_info = int(st[1])
         cache._min_pivot, cache._max_diag = float(st[2]), float(st[3])
@@ -697,7 +761,7 @@ class CBREE(Solver):
         sums = None if split else eng.empty(d + d * d + 2)
         # conditioning shifts of the one-pass Grams: predicted unweighted mean, previous weighted mean
         shift_u_h = t * cache.ens_mean + m_noise
-        small = eng.to_device(np.concatenate([m_noise, shift_u_h, cache.weighted_mean]))
+        small = eng.to_device_small(np.concatenate([m_noise, shift_u_h, cache.weighted_mean]))
         m_noise_d, shift_u, shift_w = small[0:d], small[d:2 * d], small[2 * d:3 * d]
         desc = self._lsf_descriptor(d)
         resample = self.resample and self.mixture_model == "vMFNM"
@@ -712,10 +776,15 @@ class CBREE(Solver):
             F = eng.to_device(u * np.sqrt(s))
             eng.cbree_step(src, dst, t, m_noise_d, F, step_desc, shift_u, sums, z=zdev)
         else:
-            F = eng.empty(d * d)
-            fstats = eng.empty(8)
-            eng.chol_scaled(cache._stats["C_w"] if not cache._cw_dirty else eng.to_device(cache.weighted_cov), d,
-                            scale, F, fstats)
+            F0 = cache._stats.get("F0") if (cache._stats and not cache._cw_dirty) else None
+            if F0 is not None:  # factored on the side stream while the host did its bookkeeping
+                torch.cuda.current_stream(eng.device).wait_event(cache._stats["F0_event"])
+                F = F0 * math.sqrt(scale)
+            else:
+                F = eng.empty(d * d)
+                fstats = eng.empty(8)
+                eng.chol_scaled(cache._stats["C_w"] if not cache._cw_dirty else eng.to_device(cache.weighted_cov), d,
+                                scale, F, fstats)
             self._step_draws += 1
             eng.cbree_step(src, dst, t, m_noise_d, F, step_desc, shift_u, sums, seed=self._philox_seed,
                            draw=_STREAM_STEP + self._step_draws)
@@ -803,24 +872,30 @@ class CBREE(Solver):
 
     def _update_stepsize(self, cache_list: list) -> None:
         """Embedded two-stage error estimate on (mean, tril cov) of the last two ensembles (solver.py:740-781);
-        the moments were produced by the sweeps, nothing N-sized is touched."""
+        the moments were produced by the sweeps, nothing N-sized is touched.  Evaluated on the mean and the lower
+        triangle only: the zeros of the upper triangle of ``tril`` add nothing to the sum of squares, they only count
+        in the average (which the reference takes over all (d + 1) d entries)."""
         ch1, ch2 = cache_list[-2], cache_list[-1]
         h = -np.log(ch1.t_step)
         phi = (np.exp(-2 * h) - 1) / (-2 * h)
         bm1 = phi - 2 * (phi - 1) / (-2 * h)
         bm2 = 2 * (phi - 1) / (-2 * h)
-        m1, m2 = ch1.ens_mean, ch2.ens_mean
-        m2_hat = 2 * h * (bm1 * m1 + bm2 * m2)
         phi = (np.exp(-4 * h) - 1) / (-2 * h)
         bc1 = phi - 2 * (phi - 1) / (-2 * h)
         bc2 = 2 * (phi - 1) / (-2 * h)
-        c1, c2 = ch1.ens_cov, ch2.ens_cov
-        c2_hat = 2 * h * (bc1 * c1 + bc2 * c2)
-        x = self._stack(m2, c2)
-        x_hat = self._stack(m2_hat, c2_hat)
+        d = ch2.ens_mean.shape[0]
+        il = self._tril_cache.get(d) if hasattr(self, "_tril_cache") else None
+        if il is None:
+            self._tril_cache = {d: np.tril_indices(d)}
+            il = self._tril_cache[d]
+        x1 = np.concatenate((ch1.ens_mean, ch1.ens_cov[il]))
+        x = np.concatenate((ch2.ens_mean, ch2.ens_cov[il]))
+        b1 = np.concatenate((np.full(d, bm1), np.full(il[0].shape[0], bc1)))
+        b2 = np.concatenate((np.full(d, bm2), np.full(il[0].shape[0], bc2)))
+        x_hat = 2 * h * (b1 * x1 + b2 * x)
         delta = x - x_hat
         w = self.stepsize_tolerance + self.stepsize_tolerance * np.maximum(abs(x), abs(x_hat))
-        err = np.sqrt(np.average((delta / w) ** 2))
+        err = np.sqrt(np.sum((delta / w) ** 2) / ((d + 1) * d))
         q = 0.9 * np.sqrt(1 / err)
         ch2.t_step = np.maximum(np.exp(-100), np.minimum(np.exp(-1e-5), np.exp(-q * h)))
 
@@ -993,8 +1068,66 @@ class CBREE(Solver):
             msg = "Not Converged."
         return self._build_solution(cache_list, msg, None)  # costs after the final importance sampling (solver.py:497)
 
+    def _device_list(self):
+        dv = self.devices
+        if dv is None:
+            return None
+        dv = list(range(int(dv))) if isinstance(dv, (int, np.integer)) else [int(x) for x in dv]
+        return dv if len(dv) > 1 else None
+
+    def _solve_on_devices(self, prob: Problem, devices) -> Solution:
+        """One host thread per device, every thread runs the single-rank ``solve`` on its particle shard with a
+        :class:`~.engine.ThreadComm` (the ranks of a torchrun launch, inside one process).  All threads execute the
+        identical scalar control flow on identical reduced values; rank 0's Solution is returned with the N-sized
+        histories replaced by views over all shards."""
+        import threading
+
+        import torch
+
+        from .engine import ThreadComm, ThreadGroup
+
+        if torch.cuda.device_count() < len(devices):
+            raise ValueError(f"devices={devices}: this process sees {torch.cuda.device_count()} CUDA device(s)")
+        tgroup = ThreadGroup(devices)
+        results, errors = [None] * len(devices), [None] * len(devices)
+
+        def work(rank):
+            dev = torch.device("cuda", devices[rank])
+            eng = None
+            try:
+                torch.cuda.set_device(dev)
+                eng = Engine.get(dev, ThreadComm(tgroup, rank))
+                mine = deepcopy(self)  # same options, same generator state: identical host decisions on every rank
+                mine.devices = None
+                mine.quiet = True
+                mine.verbose = self.verbose and rank == 0
+                results[rank] = CBREE.solve(mine, prob)
+            except BaseException as e:  # noqa: BLE001  (reported by the calling thread)
+                errors[rank] = e
+                tgroup.barrier.abort()
+            finally:
+                if eng is not None:  # later single-device solves on this device must not meet a dead group
+                    from .engine import Comm
+
+                    eng.comm, eng._comm_given = Comm(enabled=False), False
+
+        threads = [threading.Thread(target=work, args=(r,), name=f"ree-dev{devices[r]}") for r in range(len(devices))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        first = next((e for e in errors if e is not None and not isinstance(e, threading.BrokenBarrierError)), None)
+        if first is None:
+            first = next((e for e in errors if e is not None), None)
+        if first is not None:
+            raise first
+        return _merge_sharded_solutions(results)
+
     def solve(self, prob: Problem) -> Solution:
         """Estimate the rare event of `prob` (solver.py:365-503)."""
+        devices = self._device_list()
+        if devices is not None:
+            return self._solve_on_devices(prob, devices)
         try:  # the list below is private to this call: retired caches' buffers are recycled
             cache_list = self.start(prob, recycle=True)
             while not cache_list[-1].converged and cache_list[-1].iteration <= self.num_steps:
@@ -1022,12 +1155,12 @@ class CBREE(Solver):
             self._importance_sampling(c)
         self._compute_weighted_estimates(cache_list)
         last = cache_list[-1]
-        other = {
-            "Average Estimate": last.estimate_uniform_avg,
-            "Root Weighted Average Estimate": last.estimate_sqrt_avg,
-            "VAR Weighted Average Estimate": last.estimate_cvar_avg,
-            "CVAR": last.cvar_is_weights,
-            "SFP": last.sfp,
+        other = {  # NumPy scalars like the reference's (callers use ``.tolist()``, convergence_analysis.py:222)
+            "Average Estimate": np.float64(last.estimate_uniform_avg),
+            "Root Weighted Average Estimate": np.float64(last.estimate_sqrt_avg),
+            "VAR Weighted Average Estimate": np.float64(last.estimate_cvar_avg),
+            "CVAR": np.float64(last.cvar_is_weights),
+            "SFP": np.float64(last.sfp),
         }
         tmp = flatten_cache_list(cache_list)
         tmp["sigma"] = np.insert(tmp["sigma"], 0, 0)  # thesis notation, solver.py:486-488

@@ -147,3 +147,37 @@ def test_study_cbree_observation_window_like_reference_test():
         assert isinstance(data["t_step"][0], np.ndarray) and data["t_step"][0].ndim == 1
         agg = ree.aggregate_df(ree.add_evaluations(data).drop(columns=["index"]))
         assert len(agg.index) == 1 and os.path.exists(f2)
+
+
+@pytest.mark.gpu
+@pytest.mark.needs_reference
+def test_reference_harness_unchanged_on_the_engine(tmp_path):
+    """SURVEY.md 8f-1 as written: the REFERENCE's own ``do_multiple_solves`` and ``study_cbree_observation_window``
+    (evaluation/convergence_analysis.py:34-333, imported unmodified through oracle/ref_loader.py with a plotly stub)
+    drive the engine's CBREE on the engine's problems -- what test/test_do_multiple_solves.py:6-24 and
+    test/test_study_cbree_observation_window.py:6-28 check for the reference's solver.  Exercises ``set_options(...,
+    in_situ=False)`` on solved solvers, ``Solution.other``, ``return_caches`` / ``solve_from_caches`` from foreign code."""
+    import pandas as pd
+
+    import ref_loader
+    import rareeventestimation_b200 as ree
+
+    ca = ref_loader.load_reference_evaluation()
+    num_runs = 10
+    for p in ree.problems_lowdim:
+        p.set_sample(1000, seed=5000)
+        cbree = ree.CBREE(quiet=True)
+        file = ca.do_multiple_solves(p, cbree, num_runs, dir=str(tmp_path), save_other=True, other_list=["t_step"],
+                                     addtnl_cols={"col": "val"}, verbose=False)
+        df = pd.read_csv(file)
+        assert len(df.index) == num_runs, "Dataframe has the wrong number of rows"
+        assert (df["Message"] == "Success").mean() >= 0.8
+        ok = df[df["Message"] == "Success"]
+        assert abs(ok["Estimate"].mean() / p.prob_fail_true - 1) < 0.15, p.name
+        assert (df["Cost"] == 1000 * (2 + df["Steps"])).all()
+    p = ree.problems_lowdim[0].set_sample(1000, seed=5000)
+    file = ca.study_cbree_observation_window(p, ree.CBREE(quiet=True), num_runs, dir=str(tmp_path), save_other=True,
+                                             observation_window_range=range(2, 15), other_list=["t_step"],
+                                             addtnl_cols={"col": "val"}, verbose=False)
+    df = pd.read_csv(file)
+    assert len(df.index) == num_runs * 14

@@ -1,5 +1,10 @@
-"""Timings of the other BASELINE.json configurations on one GPU (one rank's share of the multi-GPU ones).
-Usage: python tools/config_bench.py [pde] [osc] [cmc] [sis]     -> one JSON line per configuration."""
+"""Timings of the other BASELINE.json configurations.
+  one GPU (one rank's share of the multi-GPU configurations):
+      python tools/config_bench.py [pde] [osc] [cmc] [sis]
+  the configurations BASELINE.json quotes on 8 GPUs, at their full size, particles sharded over the ranks:
+      python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/config_bench.py osc cmc sis
+      (configs[3]: CBREE oscillator d=6, N=1e8; configs[4]: CMC and SIS-aCS, affine d=100, N=1e8)
+-> one JSON line per configuration (rank 0); times are device times, the maximum over the ranks."""
 import json
 import os
 import sys
@@ -14,7 +19,33 @@ from rareeventestimation_b200.problem import DeviceSample  # noqa: E402
 
 HBM = 6546.6
 which = set(sys.argv[1:]) or {"pde", "osc", "cmc", "sis"}
-eng = Engine.get()
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:
+    import torch.distributed as dist
+    from rareeventestimation_b200.engine import Comm
+
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = Engine.get(torch.device("cuda", local), Comm())
+else:
+    eng = Engine.get()
+
+
+def sync_max(x):
+    """max over the ranks of a host number (after a device synchronisation)."""
+    torch.cuda.synchronize()
+    t = torch.tensor([x], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def say(d):
+    if rank == 0:
+        d["n_gpus"] = world
+        print(json.dumps(d), flush=True)
+
 
 
 def cbree_iterations(prob, n, d, steps=6, warm=2, **kw):
@@ -32,12 +63,11 @@ def cbree_iterations(prob, n, d, steps=6, warm=2, **kw):
     for _ in range(steps):
         solver.advance(cl)
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    ms = sync_max(e0.elapsed_time(e1)) / steps
     return ms, t_start, cl[-1]
 
 
-if "pde" in which:
+if "pde" in which and world == 1:
     n, d = 1_000_000, 150
     prob = ree.diffusion_problem
     ens = eng.philox_normal(n, d, 1, 1)
@@ -55,18 +85,31 @@ if "pde" in which:
     del ens
     eng.drop_pool()
     ms, t_start, last = cbree_iterations(prob, n, d, steps=4, warm=1)
-    print(json.dumps({"config": "CBREE diffusion PDE d=150 N=1e6", "ms_per_iteration": ms, "p_it_per_s": n / ms * 1e3,
-                      "lsf_ms_per_sweep": lsf_ms, "lsf_evals_per_s": n / lsf_ms * 1e3, "lsf_fp64_tflops": flop / lsf_ms / 1e9,
-                      "start_s": t_start, "sigma": last.sigma, "path": eng.path(d)}), flush=True)
+    say({"config": "CBREE diffusion PDE d=150 N=1e6", "ms_per_iteration": ms, "p_it_per_s": n / ms * 1e3,
+         "lsf_ms_per_sweep": lsf_ms, "lsf_evals_per_s": n / lsf_ms * 1e3, "lsf_fp64_tflops": flop / lsf_ms / 1e9,
+         "start_s": t_start, "sigma": last.sigma, "path": eng.path(d)})
     eng.drop_pool()
 
 if "osc" in which:
-    n, d = 12_500_000, 6  # one rank's share of N=1e8 over 8 GPUs
+    n, d = (100_000_000, 6) if world > 1 else (12_500_000, 6)  # N=1e8 over the ranks; alone: one rank's share of 8
     ms, t_start, last = cbree_iterations(ree.prob_nonlin_osc, n, d)
-    bytes_it = n * (24 * d + 48)
-    print(json.dumps({"config": "CBREE oscillator d=6, N=1.25e7 (1/8 of 1e8)", "ms_per_iteration": ms,
-                      "p_it_per_s": n / ms * 1e3, "hbm_frac_iteration": bytes_it / ms / 1e6 / HBM, "start_s": t_start,
-                      "path": eng.path(d)}), flush=True)
+    bytes_it = n / world * (24 * d + 48)
+    say({"config": f"CBREE oscillator d=6, N={n:.3g}" + ("" if world > 1 else " (1/8 of 1e8)"), "ms_per_iteration": ms,
+         "p_it_per_s": n / ms * 1e3, "hbm_frac_iteration": bytes_it / ms / 1e6 / HBM, "start_s": t_start,
+         "path": eng.path(d)})
+    eng.drop_pool()
+    # the complete solve with the reference's defaults (test/test_nonlinear_oscillator_prob.py:4-9 at this size)
+    prob = ree.prob_nonlin_osc
+    prob.sample = DeviceSample(n, d, seed=0x5EED)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sol = ree.CBREE(seed=1, quiet=True).solve(prob)
+    dt = sync_max(time.perf_counter() - t0)
+    say({"config": f"CBREE oscillator d=6, N={n:.3g}: complete solve, reference defaults", "seconds": dt,
+         "steps": int(sol.num_steps), "msg": sol.msg, "pf": float(sol.prob_fail_hist[-1]), "truth": float(prob.prob_fail_true),
+         "rel_err": abs(float(sol.prob_fail_hist[-1]) / float(prob.prob_fail_true) - 1), "lsf_evals": int(sol.costs),
+         "p_it_per_s": sol.costs / dt})
+    del sol
     eng.drop_pool()
 
 if "cmc" in which:
@@ -76,20 +119,21 @@ if "cmc" in which:
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     sol = ree.CMC(n, seed=2, verbose=False).solve(prob)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    print(json.dumps({"config": "CMC affine d=100, N=1e8", "seconds": dt, "samples_per_s": n / dt,
-                      "pf": float(sol.prob_fail_hist[-1]), "truth": float(prob.prob_fail_true)}), flush=True)
+    dt = sync_max(time.perf_counter() - t0)
+    say({"config": "CMC affine d=100, N=1e8", "seconds": dt, "samples_per_s": n / dt,
+         "pf": float(sol.prob_fail_hist[-1]), "truth": float(prob.prob_fail_true)})
     eng.drop_pool()
 
 if "sis" in which:
-    n, d = 10_000_000, 100
+    n, d = (100_000_000, 100) if world > 1 else (10_000_000, 100)  # population per level (80 GB at 1e8: sharded)
     prob = ree.make_linear_problem(d)
     prob.sample = DeviceSample(n, d, seed=5)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     sol = ree.SIS(seed=1, mixture_model="aCS").solve(prob)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    print(json.dumps({"config": "SIS-aCS affine d=100, N=1e7 per level", "seconds": dt, "lsf_evals": int(sol.costs),
-                      "lsf_evals_per_s": sol.costs / dt, "levels": int(sol.num_steps),
-                      "pf": float(sol.prob_fail_hist[-1]), "truth": float(prob.prob_fail_true)}), flush=True)
+    dt = sync_max(time.perf_counter() - t0)
+    say({"config": f"SIS-aCS affine d=100, N={n:.3g} per level", "seconds": dt, "lsf_evals": int(sol.costs),
+         "lsf_evals_per_s": sol.costs / dt, "levels": int(sol.num_steps),
+         "pf": float(sol.prob_fail_hist[-1]), "truth": float(prob.prob_fail_true)})
+if world > 1:
+    dist.destroy_process_group()

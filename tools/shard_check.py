@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 ap = argparse.ArgumentParser()
 ap.add_argument("--out")
 ap.add_argument("--compare", nargs=2)
-ap.add_argument("--n", type=int, default=200_000)
+ap.add_argument("--particles", type=int, default=200_000)
 args = ap.parse_args()
 
 if args.compare:
@@ -53,7 +53,7 @@ for name, prob, d, kw in [("linear d=100", ree.make_linear_problem(100), 100, {}
                           ("oscillator d=6", ree.prob_nonlin_osc, 6, {}),
                           ("linear d=20 vMFNM resample", ree.make_linear_problem(20), 20,
                            dict(resample=True, mixture_model="vMFNM"))]:
-    prob.sample = DeviceSample(args.n, d, seed=0x5EED)
+    prob.sample = DeviceSample(args.particles, d, seed=0x5EED)
     sol = ree.CBREE(seed=3, num_steps=8, convergence_check=False, divergence_check=False, quiet=True,
                     return_caches=True, save_history=True, **kw).solve(prob)
     caches = sol.other["cache_list"]
