@@ -39,7 +39,6 @@ struct XfArgs {
     const double* logdet;
     double* logq;
     double* small;  // per-CTA ExpSums
-    int debug;      // REE_XF_DEBUG (timing experiments only): 1 = producers skip the noise generation, 2 = consumers skip the DMMAs
 };
 
 struct GenStage {  // rows 8q+lc and 8q+4+lc of the warp's staging block at particle column lr, minus the row mean
@@ -299,7 +298,6 @@ __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArg
             mbar_wait(bar_c + 16u * b + 8u, ph ^ 1u);  // buffer b is free (passes at once the first two times)
             const uint64_t particle = (uint64_t)(a.first + wt * 8 + lr);
             constexpr int NQ = (NTB + NPC - 1) / NPC;  // k-pairs q = h + NPC * i, i < NQ
-            if (a.debug != 1)
 #pragma unroll
             for (int i0 = 0; i0 < NQ; i0 += PGB) {
                 double z0[PGB], z1[PGB];
@@ -405,7 +403,6 @@ __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArg
         const uint32_t nzb = nz_c + b * (uint32_t)(NZ * 8);
         const bool have_prev = CONS == 2 && k > 0;
         double2 bq = lds128(nzb);
-        if (a.debug != 2)
 #pragma unroll
         for (int q = 0; q < NTB; ++q) {
             if (EXACT || q < ntd) {
@@ -872,14 +869,6 @@ static int launch_xf_bucket(const SplitCfg& c, const XfArgs& a, cudaStream_t st)
     const int sms = ree_grid_ctas() / 2;  // persistent: one CTA per SM
     const int64_t nwt = (a.n + 7) / 8;
     if constexpr (MODE == 1 && TRI) {
-        if (!a.z && c.ntb == 13 && (a.d + 7) / 8 == 13 && xf_variant() >= 7) {  // experiments: phased, unspecialised
-            const int v = xf_variant();
-            if (v == 7) { const int64_t w = (nwt + 11) / 12; return launch_xf<1, 13, 12, true, true, 13>(a, (int)(w < sms ? w : sms), st); }
-            if (v == 8) { const int64_t w = (nwt + 11) / 12; return launch_xf<1, 13, 12, true, true, 7>(a, (int)(w < sms ? w : sms), st); }
-            if (v == 9) { const int64_t w = (nwt + 15) / 16; return launch_xf<1, 13, 16, true, true, 13>(a, (int)(w < sms ? w : sms), st); }
-            if (v == 10) { const int64_t w = (nwt + 7) / 8; return launch_xf<1, 13, 8, true, true, 13>(a, (int)(w < sms ? w : sms), st); }
-            if (v == 11) { const int64_t w = (nwt + 11) / 12; return launch_xf<1, 13, 12, true, true, 4>(a, (int)(w < sms ? w : sms), st); }
-        }
         if (!a.z && xf_ws()) {  // Philox noise: producer / consumer warps
             if (c.ntb == 7) return launch_xf_ws_variants<7, 8>(a, st);
             if (c.ntb == 13) return launch_xf_ws_variants<13, 8>(a, st);
@@ -936,14 +925,6 @@ int ree_split_step(const double* x, double* x_new, int64_t n, int d, int64_t ld,
     a.x = x; a.n = n; a.ld = ld; a.d = d; a.A = F; a.x_new = x_new; a.t = t; a.m_noise = m_noise; a.z = z;
     a.seed = seed; a.draw = draw; a.first = first; a.lsf_mode = lsf_mode; a.coef = coef; a.offset = offset;
     a.g_new = g_new; a.e_new = e_new;
-    {
-        static int dbg = -1;
-        if (dbg < 0) {
-            const char* e = getenv("REE_XF_DEBUG");
-            dbg = e ? atoi(e) : 0;
-        }
-        a.debug = dbg;
-    }
     return tri ? launch_xf_bucket<1, true>(c, a, st) : launch_xf_bucket<1, false>(c, a, st);
 }
 
