@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--ref-n", type=int, default=100_000, help="particles of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-fp64-probe", action="store_true", help="skip the in-line fp64 peak probe (profiling runs)")
     ap.add_argument("--no-code-warmup", action="store_true",
                     help="skip the small warm-up solve (profiling runs under ncu: its launches would fill the capture)")
     return ap.parse_args()
@@ -352,7 +353,7 @@ def run_b200(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     fp64_peak, fp64_src = None, None
-    if rank == 0 and world == 1 and os.path.exists(os.path.join(ROOT, "tools", "fp64_peak")):
+    if rank == 0 and world == 1 and not args.no_fp64_probe and os.path.exists(os.path.join(ROOT, "tools", "fp64_peak")):
         # the fp64 roofline denominator measured in this very run (dependent-free DFMA / DMMA chains, < 1 s), with the
         # SM clock sampled while it runs
         try:

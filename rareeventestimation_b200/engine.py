@@ -536,7 +536,7 @@ class Engine:
         return bool(comm.peer)
 
     def adapt(self, ens: Ensemble, tgt_kind: int, sigma: float, sigma_hi: Optional[float], cvar_tgt: float, beta: float,
-              do_beta: bool, ess_tgt_n: float) -> np.ndarray:
+              do_beta: bool, ess_tgt_n: float, overlap=None) -> np.ndarray:
         """sigma / beta searches of one iteration in one persistent kernel (``ree_cbree_adapt``): bounded Brent over
         sigma in [sigma, sigma_hi] (skipped if ``sigma_hi`` is None), then the hybrd root find over beta (or only the ESS
         of (sigma, beta)).  Returns the 16 result doubles on the host; needs :meth:`peers_connected`."""
@@ -550,6 +550,8 @@ class Engine:
         check(self.lib.ree_cbree_adapt(ens.g.data_ptr(), ens.e.data_ptr() if ens.e is not None else None, ens.n,
                                        C.byref(p), ell.data_ptr(), ws.data_ptr(), out.data_ptr(), self.stream),
               "ree_cbree_adapt")
+        if overlap is not None:
+            overlap()
         return self.fetch(out, 16)
 
     def vector_range(self, v: torch.Tensor, n: int, d: int) -> torch.Tensor:

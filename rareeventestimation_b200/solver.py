@@ -686,7 +686,7 @@ class CBREE(Solver):
         return self._eng.logtgt(dev.g, dev.e, dev.n, cache.sigma, self._tgt_kind(),
                                 out=self._eng.scratch("ell", dev.ld))
 
-    def _update_beta_and_sigma_device(self, cache: CBREECache) -> None:
+    def _update_beta_and_sigma_device(self, cache: CBREECache, overlap=None) -> None:
         """solver.py:505-523 with both searches inside one kernel (``ree_cbree_adapt``): one launch and one readback
         per iteration instead of ~25 host-driven objective evaluations.  Outcomes, messages and failure paths are those
         of :meth:`_update_sigma_cvar` / :meth:`_update_beta`."""
@@ -708,7 +708,7 @@ class CBREE(Solver):
         if self.sigma_adaptivity == "sfp":
             self._update_sigma_sfp(cache)
         out = eng.adapt(dev, self._tgt_kind(), cache.sigma, sigma_hi, self.cvar_tgt, cache.beta,
-                        bool(self.beta_adaptivity), self.ess_tgt * cache._n_total)
+                        bool(self.beta_adaptivity), self.ess_tgt * cache._n_total, overlap=overlap)
         cache._search = (int(out[5]), int(out[6]), int(out[3]), int(out[4]))  # evaluations and exit codes
         if sigma_hi is not None:
             if out[3] == -1:  # my_log_cvar on a vector without finite entries (utilities.py:92)
@@ -730,10 +730,12 @@ class CBREE(Solver):
         else:
             _log.info(f"Iteration {cache.iteration}: {msg}")
 
-    def _update_beta_and_sigma(self, cache: CBREECache) -> None:
-        """solver.py:505-523."""
+    def _update_beta_and_sigma(self, cache: CBREECache, overlap=None) -> None:
+        """solver.py:505-523.  ``overlap`` is host work that may run while the device searches (device path only)."""
         if self.search == "device" and self._eng.peers_connected():
-            return self._update_beta_and_sigma_device(cache)
+            return self._update_beta_and_sigma_device(cache, overlap)
+        if overlap is not None:
+            overlap()
         if self.sigma_adaptivity == "cvar":
             self._update_sigma_cvar(cache)
         if self.sigma_adaptivity == "sfp":
@@ -749,21 +751,31 @@ class CBREE(Solver):
     # ------------------------------------------------------------------ #
     # the step
     # ------------------------------------------------------------------ #
-    def _perform_step(self, cache: CBREECache) -> CBREECache:
-        """solver.py:642-694 (GM branch).  sweep 1 (``ree_cbree_step``) + post-processing (sweep 2)."""
+    def _prepare_step(self, cache: CBREECache) -> dict:
+        """Everything of :meth:`_perform_step` that does not depend on the sigma / beta of this iteration (runs on the
+        host while the search kernel works): noise mean, conditioning shifts of the one-pass Grams, the small upload,
+        the target ensemble."""
         eng, src = self._eng, cache._dev
         n, d = src.n, src.d
         t = float(cache.t_step)
         m_noise = (1 - t) * cache.weighted_mean
+        shift_u_h = t * cache.ens_mean + m_noise  # predicted unweighted mean; the weighted Gram is shifted by m_w
+        small = eng.to_device_small(np.concatenate([m_noise, shift_u_h, cache.weighted_mean]))
+        return dict(t=t, small=small, dst=eng.alloc_ensemble(n, d, first=src.first), desc=self._lsf_descriptor(d))
+
+    def _perform_step(self, cache: CBREECache, prep: Optional[dict] = None) -> CBREECache:
+        """solver.py:642-694 (GM branch).  sweep 1 (``ree_cbree_step``) + post-processing (sweep 2)."""
+        eng, src = self._eng, cache._dev
+        n, d = src.n, src.d
+        if isinstance(prep, dict) and "error" in prep:
+            raise prep["error"]
+        if not prep or prep.get("t") != float(cache.t_step):
+            prep = self._prepare_step(cache)
+        t, small, dst, desc = prep["t"], prep["small"], prep["dst"], prep["desc"]
         scale = (1 - t**2) * (1 + cache.beta)
-        dst = eng.alloc_ensemble(n, d, first=src.first)
         split = eng.path(d) == 2  # transform only; the moments come from the one-pass Gram kernel afterwards
         sums = None if split else eng.empty(d + d * d + 2)
-        # conditioning shifts of the one-pass Grams: predicted unweighted mean, previous weighted mean
-        shift_u_h = t * cache.ens_mean + m_noise
-        small = eng.to_device_small(np.concatenate([m_noise, shift_u_h, cache.weighted_mean]))
         m_noise_d, shift_u, shift_w = small[0:d], small[d:2 * d], small[2 * d:3 * d]
-        desc = self._lsf_descriptor(d)
         resample = self.resample and self.mixture_model == "vMFNM"
         step_desc = None if resample else desc  # the transformed ensemble of the resampling branch is only fitted
         if self.noise == "numpy":
@@ -1028,9 +1040,17 @@ class CBREE(Solver):
         (the text is kept for ``Solution.msg``)."""
         if self.stepsize_adaptivity and len(cache_list) > 1 and cache_list[-1].iteration % 2 == 0:
             self._update_stepsize(cache_list)
-        self._update_beta_and_sigma(cache_list[-1])
+        prep = {}
+
+        def prepare():  # host-side preparation of the step, overlapped with the search kernel
+            try:
+                prep.update(self._prepare_step(cache_list[-1]))
+            except Exception as e:  # noqa: BLE001  (re-raised inside the step's own error handling below)
+                prep["error"] = e
+
+        self._update_beta_and_sigma(cache_list[-1], overlap=prepare)
         try:
-            cache_list.append(self._perform_step(cache_list[-1]))
+            cache_list.append(self._perform_step(cache_list[-1], prep))
         except Exception as e:
             self._msg = str(e)
             if not self.verbose:

@@ -63,6 +63,7 @@ def cbree_iterations(prob, n, d, steps=6, warm=2, **kw):
     for _ in range(steps):
         solver.advance(cl)
     e1.record()
+    torch.cuda.synchronize()
     ms = sync_max(e0.elapsed_time(e1)) / steps
     return ms, t_start, cl[-1]
 
