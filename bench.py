@@ -391,7 +391,8 @@ def run_b200(args):
     names = {"step": "ree_cbree_step", "moments": "ree_cbree_moments", "maha": "ree_cbree_maha"}
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tr_file = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        tr = json.load(open(tr_file if os.path.exists(tr_file) else os.path.join(ROOT, "profiles", "r1_traffic.json")))
         if split and int(tr.get("d", -1)) == d:
             traffic = tr["bytes_per_particle"][names[dom]] * n_local
     except Exception:
