@@ -179,17 +179,22 @@ class ThreadComm(Comm):
         if not self.enabled:
             return t
         g = self.tgroup
-        torch.cuda.current_stream(t.device).synchronize()  # this rank's contribution is final
+        self._drain(t)  # this rank's contribution is final
         g.slots[self.rank] = t
         self._sync_point()
         acc = None
         for r in range(self.world):  # rank order on every rank: identical bits
             part = g.slots[r] if r == self.rank else g.slots[r].to(t.device)
             acc = part.clone() if acc is None else acc.add_(part)
-        torch.cuda.current_stream(t.device).synchronize()  # all peer reads are done ...
-        self._sync_point()                                  # ... on every rank, before anybody's buffer changes
+        self._drain(t)       # all peer reads are done ...
+        self._sync_point()   # ... on every rank, before anybody's buffer changes
         t.copy_(acc)
         return t
+
+    @staticmethod
+    def _drain(t: torch.Tensor) -> None:
+        if t.is_cuda:
+            torch.cuda.current_stream(t.device).synchronize()
 
     def combine_expsums_(self, out4: torch.Tensor) -> torch.Tensor:
         if self.enabled:
@@ -214,11 +219,11 @@ class ThreadComm(Comm):
         if not self.enabled:
             return t.clone()
         g = self.tgroup
-        torch.cuda.current_stream(t.device).synchronize()
+        self._drain(t)
         g.slots[self.rank] = t
         self._sync_point()
         out = torch.cat([g.slots[r] if r == self.rank else g.slots[r].to(t.device) for r in range(self.world)])
-        torch.cuda.current_stream(t.device).synchronize()
+        self._drain(t)
         self._sync_point()
         return out
 

@@ -254,3 +254,71 @@ def test_solver_is_deep_copyable_after_a_solve():
     assert c.rng is not s.rng
     d = deepcopy(c)
     assert d.rng is not c.rng and d.rng.integers(0, 10**9) == deepcopy(c).rng.integers(0, 10**9)
+
+
+def test_thread_comm_three_ranks_cpu():
+    """The communicator of ``CBREE(devices=N)`` (one host thread per device, engine.ThreadComm) on CPU tensors with three
+    threads: shards cover the particles, the packed sums are added in rank order (identical bits on every rank),
+    objects are broadcast, vectors gathered in rank order; a failing rank releases the others instead of hanging them."""
+    import threading
+
+    import torch
+
+    from rareeventestimation_b200.engine import ThreadComm, ThreadGroup
+
+    world = 3
+    tg = ThreadGroup(list(range(world)))
+    n, d = 1000, 4
+    X = np.random.default_rng(7).standard_normal((n, d)) * 1e3
+    out = [None] * world
+
+    def work(r):
+        comm = ThreadComm(tg, r)
+        lo, hi = comm.shard(n)
+        part = torch.from_numpy(np.concatenate([X[lo:hi].sum(0), (X[lo:hi].T @ X[lo:hi]).ravel(), [hi - lo]]))
+        total = comm.allreduce_sum_(part.clone())
+        seed = comm.broadcast_object(1234 + r, src=1)
+        gathered = comm.all_gather_vec(torch.tensor([float(lo), float(hi)], dtype=torch.float64))
+        out[r] = (lo, hi, total.numpy().copy(), seed, gathered.numpy().copy())
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert [o[:2] for o in out] == [(0, 334), (334, 667), (667, 1000)]
+    want = np.concatenate([X.sum(0), (X.T @ X).ravel(), [n]])
+    for r in range(world):
+        np.testing.assert_allclose(out[r][2], want, rtol=1e-12)
+        np.testing.assert_array_equal(out[r][2], out[0][2])
+        assert out[r][3] == 1235
+        np.testing.assert_array_equal(out[r][4], [0, 334, 334, 667, 667, 1000])
+    # a rank that dies aborts the barrier: the others raise instead of waiting forever
+    tg2 = ThreadGroup([0, 1])
+    errs = []
+
+    def survivor():
+        try:
+            ThreadComm(tg2, 0).allreduce_sum_(torch.zeros(3, dtype=torch.float64))
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    t = threading.Thread(target=survivor)
+    t.start()
+    tg2.barrier.abort()
+    t.join(timeout=30)
+    assert not t.is_alive() and len(errs) == 1
+
+
+def test_get_slope_matches_polyfit():
+    """The closed form behind get_slope equals the reference's polyfit call (utilities.py:145-163) to rounding."""
+    import warnings
+
+    import rareeventestimation_b200 as ree
+
+    rng = np.random.default_rng(3)
+    for n in [2, 3, 5, 14, 40]:
+        y = rng.standard_normal(n) * 10.0 ** int(rng.integers(-3, 4))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = np.polyfit(np.arange(n), y, deg=1, full=True)[0][0]
+        assert ree.get_slope(y) == pytest.approx(want, rel=1e-12, abs=1e-15 * np.abs(y).max())
+    assert math.isnan(ree.get_slope([1.0]))
