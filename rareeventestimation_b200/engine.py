@@ -322,6 +322,7 @@ class Engine:
         self._scratch = {}
         self._staging = None
         self._pin_ring, self._pin_next, self._pin_down, self._side = None, 0, None, None
+        self._pin_slots = [None, None]
         self._fetch_buf = np.empty(64, dtype=np.float64)
         with torch.cuda.device(self.device):
             self.num_ctas = self.lib.ree_num_ctas()
@@ -385,6 +386,18 @@ class Engine:
         self._pin_down[:n].copy_(t.reshape(-1), non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return self._pin_down[:n].numpy()
+
+    def to_host_async(self, t: torch.Tensor, slot: int):
+        """Stream-ordered readback into pinned buffer `slot` (0 or 1): returns (host view, event).  The view is valid once
+        the event has completed and until the next readback into the same slot."""
+        n = t.numel()
+        if self._pin_slots[slot] is None or self._pin_slots[slot].numel() < n:
+            self._pin_slots[slot] = torch.empty(max(n, 1 << 12), dtype=F64, pin_memory=True)
+        buf = self._pin_slots[slot][:n]
+        buf.copy_(t.reshape(-1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return buf.numpy(), ev
 
     def side_stream(self) -> "torch.cuda.Stream":
         if self._side is None:
@@ -541,7 +554,7 @@ class Engine:
         return bool(comm.peer)
 
     def adapt(self, ens: Ensemble, tgt_kind: int, sigma: float, sigma_hi: Optional[float], cvar_tgt: float, beta: float,
-              do_beta: bool, ess_tgt_n: float, overlap=None) -> np.ndarray:
+              do_beta: bool, ess_tgt_n: float, overlap=None, wait: bool = True) -> Optional[np.ndarray]:
         """sigma / beta searches of one iteration in one persistent kernel (``ree_cbree_adapt``): bounded Brent over
         sigma in [sigma, sigma_hi] (skipped if ``sigma_hi`` is None), then the hybrd root find over beta (or only the ESS
         of (sigma, beta)).  Returns the 16 result doubles on the host; needs :meth:`peers_connected`."""
@@ -555,9 +568,15 @@ class Engine:
         check(self.lib.ree_cbree_adapt(ens.g.data_ptr(), ens.e.data_ptr() if ens.e is not None else None, ens.n,
                                        C.byref(p), ell.data_ptr(), ws.data_ptr(), out.data_ptr(), self.stream),
               "ree_cbree_adapt")
+        if not wait:
+            return None
         if overlap is not None:
             overlap()
         return self.fetch(out, 16)
+
+    def adapt_result(self) -> np.ndarray:
+        """The 16 result doubles of the last :meth:`adapt` launch on this device (synchronising)."""
+        return self.fetch(self.scratch("adapt_out", 16), 16)
 
     def vector_range(self, v: torch.Tensor, n: int, d: int) -> torch.Tensor:
         """Device [max, min] over the finite entries of this rank's part of an N-vector."""

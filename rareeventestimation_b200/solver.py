@@ -430,10 +430,16 @@ class CBREE(Solver):
     # post-processing of an ensemble: moments, IS density, weights  (device)
     # ------------------------------------------------------------------ #
     def _post_ensemble(self, cache: CBREECache, sums_ready=None,
-                       shift_u=None, shift_w=None, model=None):
+                       shift_u=None, shift_w=None, model=None, defer=False):
         """Everything the reference derives from (X, g, e, sigma, beta) of one cache:
         unweighted mean/cov + factorisation (solver.py:670-674), ESS shift (my_softmax), Mahalanobis sweep with
-        IS statistics (683-686, 843-846) and the weighted mean/cov (629-636).  One D2H copy at the end."""
+        IS statistics (683-686, 843-846) and the weighted mean/cov (629-636).
+
+        Split path: what the NEXT iteration's control flow needs -- both means / covariances, the ESS tuple, the failure
+        count -- is read back BEFORE the factorisation and the Mahalanobis / IS sweep are enqueued, so the host works on
+        it while the GPU runs those; their results (pivot statistics, IS tuple) arrive with a second small readback.
+        ``defer=True`` returns after the first one; :meth:`_finish_post` completes the cache."""
+        self._finish_post(getattr(self, "_open_post", None))
         eng, dev = self._eng, cache._dev
         d = dev.d
         kind = self._tgt_kind()
@@ -446,19 +452,14 @@ class CBREE(Solver):
         stats, is4, ess4 = res[o:o + 8], res[o + 8:o + 12], res[o + 12:o + 16]
         tails = res[o + 16:o + 20]
         L, Linv = eng.empty(d * d), eng.empty(d * d)
-        if eng.path(d) == 2 and sums_ready is None:
-            # split path: log-weights + softmax shift, both Grams in one pass, factorisation, Mahalanobis / IS pass
+        early = eng.path(d) == 2 and sums_ready is None
+        if early:
+            # split path: log-weights + softmax shift, both Grams in one pass, moments of both
             a_vec = eng.scratch("logw", dev.ld)
             eng.reduce_ess(dev, cache.sigma, cache.beta, kind, out=ess4, a_out=a_vec)
             sums_uw = eng.empty(2 * slen)
             sums_u, sums_w = eng.cbree_moments(dev, a_vec, ess4[0:1], shift_u, sums_uw)
-            eng.moments_chol(sums_u, shift_u, d, 1, False, mean, cov, L, Linv, stats)
-            if model is None:
-                eng.cbree_maha(dev, mean, Linv, stats[0:1], cache.sigma, cache.beta, kind, None, None, is4)
-            elif getattr(model, "_is4_dev", None) is not None:  # already computed with g and e of the redraw
-                is4.copy_(model._is4_dev)
-            else:  # the ensemble was drawn from the fitted vMFN model: its density replaces the Gaussian fit
-                model.logpdf_device(eng, dev, is4=is4)
+            eng.moments_chol(sums_u, shift_u, d, 1, False, mean, cov)  # mean / cov only; factorised after the readback
             eng.moments_chol(sums_w, shift_u, d, 0, True, m_w, C_w)
         else:
             if sums_ready is None:
@@ -493,7 +494,21 @@ class CBREE(Solver):
                 F0_event.record(side)
             res.record_stream(side)
             F0.record_stream(main)
-        host = eng.to_host(res)  # the one synchronising D2H of the iteration (pinned)
+        if early:
+            host, ev_a = eng.to_host_async(res, 0)
+            # enqueued behind the readback: factorisation (+ inverse, eigenvalue brackets) and the Mahalanobis / IS sweep
+            eng.moments_chol(sums_u, shift_u, d, 1, False, mean, cov, L, Linv, stats)
+            if model is None:
+                eng.cbree_maha(dev, mean, Linv, stats[0:1], cache.sigma, cache.beta, kind, None, None, is4)
+            elif getattr(model, "_is4_dev", None) is not None:  # already computed with g and e of the redraw
+                is4.copy_(model._is4_dev)
+            else:  # the ensemble was drawn from the fitted vMFN model: its density replaces the Gaussian fit
+                model.logpdf_device(eng, dev, is4=is4)
+            host_b, ev_b = eng.to_host_async(res[o:o + 12], 1)
+            ev_a.synchronize()
+        else:
+            host = eng.to_host(res)  # the one synchronising D2H of the iteration (pinned)
+            host_b, ev_b = host[o:o + 12], None
         self._peer_checks = getattr(self, "_peer_checks", 0) + 1
         if self._peer_checks % 16 == 1:  # (a 4-byte synchronising copy of the time-out flag: not every iteration)
             eng.comm.check_peers()
@@ -501,20 +516,36 @@ class CBREE(Solver):
         cache.ens_cov = host[d:d + d * d].reshape(d, d).copy()
         cache.weighted_mean = host[d + d * d:2 * d + d * d].copy()
         cache.weighted_cov = host[2 * d + d * d:o].reshape(d, d).copy()
-        st, i4, e4, tl = host[o:o + 8], host[o + 8:o + 12], host[o + 12:o + 16], host[o + 16:o + 20]
+        e4, tl = host[o + 12:o + 16], host[o + 16:o + 20]
         cache._stats = dict(C_w=C_w, F0=F0, F0_event=F0_event)  # views into `res`; the O(N) scratch is released here
         cache._vmfn_density = model is not None
+        cache.num_failed = float(tl[0])
+        cache._ess4 = e4.copy()
+        cache._n_total = float(tl[1])
+        cache._pending_b = (host_b, ev_b)
+        self._open_post = cache
+        if e4[3] <= 0:  # my_softmax on an all-non-finite vector (utilities.py:121)
+            self._open_post = None
+            raise ValueError("attempt to get argmax of an empty sequence")
+        if not defer:
+            self._finish_post(cache)
+        return cache
+
+    def _finish_post(self, cache: Optional[CBREECache]) -> None:
+        """Second readback of :meth:`_post_ensemble`: pivot statistics of the Gaussian fit and the IS tuple."""
+        if cache is None or getattr(cache, "_pending_b", None) is None:
+            return
+        host_b, ev_b = cache._pending_b
+        cache._pending_b = None
+        if getattr(self, "_open_post", None) is cache:
+            self._open_post = None
+        if ev_b is not None:
+            ev_b.synchronize()
+        st, i4 = host_b[0:8], host_b[8:12]
         cache._chol_info = int(st[1])
         cache._min_pivot, cache._max_diag = float(st[2]), float(st[3])
         cache._tr_inv, cache._norm_inf = float(st[4]), float(st[5])
-        cache.num_failed = float(tl[0])
-        n_tot = float(tl[1])
-        cache._is4 = i4.copy()
-        cache._ess4 = e4.copy()
-        cache._n_total = n_tot
-        if e4[3] <= 0:  # my_softmax on an all-non-finite vector (utilities.py:121)
-            raise ValueError("attempt to get argmax of an empty sequence")
-        return cache
+        cache._is4 = np.array(i4, dtype=np.float64)
 
     def _finish_is_stats(self, cache: CBREECache):
         """cvar_is_weights (solver.py:683-686) and the IS estimate (843-846) from the sweep-2 sums."""
@@ -686,29 +717,77 @@ class CBREE(Solver):
         return self._eng.logtgt(dev.g, dev.e, dev.n, cache.sigma, self._tgt_kind(),
                                 out=self._eng.scratch("ell", dev.ld))
 
-    def _update_beta_and_sigma_device(self, cache: CBREECache, overlap=None) -> None:
-        """solver.py:505-523 with both searches inside one kernel (``ree_cbree_adapt``): one launch and one readback
-        per iteration instead of ~25 host-driven objective evaluations.  Outcomes, messages and failure paths are those
-        of :meth:`_update_sigma_cvar` / :meth:`_update_beta`."""
-        eng, dev = self._eng, cache._dev
-        sigma_hi = None
+    def _sigma_sfp_value(self, cache: CBREECache, t_step) -> float:
+        """sigma after the closed-form update of solver.py:564-580 for step size ``t_step`` (nothing is modified)."""
+        delta_max = self.lip_sigma * np.log(1 / t_step)
+        if self.sfp_tgt > np.finfo(float).eps:
+            delta = np.sqrt(np.maximum(0, self.sfp_tgt - self._sfp_now(cache))) * delta_max / np.sqrt(self.sfp_tgt)
+        else:
+            delta = 0
+        return cache.sigma + delta
+
+    def _search_args(self, cache: CBREECache, t_step) -> tuple:
+        """What the search kernel is launched with for this cache and step size -- a pure function of the cache's
+        host-side state: (sigma the searches start from, upper bound of the Brent search or None, failure note or None)."""
+        sigma, sigma_hi, note = cache.sigma, None, None
         if self.sigma_adaptivity == "cvar":
             try:
                 if self._sfp_now(cache) < self.sfp_tgt:
-                    self._update_sigma_sfp(cache)
+                    sigma = self._sigma_sfp_value(cache, t_step)
                 else:
-                    sigma_hi = cache.sigma + self.lip_sigma * np.log(1 / cache.t_step)
+                    sigma_hi = cache.sigma + self.lip_sigma * np.log(1 / t_step)
                     if not (math.isfinite(cache.sigma) and math.isfinite(sigma_hi)):
                         raise ValueError("Optimization bounds must be finite scalars.")
                     if cache.sigma > sigma_hi:
                         raise ValueError("The lower bound exceeds the upper bound.")
             except Exception as e:
-                sigma_hi = None
-                self._note_failure(cache, f"Failed to update sigma: {str(e)}")
+                sigma, sigma_hi, note = cache.sigma, None, f"Failed to update sigma: {str(e)}"
         if self.sigma_adaptivity == "sfp":
-            self._update_sigma_sfp(cache)
-        out = eng.adapt(dev, self._tgt_kind(), cache.sigma, sigma_hi, self.cvar_tgt, cache.beta,
-                        bool(self.beta_adaptivity), self.ess_tgt * cache._n_total, overlap=overlap)
+            sigma = self._sigma_sfp_value(cache, t_step)
+        return (float(sigma), None if sigma_hi is None else float(sigma_hi), note, float(cache.beta),
+                bool(self.beta_adaptivity), float(self.ess_tgt * cache._n_total), self._tgt_kind(), float(self.cvar_tgt))
+
+    def _launch_search(self, cache: CBREECache, args: tuple, overlap=None, wait=True):
+        sigma, sigma_hi, _, beta, do_beta, ess_n, kind, cvar_tgt = args
+        return self._eng.adapt(cache._dev, kind, sigma, sigma_hi, cvar_tgt, beta, do_beta, ess_n, overlap=overlap, wait=wait)
+
+    def _speculate_search(self, cache_list: list):
+        """Launch the NEXT iteration's sigma / beta search now (behind the Mahalanobis sweep already in the stream): its
+        inputs -- g, e, the failure count, the step size the controller will choose -- are all known once the moments
+        of the new ensemble are on the host.  Nothing of the cache is modified; the next :meth:`advance` recomputes the
+        arguments and takes the result over if they are identical (else it searches again)."""
+        cache = cache_list[-1]
+        t_next = cache.t_step
+        if self.stepsize_adaptivity and len(cache_list) > 1 and cache.iteration % 2 == 0:
+            t_next = self._stepsize_value(cache_list)
+        args = self._search_args(cache, t_next)
+        self._launch_search(cache, args, wait=False)
+        pend = dict(cache=cache, args=args, t_next=t_next, prep=None)
+        try:  # the step's host-side preparation as well (it only depends on the step size), while the GPU is busy
+            keep, cache.t_step = cache.t_step, t_next
+            pend["prep"] = self._prepare_step(cache)
+        except Exception:  # noqa: BLE001  (the next advance prepares again and reports the error in the usual place)
+            pend["prep"] = None
+        finally:
+            cache.t_step = keep
+        return pend
+
+    def _update_beta_and_sigma_device(self, cache: CBREECache, overlap=None, pending=None) -> None:
+        """solver.py:505-523 with both searches inside one kernel (``ree_cbree_adapt``): one launch and one readback
+        per iteration instead of ~25 host-driven objective evaluations.  Outcomes, messages and failure paths are those
+        of :meth:`_update_sigma_cvar` / :meth:`_update_beta`."""
+        eng = self._eng
+        args = self._search_args(cache, cache.t_step)
+        sigma0, sigma_hi, note = args[0], args[1], args[2]
+        if note is not None:
+            self._note_failure(cache, note)
+        cache.sigma = sigma0  # (the closed-form update, if it applied)
+        if pending is not None and pending["cache"] is cache and pending["args"] == args:
+            if overlap is not None:  # the search was launched at the end of the previous iteration
+                overlap()
+            out = eng.adapt_result()
+        else:
+            out = self._launch_search(cache, args, overlap=overlap)
         cache._search = (int(out[5]), int(out[6]), int(out[3]), int(out[4]))  # evaluations and exit codes
         if sigma_hi is not None:
             if out[3] == -1:  # my_log_cvar on a vector without finite entries (utilities.py:92)
@@ -730,10 +809,10 @@ class CBREE(Solver):
         else:
             _log.info(f"Iteration {cache.iteration}: {msg}")
 
-    def _update_beta_and_sigma(self, cache: CBREECache, overlap=None) -> None:
+    def _update_beta_and_sigma(self, cache: CBREECache, overlap=None, pending=None) -> None:
         """solver.py:505-523.  ``overlap`` is host work that may run while the device searches (device path only)."""
         if self.search == "device" and self._eng.peers_connected():
-            return self._update_beta_and_sigma_device(cache, overlap)
+            return self._update_beta_and_sigma_device(cache, overlap, pending)
         if overlap is not None:
             overlap()
         if self.sigma_adaptivity == "cvar":
@@ -763,8 +842,9 @@ class CBREE(Solver):
         small = eng.to_device_small(np.concatenate([m_noise, shift_u_h, cache.weighted_mean]))
         return dict(t=t, small=small, dst=eng.alloc_ensemble(n, d, first=src.first), desc=self._lsf_descriptor(d))
 
-    def _perform_step(self, cache: CBREECache, prep: Optional[dict] = None) -> CBREECache:
-        """solver.py:642-694 (GM branch).  sweep 1 (``ree_cbree_step``) + post-processing (sweep 2)."""
+    def _perform_step(self, cache: CBREECache, prep: Optional[dict] = None, defer: bool = False) -> CBREECache:
+        """solver.py:642-694 (GM branch).  sweep 1 (``ree_cbree_step``) + post-processing (sweep 2).  With ``defer`` the
+        new cache comes back as soon as the moments are on the host; :meth:`_complete_step` finishes it."""
         eng, src = self._eng, cache._dev
         n, d = src.n, src.d
         if isinstance(prep, dict) and "error" in prep:
@@ -818,10 +898,15 @@ class CBREE(Solver):
         new.t_step = cache.t_step
         new.num_lsf_evals = self.lsf.counter
         new._cw_dirty = False
-        self._post_ensemble(new, sums_ready=sums, shift_u=shift_u, shift_w=shift_w, model=model)
+        self._post_ensemble(new, sums_ready=sums, shift_u=shift_u, shift_w=shift_w, model=model, defer=defer)
+        if not defer:
+            self._complete_step(new)
+        return new
+
+    def _complete_step(self, new: CBREECache) -> None:
+        self._finish_post(new)
         self._finish_is_stats(new)
         self._compute_weights_check(new)
-        return new
 
     def _vmfn_redraw(self, dev: Ensemble) -> VMFNMixture:
         """``model = VMFNMixture(1); model.fit(X); X = model.sample(N, rng)`` on the device ensemble ``dev`` (in place)
@@ -883,6 +968,9 @@ class CBREE(Solver):
         return np.concatenate((m[None, ...], np.tril(c)))
 
     def _update_stepsize(self, cache_list: list) -> None:
+        cache_list[-1].t_step = self._stepsize_value(cache_list)
+
+    def _stepsize_value(self, cache_list: list):
         """Embedded two-stage error estimate on (mean, tril cov) of the last two ensembles (solver.py:740-781);
         the moments were produced by the sweeps, nothing N-sized is touched.  Evaluated on the mean and the lower
         triangle only: the zeros of the upper triangle of ``tril`` add nothing to the sum of squares, they only count
@@ -909,7 +997,7 @@ class CBREE(Solver):
         w = self.stepsize_tolerance + self.stepsize_tolerance * np.maximum(abs(x), abs(x_hat))
         err = np.sqrt(np.sum((delta / w) ** 2) / ((d + 1) * d))
         q = 0.9 * np.sqrt(1 / err)
-        ch2.t_step = np.maximum(np.exp(-100), np.minimum(np.exp(-1e-5), np.exp(-q * h)))
+        return np.maximum(np.exp(-100), np.minimum(np.exp(-1e-5), np.exp(-q * h)))
 
     def _compute_initial_stepsize(self, cache: CBREECache) -> None:
         """solver.py:783-817, including the trial Euler step and the ``(f0 - f2/w)`` parenthesisation."""
@@ -1038,21 +1126,40 @@ class CBREE(Solver):
     def advance(self, cache_list: list) -> bool:
         """One pass of the loop body of ``solve`` (solver.py:413-467).  False if the step or the callback failed
         (the text is kept for ``Solution.msg``)."""
+        pending, self._pending = getattr(self, "_pending", None), None
+        if pending is not None and pending["cache"] is not cache_list[-1]:
+            self._drop_pending(pending)
+            pending = None
         if self.stepsize_adaptivity and len(cache_list) > 1 and cache_list[-1].iteration % 2 == 0:
-            self._update_stepsize(cache_list)
+            if pending is not None:  # computed (from the same two caches) when the search was launched ahead
+                cache_list[-1].t_step = pending["t_next"]
+            else:
+                self._update_stepsize(cache_list)
         prep = {}
 
         def prepare():  # host-side preparation of the step, overlapped with the search kernel
+            if pending is not None and pending["prep"] is not None:
+                prep.update(pending["prep"])
+                return
             try:
                 prep.update(self._prepare_step(cache_list[-1]))
             except Exception as e:  # noqa: BLE001  (re-raised inside the step's own error handling below)
                 prep["error"] = e
 
-        self._update_beta_and_sigma(cache_list[-1], overlap=prepare)
+        self._update_beta_and_sigma(cache_list[-1], overlap=prepare, pending=pending)
+        # The next search can be launched before this step's Mahalanobis sweep has finished when nothing can change the
+        # new cache in between (no callback) and the search runs on the device.
+        speculate = (self.callback is None and self.search == "device" and self._eng.peers_connected()
+                     and self._eng.path(cache_list[-1]._dev.d) == 2)
         try:
-            cache_list.append(self._perform_step(cache_list[-1], prep))
+            new = self._perform_step(cache_list[-1], prep, defer=speculate)
+            if speculate:
+                self._pending = self._speculate_search(cache_list + [new])
+                self._complete_step(new)
+            cache_list.append(new)
         except Exception as e:
             self._msg = str(e)
+            self._pending = None
             if not self.verbose:
                 warn(str(e))
             return False
@@ -1073,6 +1180,11 @@ class CBREE(Solver):
             self._print_row(self._table, cache_list)
         return True
 
+    def _drop_pending(self, pending) -> None:
+        if pending is not None and pending.get("prep"):
+            self._eng.release(pending["prep"].get("dst"))
+            pending["prep"] = None
+
     def _retire(self, cache: CBREECache):
         """A cache left the observation window.  Its HBM buffers are recycled only inside :meth:`solve` -- there the
         cache list never leaves the solver before it is pruned (no callback, no ``return_caches``); users of the
@@ -1084,6 +1196,9 @@ class CBREE(Solver):
     def finish(self, cache_list: list) -> Solution:
         """solver.py:468-503: exit message, importance sampling of the retained caches, Solution."""
         msg = self._msg
+        self._drop_pending(getattr(self, "_pending", None))  # (a search launched ahead for an iteration that never came)
+        self._pending = None
+        self._finish_post(getattr(self, "_open_post", None))
         if not cache_list[-1].converged and cache_list[-1].iteration > self.num_steps:
             msg = "Not Converged."
         return self._build_solution(cache_list, msg, None)  # costs after the final importance sampling (solver.py:497)
