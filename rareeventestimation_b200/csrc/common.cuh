@@ -13,6 +13,20 @@
 // error plumbing (ree_api.cu owns the storage)
 // ---------------------------------------------------------------------------------------
 int ree_set_error(int code, const char* what);
+
+// Opt a kernel in to more than 48 KB of dynamic shared memory ONCE per device (the attribute is per function and
+// device, not per launch).  Use inside the launcher of one kernel / one template instantiation: the flag is a
+// function-local static.
+#define REE_OPT_IN_SMEM(kern, bytes)                                                                     \
+    do {                                                                                                 \
+        static bool ree_done_[64] = {false};                                                             \
+        int ree_dev_ = 0;                                                                                \
+        cudaGetDevice(&ree_dev_);                                                                        \
+        if (ree_dev_ >= 0 && ree_dev_ < 64 && !ree_done_[ree_dev_]) {                                    \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));      \
+            ree_done_[ree_dev_] = true;                                                                  \
+        }                                                                                                \
+    } while (0)
 int ree_check_launch(const char* what);
 int ree_grid_ctas();
 

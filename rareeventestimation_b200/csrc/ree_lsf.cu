@@ -216,7 +216,7 @@ int ree_lsf_launch(const ree_lsf* lsf, const double* x, int64_t n, int64_t ld, d
             if (ree_pde_mma_supported(&l)) return ree_pde_mma_launch(&l, x, n, ld, g, st);
             size_t smem = (size_t)l.d * REE_PDE_TPB * sizeof(double);
             if (smem > 200 * 1024) return ree_set_error(REE_E_UNSUPPORTED, "diffusion LSF: d too large for shared memory");
-            cudaFuncSetAttribute(k_lsf_diffusion, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            REE_OPT_IN_SMEM(k_lsf_diffusion, 200 * 1024);
             int grid = lsf_grid(n, REE_PDE_TPB);
             k_lsf_diffusion<<<grid, REE_PDE_TPB, smem, st>>>(l, x, n, ld, g);
             return ree_check_launch("ree_lsf_eval(diffusion)");

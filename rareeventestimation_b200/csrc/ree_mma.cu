@@ -492,7 +492,7 @@ static int launch_k(const MmaArgs& a, int grid, cudaStream_t st) {
                              (SWEEP == 1 ? BM_SMEM_DOUBLES : 0)) * sizeof(double);
     static_assert(smem <= 227 * 1024, "shared memory budget");
     auto kern = k_sweep<SWEEP, NTB, NW, MAXM, KS, EXACT, TRI>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    REE_OPT_IN_SMEM(kern, smem);
     kern<<<grid, NW * 32, smem, st>>>(a);
     return ree_check_launch(SWEEP == 1 ? "k_sweep<1>" : "k_sweep<2>");
 }

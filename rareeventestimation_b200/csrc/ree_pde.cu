@@ -188,7 +188,7 @@ int ree_pde_mma_launch(const ree_lsf* l, const double* x, int64_t n, int64_t ld,
     constexpr size_t smem = (size_t)S * PdeDims<KK>::BLOCK_BYTES;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     auto kern = k_pde_mma<KK, NW, S>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    REE_OPT_IN_SMEM(kern, smem);
     kern<<<grid, NW * 32, smem, st>>>(g_pack[dev], nb, x, n, ld, l->d, l->p0, l->p1, l->offset, g);
     return ree_check_launch("k_pde_mma");
 }

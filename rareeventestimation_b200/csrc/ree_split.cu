@@ -811,7 +811,7 @@ static int launch_xf(const XfArgs& a, int grid, cudaStream_t st) {
                              (MODE == 1 ? BM_SMEM_DOUBLES : 0)) * sizeof(double);
     static_assert(smem <= 227 * 1024, "shared memory budget");
     auto kern = k_xform<MODE, NTB, NW, EXACT, TRI, PGB>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    REE_OPT_IN_SMEM(kern, smem);
     kern<<<grid, NW * 32, smem, st>>>(a);
     return ree_check_launch(MODE == 1 ? "k_xform<1>" : "k_xform<2>");
 }
@@ -833,7 +833,7 @@ static int launch_xf_ws(const XfArgs& a, int grid, cudaStream_t st) {
     static_assert(RC == 0 || (NC * RC + NC * NPC * RP) * 32 <= 65536 / ((1 + NPC) * NC * 32) / 8 * 8 * (1 + NPC) * NC * 32,
                   "register pool");
     auto kern = k_xform_ws<NTB, NC, NPC, EXACT, PGB, RC, RP, CONS>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    REE_OPT_IN_SMEM(kern, smem);
     kern<<<grid, (1 + NPC) * NC * 32, smem, st>>>(a);
     return ree_check_launch("k_xform_ws");
 }
@@ -904,7 +904,7 @@ static int launch_g2(const GramArgs& a, int grid, cudaStream_t st) {
     int rc = make_ensemble_tmap(&tmap, a.x, a.ld, a.d, S, ROWS);
     if (rc) return rc;
     auto kern = k_gram2<NTB, NW, MAXM, KS, EXACT, WM>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    REE_OPT_IN_SMEM(kern, smem);
     kern<<<grid, NW * 32, smem, st>>>(a, tmap);
     return ree_check_launch("k_gram2");
 }

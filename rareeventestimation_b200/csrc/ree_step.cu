@@ -289,7 +289,7 @@ static int launch_gram(const double* x, int64_t n, int d, int64_t ld, const doub
     do {                                                                                                \
         const int slabs = (maxo + M - 1) / M;                                                           \
         if (grid * slabs > 2 * ree_grid_ctas()) grid = 2 * ree_grid_ctas() / slabs;                     \
-        cudaFuncSetAttribute(k_gram<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        REE_OPT_IN_SMEM(k_gram<M>, 72 * 1024); /* d <= 256: (33 d + 32) doubles */                     \
         k_gram<M><<<dim3(grid, slabs), GT, smem, st>>>(x, n, d, ld, shift, w, g, partials);             \
     } while (0)
     if (maxo <= 1) LAUNCH_GRAM(1);
