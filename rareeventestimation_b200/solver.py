@@ -1149,8 +1149,7 @@ class CBREE(Solver):
         self._update_beta_and_sigma(cache_list[-1], overlap=prepare, pending=pending)
         # The next search can be launched before this step's Mahalanobis sweep has finished when nothing can change the
         # new cache in between (no callback) and the search runs on the device.
-        speculate = (self.callback is None and self.search == "device" and self._eng.peers_connected()
-                     and self._eng.path(cache_list[-1]._dev.d) == 2)
+        speculate = self.callback is None and self.search == "device" and self._eng.peers_connected()
         try:
             new = self._perform_step(cache_list[-1], prep, defer=speculate)
             if speculate:
