@@ -103,7 +103,7 @@ class VMFNMixture(MixtureModel):
 
     def _mu_device(self, eng: Engine):
         if self._dev_mu is None:
-            self._dev_mu = eng.to_device(np.ascontiguousarray(self.mu[:, 0]))
+            self._dev_mu = eng.to_device_small(np.ascontiguousarray(self.mu[:, 0]))
         return self._dev_mu
 
     # ------------------------------------------------------------------ #
@@ -118,7 +118,7 @@ class VMFNMixture(MixtureModel):
         assert self.fitted, "Fit vMFNM before accessing parameters!"
         kappa, m, om = self._scalars()
         v, b = _house(self.mu[:, 0])
-        hv = eng.to_device(v)
+        hv = eng.to_device_small(v)
         if variates is None:
             return eng.vmfn_sample(dst, hv, b, kappa, m, om, seed, draw)
         r, w, V = variates
