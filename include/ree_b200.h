@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define REE_ABI_VERSION 8
+#define REE_ABI_VERSION 9
 
 /* argument errors */
 #define REE_E_BADARG (-1)
@@ -271,6 +271,12 @@ int ree_peer_connect(const unsigned char* handles);
  * has called ree_peer_create on its device (host barrier), each calls this with the device ordinal of every rank; the
  * mailboxes are reached through cudaDeviceEnablePeerAccess instead of CUDA IPC. */
 int ree_peer_connect_local(const int* devices);
+/* In-place sum over all ranks of a small fp64 device vector (n <= ree_peer_allreduce_max()): one kernel that stages the
+ * local vector behind this rank's mailbox, uses one mailbox exchange as the barrier and adds all ranks' staging areas in
+ * rank order over NVLink (identical bits on every rank).  Replaces the NCCL all_reduce of the packed d x d sums.  Stream
+ * ordered; every rank must call it in the same order as the other peer calls. */
+int ree_peer_allreduce_sum(double* buf, int64_t n, void* stream);
+int64_t ree_peer_allreduce_max(void);
 int ree_peer_ready(void);
 int ree_peer_combine_expsums(double* out4, void* stream);
 int ree_peer_check(void);

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libree_b200.so")
 TGT_KINDS = {"algebraic": 0, "tanh": 1, "arctan": 2, "erf": 3, "relu": 4, "sigmoid": 5}
 LSF_EXTERNAL, LSF_AFFINE, LSF_CONVEX, LSF_FUJITA_RACKWITZ, LSF_OSCILLATOR, LSF_DIFFUSION = range(6)
 NOISE_INJECT, NOISE_PHILOX = 0, 1
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class ReeError(RuntimeError):
@@ -99,6 +99,8 @@ PROTOTYPES = {
     "ree_peer_create": (_INT, [_INT, _INT, _P]),
     "ree_peer_connect": (_INT, [_P]),
     "ree_peer_connect_local": (_INT, [C.POINTER(C.c_int)]),
+    "ree_peer_allreduce_sum": (_INT, [_P, _I64, _P]),
+    "ree_peer_allreduce_max": (_I64, []),
     "ree_peer_ready": (_INT, []),
     "ree_peer_combine_expsums": (_INT, [_P, _P]),
     "ree_peer_check": (_INT, []),

@@ -12,9 +12,18 @@ struct PeerSlot {  // 64 bytes
 };
 struct PeerBox {
     PeerSlot slot[2][REE_PEER_MAX];
-    unsigned long long seq;  // exchanges completed by the owner of this mailbox (only the owner reads / writes it)
-    unsigned long long pad[7];
+    unsigned long long seq;     // exchanges completed by the owner of this mailbox (only the owner reads / writes it)
+    unsigned long long ar_seq;  // all-reduces completed by the owner (parity of the staging area below)
+    unsigned long long pad[6];
 };
+
+// Behind every mailbox (same allocation, same IPC handle): two staging areas of REE_PEER_STAGE doubles for the packed
+// d x d sums of ree_peer_allreduce_sum (2 (d^2 + d + 2) doubles, d <= 256).
+#define REE_PEER_STAGE (2 * (256 * 256 + 256 + 2) + 4)
+#define REE_PEER_BYTES (sizeof(PeerBox) + 2 * (size_t)REE_PEER_STAGE * sizeof(double))
+__host__ __device__ __forceinline__ double* peer_stage(PeerBox* box, int parity) {
+    return reinterpret_cast<double*>(reinterpret_cast<char*>(box) + sizeof(PeerBox)) + (size_t)parity * REE_PEER_STAGE;
+}
 
 // What a kernel needs to talk to the peers.  `box[r]` is rank r's mailbox as mapped into this process (CUDA IPC, or plain
 // peer access when one process drives several devices); box[rank] is this rank's own.

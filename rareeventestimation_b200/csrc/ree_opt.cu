@@ -544,7 +544,7 @@ static const PeerArgs* local_mailbox() {
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     if (!g_local_ready[dev]) {
         PeerArgs a{};
-        cudaError_t err = cudaMalloc((void**)&a.box[0], sizeof(PeerBox));
+        cudaError_t err = cudaMalloc((void**)&a.box[0], sizeof(PeerBox));  // (no staging areas: single rank)
         if (err == cudaSuccess) err = cudaMemset(a.box[0], 0, sizeof(PeerBox));
         if (err == cudaSuccess) err = cudaMalloc((void**)&a.error, sizeof(int));
         if (err == cudaSuccess) err = cudaMemset(a.error, 0, sizeof(int));

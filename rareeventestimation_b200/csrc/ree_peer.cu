@@ -46,6 +46,67 @@ __global__ void __launch_bounds__(32) k_peer_exchange(double* out4, const PeerAr
     }
 }
 
+// Sum of a small fp64 vector over all ranks, in place, as ONE kernel over peer memory (the packed d x d sums after the
+// Gram pass: 162 KB at d = 100) -- instead of an NCCL all_reduce launch next to the kernels that produce and consume it.
+//   1. copy the local vector into this rank's staging area [parity] (behind its mailbox), system fence;
+//   2. one mailbox exchange as the barrier: a rank publishes its sequence number only after its staging area is complete;
+//   3. every rank adds the staging areas of all ranks in rank order (NVLink reads, L1 bypassed) -> identical bits.
+// Two parities: a rank overwrites parity p again two all-reduces later, i.e. after a barrier that every rank only
+// enters once it has finished reading p.
+__global__ void __launch_bounds__(1024) k_peer_allreduce(double* buf, int n, const PeerArgs a) {
+    __shared__ double t[REE_PEER_MAX][4];
+    PeerBox* own = a.box[a.rank];
+    const int par = (int)(own->ar_seq & 1ull);
+    double* mine = peer_stage(own, par);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mine[i] = buf[i];
+    __syncthreads();  // (the publishing lanes fence at system scope before they store the sequence number: cumulative)
+    if (threadIdx.x < 32) {
+        const unsigned long long seq = own->seq + 1;
+        (void)peer_exchange_warp(a, seq, ExpSums{0.0, 0.0, 0.0, 0.0}, t);
+        if (threadIdx.x == 0) {
+            own->seq = seq;
+            own->ar_seq += 1;
+        }
+    }
+    __syncthreads();
+    // batches of AR_B elements per thread: AR_B x world independent NVLink reads in flight, then the rank-order sums
+    constexpr int AR_B = 8;
+    const double* stage[REE_PEER_MAX];
+    for (int r = 0; r < a.world; ++r) stage[r] = peer_stage(a.box[r], par);
+    for (int i0 = threadIdx.x; i0 < n; i0 += AR_B * blockDim.x) {
+        double acc[AR_B];
+#pragma unroll
+        for (int j = 0; j < AR_B; ++j) acc[j] = 0.0;
+        for (int r = 0; r < a.world; ++r) {
+            double v[AR_B];
+#pragma unroll
+            for (int j = 0; j < AR_B; ++j) {
+                const int i = i0 + j * (int)blockDim.x;
+                v[j] = 0.0;
+                if (i < n) asm("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v[j]) : "l"(stage[r] + i));
+            }
+#pragma unroll
+            for (int j = 0; j < AR_B; ++j) acc[j] += v[j];
+        }
+#pragma unroll
+        for (int j = 0; j < AR_B; ++j) {
+            const int i = i0 + j * (int)blockDim.x;
+            if (i < n) buf[i] = acc[j];
+        }
+    }
+}
+
+extern "C" int ree_peer_allreduce_sum(double* buf, int64_t n, void* stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_peer_ready[dev] || !buf)
+        return ree_set_error(REE_E_BADARG, "ree_peer_allreduce_sum: peers are not connected");
+    if (n < 1 || n > REE_PEER_STAGE) return ree_set_error(REE_E_UNSUPPORTED, "ree_peer_allreduce_sum: vector too long");
+    k_peer_allreduce<<<1, 1024, 0, ree_stream(stream)>>>(buf, (int)n, g_peer[dev].args);
+    return ree_check_launch("ree_peer_allreduce_sum");
+}
+
+extern "C" int64_t ree_peer_allreduce_max(void) { return REE_PEER_STAGE; }
+
 // ---- setup -------------------------------------------------------------------------------------
 // 1. every rank: ree_peer_create(rank, world, handle_out[64])      -> allocates the mailbox, returns its IPC handle
 // 2. exchange the handles (any transport; engine.py uses torch.distributed.all_gather_object)
@@ -58,8 +119,8 @@ extern "C" int ree_peer_create(int rank, int world, unsigned char* handle_out) {
     if (err != cudaSuccess || dev < 0 || dev >= 64) return ree_set_error(REE_E_BADARG, "ree_peer_create: no device");
     PeerState& s = g_peer[dev];
     if (!s.local) {
-        err = cudaMalloc((void**)&s.local, sizeof(PeerBox));
-        if (err == cudaSuccess) err = cudaMemset(s.local, 0, sizeof(PeerBox));
+        err = cudaMalloc((void**)&s.local, REE_PEER_BYTES);
+        if (err == cudaSuccess) err = cudaMemset(s.local, 0, REE_PEER_BYTES);
         if (err == cudaSuccess) err = cudaMalloc((void**)&s.d_error, sizeof(int));
         if (err == cudaSuccess) err = cudaMemset(s.d_error, 0, sizeof(int));
         if (err == cudaSuccess) err = cudaDeviceSynchronize();  // the mailbox is zero before its handle leaves the process
@@ -67,7 +128,7 @@ extern "C" int ree_peer_create(int rank, int world, unsigned char* handle_out) {
     } else {
         // a new process group in the same process: empty the mailbox again (the handle exchange that follows is the
         // barrier before any peer writes into it) and forget the old error
-        err = cudaMemset(s.local, 0, sizeof(PeerBox));
+        err = cudaMemset(s.local, 0, REE_PEER_BYTES);
         if (err == cudaSuccess) err = cudaMemset(s.d_error, 0, sizeof(int));
         if (err == cudaSuccess) err = cudaDeviceSynchronize();
         if (err != cudaSuccess) return ree_set_error((int)err, cudaGetErrorString(err));

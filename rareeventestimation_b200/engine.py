@@ -45,6 +45,11 @@ def merge_expsums(parts: torch.Tensor) -> torch.Tensor:
 class Comm:
     """Thin wrapper over a torch.distributed process group (or a single process)."""
 
+    # The packed d x d sums: NCCL's all_reduce (19 us for 162 KB on 2 GPUs) beats the single-CTA peer-memory kernel
+    # (41 us) under torchrun, so it stays the default there (REE_PEER_ALLREDUCE=1 selects the kernel); the threaded
+    # communicator of CBREE(devices=N) has no NCCL and uses the kernel.
+    _PEER_ALLREDUCE = "0"
+
     def __init__(self, group=None, enabled: Optional[bool] = None):
         import torch.distributed as dist
 
@@ -78,8 +83,24 @@ class Comm:
             self.dist.all_gather_object(flags, ok, group=self.group)  # also the barrier before the first exchange
         return all(flags)
 
+    def _peer_allreduce(self, t: torch.Tensor) -> bool:
+        """Sum `t` over the ranks with the peer-memory kernel (``ree_peer_allreduce_sum``) if the NVLink mailboxes are
+        connected and `t` qualifies (fp64, contiguous, on the device, short enough).  All ranks decide alike."""
+        if not (t.is_cuda and t.dtype == F64 and t.is_contiguous() and t.numel() >= 1):
+            return False
+        lib = _lib.load()
+        if t.numel() > lib.ree_peer_allreduce_max() or os.environ.get("REE_PEER_ALLREDUCE", self._PEER_ALLREDUCE) == "0":
+            return False
+        if self.peer is None:
+            self.peer = self._connect_peers(t.device)
+        if not self.peer:
+            return False
+        stream = C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+        check(lib.ree_peer_allreduce_sum(t.data_ptr(), t.numel(), stream), "ree_peer_allreduce_sum")
+        return True
+
     def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
-        if self.enabled:
+        if self.enabled and not self._peer_allreduce(t):
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t
 
@@ -150,6 +171,8 @@ class ThreadComm(Comm):
     instead of CUDA IPC); the d x d sums are added in rank order from peer-to-peer copies, so every rank holds
     identical bits."""
 
+    _PEER_ALLREDUCE = "1"
+
     def __init__(self, tgroup: ThreadGroup, rank: int):
         self.dist = None
         self.group = None
@@ -176,9 +199,9 @@ class ThreadComm(Comm):
         return True
 
     def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
-        if not self.enabled:
+        if not self.enabled or self._peer_allreduce(t):
             return t
-        g = self.tgroup
+        g = self.tgroup  # host-mediated fall-back (CPU tensors in the tests, other dtypes, long vectors)
         self._drain(t)  # this rank's contribution is final
         g.slots[self.rank] = t
         self._sync_point()

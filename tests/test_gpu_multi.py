@@ -77,3 +77,16 @@ def test_single_process_multi_device_solve(d, n, kw):
     # the engines of both devices are usable by ordinary solves afterwards
     again = ree.CBREE(**common).solve(prob)
     np.testing.assert_array_equal(again.prob_fail_hist, one.prob_fail_hist)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_peer_memory_collectives(world):
+    """NVLink mailbox exchange and the peer-memory all-reduce of the packed sums (csrc/ree_peer.cu) against NCCL and
+    against the rank-order sum, bit for bit; both staging parities, lengths 1 ... the maximum (tools/peer_check.py)."""
+    if _devices() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", str(29580 + world), os.path.join(ROOT, "tools", "peer_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("OK (all-reduce through peer memory") == world
