@@ -31,7 +31,17 @@ for it in range(200):
     comm.combine_expsums_(b)          # NCCL all_gather + ree_merge_expsums
     comm.peer = keep
     x, y = a.cpu().numpy(), b.cpu().numpy()
-    assert np.array_equal(x, y, equal_nan=True), (it, x, y)
+    # two ranks: one merge either way, identical bits.  More ranks: the mailbox kernel merges pairwise in rank order, the
+    # NCCL path's merge kernel rescales everything to the global shift once -- same value, last-bit differences.
+    if dist.get_world_size() == 2:
+        assert np.array_equal(x, y, equal_nan=True), (it, x, y)
+    else:
+        assert np.array_equal(np.isfinite(x), np.isfinite(y)), (it, x, y)
+        np.testing.assert_allclose(x[np.isfinite(x)], y[np.isfinite(y)], rtol=1e-13)
+    # ... and every rank holds the same bits (what the identical host control flow of all ranks relies on)
+    everyone = [torch.empty_like(a) for _ in range(dist.get_world_size())]
+    dist.all_gather(everyone, a)
+    assert all(torch.equal(everyone[0], e) or (torch.isnan(e).any() and torch.isnan(everyone[0]).any()) for e in everyone), it
 comm.check_peers()
 out = eng.empty(4)
 for name, peer in (("mailbox", True), ("nccl", False)):
@@ -45,7 +55,7 @@ for name, peer in (("mailbox", True), ("nccl", False)):
     torch.cuda.synchronize()
     print(f"rank {rank}: {name:8s} {1e6 * (time.perf_counter() - t0) / 300:7.1f} us per exchange + fetch", flush=True)
 comm.peer = True
-print(f"rank {rank}: OK (200 exchanges bit-identical to the NCCL path)", flush=True)
+print(f"rank {rank}: OK (200 exchanges: identical bits on all ranks, equal to the NCCL path)", flush=True)
 
 # ---- the packed-sums all-reduce through the staging areas behind the mailboxes (ree_peer_allreduce_sum) -------------
 world = dist.get_world_size()
