@@ -229,14 +229,6 @@ __global__ void __launch_bounds__(NW * 32, 1) k_xform(const XfArgs a) {
 // id computes exactly the consumer lane's fragment values (Philox counter = (particle lr, pair 4q + lc)), so both sides
 // use conflict-free 16-byte accesses at lane * 16.  full/empty mbarriers per buffer, one elected arrival per warp.
 // ---------------------------------------------------------------------------------------
-// predicated 16-byte global store: one instruction under a predicate, never a branch around it
-__device__ __forceinline__ void stg128_if(double* p, double x0, double x1, bool pred) {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.global.v2.f64 [%0], {%1, %2};\n\t}" ::"l"(p),
-        "d"(x0), "d"(x1), "r"((uint32_t)pred)
-        : "memory");
-}
-
 struct GenNoise {  // B fragments of k-pair q from the consumer's noise buffer
     uint32_t addr;  // buffer + lane * 16
     __device__ __forceinline__ void operator()(int q, double& b0, double& b1) const {
@@ -250,9 +242,7 @@ struct GenNoise {  // B fragments of k-pair q from the consumer's noise buffer
 // behind the 16-cycle DMMAs of the shared pipe, so one producer per consumer is latency-bound at ~2.4 consumer tile
 // times.  With NPC > 1 the CTA has more than 512 threads; setmaxnreg moves registers from the producers (RP) to the
 // consumers (RC), whose 2 * NTB accumulators + fragment prefetch do not fit the launch-time allocation.
-// CONS: 2 = accumulators start as t x + m, epilogue rows dealt out over the next tile's k-pair steps; 1 = same start,
-// epilogue after the tile's own DMMAs (no second accumulator set); tuning hook REE_XF_VARIANT
-template <int NTB, int NC, int NPC, bool EXACT, int PGB, int RC, int RP, int CONS>
+template <int NTB, int NC, int NPC, bool EXACT, int PGB, int RC, int RP>
 __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArgs a) {
     constexpr int MT = (1 + NPC) * NC * 32;
     constexpr int ROWS = 8 * NTB;
@@ -321,10 +311,9 @@ __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArg
     }
 
     // ---------------- consumer: F z on the tensor pipe, update, g', e' ----------------
-    // Tile k's accumulators START as t x + m_noise (one DFMA per element while the warp waits for its noise), the
-    // DMMAs add F z on top, and what is left of the epilogue -- store, |x'|^2, coef . x' -- is dealt out one row tile per
-    // k-pair step of tile k+1: the warp never leaves its DMMA stream for a burst of fp64 instructions that each queue
-    // behind the other warps' 16-cycle DMMAs (the old epilogue was 39 % of a consumer's time, profiles/r2_xform_ws_*).
+    // Tile k's accumulators START as t x + m_noise (one DFMA per element while the warp waits for its noise), the DMMAs
+    // add F z on top; the epilogue stores the rows and accumulates |x'|^2 and coef . x' in two interleaved chains each
+    // (under the other warps' DMMA streams a dependent fp64 instruction costs ~28 cycles, tools/fp64_mix.cu).
     if constexpr (RC > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RC));
     const uint32_t lf_lane = smem_u32(Lf) + lane * 8;
     const uint32_t stg_w = smem_u32(stg + warp * STG);
@@ -340,50 +329,11 @@ __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArg
             if (row < d) cp_async16(own + (uint32_t)(mt * 512), src + (int64_t)row * a.ld);
         }
     };
-    double cprev[NTB][2];  // finished tile whose rows are written out during the next tile's DMMAs
-#pragma unroll
-    for (int mt = 0; mt < NTB; ++mt) cprev[mt][0] = cprev[mt][1] = 0.0;
-    double se0 = 0.0, se1 = 0.0, sg0 = 0.0, sg1 = 0.0;
-    int64_t ip_prev = 0;
-    // straight-line code (a predicated store, no branch): the DMMA stream of the next tile must stay one basic block so
-    // that the fragment loads of k-pair q+1 are scheduled above the DMMAs of k-pair q
-    auto epi_row = [&](int mt, bool live) {
-        const int row = 8 * mt + lr;
-        const double crow = lds64(vc_lane + (uint32_t)(mt * 64));  // (0 for rows >= d)
-        const double x0 = cprev[mt][0], x1 = cprev[mt][1];         // (0 for rows >= d)
-        stg128_if(a.x_new + (int64_t)row * a.ld + ip_prev, x0, x1, live && row < d);
-        se0 = fma(x0, x0, se0);
-        se1 = fma(x1, x1, se1);
-        sg0 = fma(crow, x0, sg0);
-        sg1 = fma(crow, x1, sg1);
-    };
-    auto epi_finish = [&]() {
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-            se0 += __shfl_xor_sync(0xffffffffu, se0, o);
-            se1 += __shfl_xor_sync(0xffffffffu, se1, o);
-            sg0 += __shfl_xor_sync(0xffffffffu, sg0, o);
-            sg1 += __shfl_xor_sync(0xffffffffu, sg1, o);
-        }
-        if (lr == 0) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (ip_prev + h < a.n) {
-                    const double s = h ? se1 : se0, gsum = h ? sg1 : sg0;
-                    if (a.e_new) a.e_new[ip_prev + h] = 0.5 * (e_const + s);
-                    if (a.lsf_mode)
-                        a.g_new[ip_prev + h] = (a.lsf_mode == 1)
-                                                   ? __dadd_rn(gsum, a.offset)
-                                                   : __dadd_rn(__ddiv_rn(-gsum, __dsqrt_rn((double)d)), a.offset);
-                }
-            }
-        }
-        se0 = se1 = sg0 = sg1 = 0.0;
-    };
     int64_t wt = (int64_t)blockIdx.x * NC + warp;
     if (wt < nwt) prefetch(wt);
     int k = 0;
     for (; wt < nwt; wt += stride, ++k) {
+        const int64_t ip = wt * 8 + 2 * lc;
         const uint32_t b = (uint32_t)k & 1u, ph = ((uint32_t)k >> 1) & 1u;
         double c2[NTB][2];
         cp_async_wait_all();  // own elements only: no warp barrier needed
@@ -401,7 +351,6 @@ __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArg
         if (wt + stride < nwt) prefetch(wt + stride);  // (this lane's reads of the block precede its refill)
         mbar_wait(bar_c + 16u * b, ph);
         const uint32_t nzb = nz_c + b * (uint32_t)(NZ * 8);
-        const bool have_prev = CONS == 2 && k > 0;
         double2 bq = lds128(nzb);
 #pragma unroll
         for (int q = 0; q < NTB; ++q) {
@@ -418,28 +367,45 @@ __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArg
                         dmma(c2[mt][0], c2[mt][1], lds64(lf_lane + lf_tile<NTB, true>(mt, 2 * q + 1) * 256), bq.y);
                 bq = bn;
             }
-            if constexpr (CONS == 2) epi_row(q, have_prev);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_c + 16u * b + 8u);  // every fragment of the buffer has been read
-        if (have_prev) epi_finish();
-        se0 = se1 = sg0 = sg1 = 0.0;
+        double se[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, sg[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
         for (int mt = 0; mt < NTB; ++mt) {
-            cprev[mt][0] = c2[mt][0];
-            cprev[mt][1] = c2[mt][1];
+            const int row = 8 * mt + lr;
+            if ((EXACT || mt < ntd) && row < d) {
+                const double crow = lds64(vc_lane + (uint32_t)(mt * 64));
+                const double x0 = c2[mt][0], x1 = c2[mt][1];
+                *reinterpret_cast<double2*>(a.x_new + (int64_t)row * a.ld + ip) = make_double2(x0, x1);
+                se[mt & 1][0] = fma(x0, x0, se[mt & 1][0]);
+                se[mt & 1][1] = fma(x1, x1, se[mt & 1][1]);
+                sg[mt & 1][0] = fma(crow, x0, sg[mt & 1][0]);
+                sg[mt & 1][1] = fma(crow, x1, sg[mt & 1][1]);
+            }
         }
-        ip_prev = wt * 8 + 2 * lc;
-        if constexpr (CONS == 1) {
+        double se0 = se[0][0] + se[1][0], se1 = se[0][1] + se[1][1];
+        double sg0 = sg[0][0] + sg[1][0], sg1 = sg[0][1] + sg[1][1];
 #pragma unroll
-            for (int mt = 0; mt < NTB; ++mt) epi_row(mt, true);
-            epi_finish();
+        for (int o = 4; o < 32; o <<= 1) {
+            se0 += __shfl_xor_sync(0xffffffffu, se0, o);
+            se1 += __shfl_xor_sync(0xffffffffu, se1, o);
+            sg0 += __shfl_xor_sync(0xffffffffu, sg0, o);
+            sg1 += __shfl_xor_sync(0xffffffffu, sg1, o);
         }
-    }
-    if (CONS == 2 && k > 0) {
+        if (lr == 0) {
 #pragma unroll
-        for (int mt = 0; mt < NTB; ++mt) epi_row(mt, true);
-        epi_finish();
+            for (int h = 0; h < 2; ++h) {
+                if (ip + h < a.n) {
+                    const double s = h ? se1 : se0, gsum = h ? sg1 : sg0;
+                    if (a.e_new) a.e_new[ip + h] = 0.5 * (e_const + s);
+                    if (a.lsf_mode)
+                        a.g_new[ip + h] = (a.lsf_mode == 1)
+                                              ? __dadd_rn(gsum, a.offset)
+                                              : __dadd_rn(__ddiv_rn(-gsum, __dsqrt_rn((double)d)), a.offset);
+                }
+            }
+        }
     }
 }
 
@@ -825,14 +791,14 @@ static int xf_ws() {
     return v;
 }
 
-template <int NTB, int NC, int NPC, bool EXACT, int PGB, int RC, int RP, int CONS = 2>
+template <int NTB, int NC, int NPC, bool EXACT, int PGB, int RC, int RP>
 static int launch_xf_ws(const XfArgs& a, int grid, cudaStream_t st) {
     constexpr size_t smem = ((size_t)lf_doubles<NTB, true>() + (size_t)NC * 3 * NTB * 64 + 2 * 8 * NTB +
                              BM_SMEM_DOUBLES) * sizeof(double);
     static_assert(smem <= 227 * 1024, "shared memory budget");
     static_assert(RC == 0 || (NC * RC + NC * NPC * RP) * 32 <= 65536 / ((1 + NPC) * NC * 32) / 8 * 8 * (1 + NPC) * NC * 32,
                   "register pool");
-    auto kern = k_xform_ws<NTB, NC, NPC, EXACT, PGB, RC, RP, CONS>;
+    auto kern = k_xform_ws<NTB, NC, NPC, EXACT, PGB, RC, RP>;
     REE_OPT_IN_SMEM(kern, smem);
     kern<<<grid, (1 + NPC) * NC * 32, smem, st>>>(a);
     return ree_check_launch("k_xform_ws");
@@ -847,15 +813,13 @@ static int launch_xf_ws_variants(const XfArgs& a, cudaStream_t st) {
     if ((a.d + 7) / 8 == NTB) {
         // tuning hooks: 1 = four Philox chains per producer batch, 2 = two producers per consumer
         // with setmaxnreg 120 / 56 (measured slower: the extra DFMA streams take pipe slots from the consumers)
-        // measured at N = 1e7, d = 100 (profiles/r2_xform_variants.txt): 0: 7.39 ms; 3 (next tile's DMMAs carry the
-        // epilogue, setmaxnreg 152 / 104): 8.10; 1 (same, 176 / 80): 8.98 -- every register taken from the producers
-        // costs more than the leaner consumer gains
-        if (v == 1) return launch_xf_ws<NTB, NC, 1, true, 2, 176, 80, 2>(a, grid, st);
-        if (v == 2) return launch_xf_ws<NTB, NC, 2, true, 2, 120, 56, 1>(a, grid, st);
-        if (v == 3) return launch_xf_ws<NTB, NC, 1, true, 2, 152, 104, 2>(a, grid, st);
-        return launch_xf_ws<NTB, NC, 1, true, 2, 0, 0, 1>(a, grid, st);
+        // tuning hooks (profiles/r2_xform_variants.txt): 1 = four Box-Muller chains per producer batch, 2 = two producers
+        // per consumer with setmaxnreg 120 / 56 -- both measured slower than the default
+        if (v == 1) return launch_xf_ws<NTB, NC, 1, true, 4, 0, 0>(a, grid, st);
+        if (v == 2) return launch_xf_ws<NTB, NC, 2, true, 2, 120, 56>(a, grid, st);
+        return launch_xf_ws<NTB, NC, 1, true, 2, 0, 0>(a, grid, st);
     }
-    return launch_xf_ws<NTB, NC, 1, false, 2, 0, 0, 1>(a, grid, st);
+    return launch_xf_ws<NTB, NC, 1, false, 2, 0, 0>(a, grid, st);
 }
 
 template <int MODE, int NTB, int NW, bool TRI>
