@@ -346,6 +346,8 @@ class Engine:
         self._staging = None
         self._pin_ring, self._pin_next, self._pin_down, self._side = None, 0, None, None
         self._pin_slots = [None, None]
+        self._open_post = None
+        self.adapt_launches = 0
         self._fetch_buf = np.empty(64, dtype=np.float64)
         with torch.cuda.device(self.device):
             self.num_ctas = self.lib.ree_num_ctas()
@@ -591,6 +593,7 @@ class Engine:
         check(self.lib.ree_cbree_adapt(ens.g.data_ptr(), ens.e.data_ptr() if ens.e is not None else None, ens.n,
                                        C.byref(p), ell.data_ptr(), ws.data_ptr(), out.data_ptr(), self.stream),
               "ree_cbree_adapt")
+        self.adapt_launches += 1  # (a search launched ahead is only adopted if no other search ran on this engine since)
         if not wait:
             return None
         if overlap is not None:

@@ -439,7 +439,8 @@ class CBREE(Solver):
         count -- is read back BEFORE the factorisation and the Mahalanobis / IS sweep are enqueued, so the host works on
         it while the GPU runs those; their results (pivot statistics, IS tuple) arrive with a second small readback.
         ``defer=True`` returns after the first one; :meth:`_finish_post` completes the cache."""
-        self._finish_post(getattr(self, "_open_post", None))
+        # (the pinned readback slots belong to the engine: an unfinished cache of ANY solver on it is completed first)
+        self._finish_post(getattr(self._eng, "_open_post", None))
         eng, dev = self._eng, cache._dev
         d = dev.d
         kind = self._tgt_kind()
@@ -523,9 +524,9 @@ class CBREE(Solver):
         cache._ess4 = e4.copy()
         cache._n_total = float(tl[1])
         cache._pending_b = (host_b, ev_b)
-        self._open_post = cache
+        eng._open_post = cache
         if e4[3] <= 0:  # my_softmax on an all-non-finite vector (utilities.py:121)
-            self._open_post = None
+            eng._open_post = None
             raise ValueError("attempt to get argmax of an empty sequence")
         if not defer:
             self._finish_post(cache)
@@ -537,8 +538,8 @@ class CBREE(Solver):
             return
         host_b, ev_b = cache._pending_b
         cache._pending_b = None
-        if getattr(self, "_open_post", None) is cache:
-            self._open_post = None
+        if getattr(cache._engine, "_open_post", None) is cache:
+            cache._engine._open_post = None
         if ev_b is not None:
             ev_b.synchronize()
         st, i4 = host_b[0:8], host_b[8:12]
@@ -762,7 +763,7 @@ class CBREE(Solver):
             t_next = self._stepsize_value(cache_list)
         args = self._search_args(cache, t_next)
         self._launch_search(cache, args, wait=False)
-        pend = dict(cache=cache, args=args, t_next=t_next, prep=None)
+        pend = dict(cache=cache, args=args, t_next=t_next, prep=None, token=self._eng.adapt_launches)
         try:  # the step's host-side preparation as well (it only depends on the step size), while the GPU is busy
             keep, cache.t_step = cache.t_step, t_next
             pend["prep"] = self._prepare_step(cache)
@@ -782,7 +783,8 @@ class CBREE(Solver):
         if note is not None:
             self._note_failure(cache, note)
         cache.sigma = sigma0  # (the closed-form update, if it applied)
-        if pending is not None and pending["cache"] is cache and pending["args"] == args:
+        if (pending is not None and pending["cache"] is cache and pending["args"] == args
+                and pending["token"] == eng.adapt_launches):
             if overlap is not None:  # the search was launched at the end of the previous iteration
                 overlap()
             out = eng.adapt_result()
@@ -1197,7 +1199,7 @@ class CBREE(Solver):
         msg = self._msg
         self._drop_pending(getattr(self, "_pending", None))  # (a search launched ahead for an iteration that never came)
         self._pending = None
-        self._finish_post(getattr(self, "_open_post", None))
+        self._finish_post(getattr(self._eng, "_open_post", None))
         if not cache_list[-1].converged and cache_list[-1].iteration > self.num_steps:
             msg = "Not Converged."
         return self._build_solution(cache_list, msg, None)  # costs after the final importance sampling (solver.py:497)
