@@ -543,3 +543,29 @@ def test_singular_covariance_raises_like_scipy(ree):
     with pytest.warns(RuntimeWarning, match="positive definite"):
         with pytest.raises(np.linalg.LinAlgError):
             ree.CBREE(seed=1, t_step=0.5, quiet=True).solve(prob)
+
+
+def test_interleaved_solvers_share_a_device(ree):
+    """The start / advance / finish API with two solvers advanced alternately on ONE engine: the deferred second readback
+    of an iteration and the sigma / beta search launched ahead for the next one use per-engine buffers, so each solver
+    must finish the other's open readback first and must not adopt a search the other one has overwritten -- both
+    trajectories equal those of the same solvers run alone, bit for bit."""
+    def make(seed, d):
+        prob = ree.make_linear_problem(d).set_sample(4000, seed=seed)
+        return prob, ree.CBREE(seed=seed, quiet=True, convergence_check=False, divergence_check=False, num_steps=6)
+
+    alone = {}
+    for seed, d in [(3, 100), (4, 64)]:
+        prob, solver = make(seed, d)
+        alone[seed] = solver.solve(prob)
+    pa, sa = make(3, 100)
+    pb, sb = make(4, 64)
+    ca, cb = sa.start(pa), sb.start(pb)
+    for _ in range(7):
+        assert sa.advance(ca)
+        assert sb.advance(cb)
+    ra, rb = sa.finish(ca), sb.finish(cb)
+    for got, want in [(ra, alone[3]), (rb, alone[4])]:
+        np.testing.assert_array_equal(got.prob_fail_hist, want.prob_fail_hist)
+        np.testing.assert_array_equal(got.temp_hist, want.temp_hist)
+        np.testing.assert_array_equal(np.asarray(got.lsf_eval_hist)[-1], np.asarray(want.lsf_eval_hist)[-1])
