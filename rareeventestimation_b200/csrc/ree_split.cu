@@ -57,12 +57,12 @@ struct GenStage {  // rows 8q+lc and 8q+4+lc of the warp's staging block at part
 // transform kernel: one warp = 8 particles x all dimensions, persistent over warp tiles
 // ---------------------------------------------------------------------------------------
 // PGB: Philox + Box-Muller chains generated together (instruction-level parallelism inside a warp)
-template <int MODE, int NTB, int NW, bool EXACT, bool TRI, int PGB>
-__global__ void __launch_bounds__(NW * 32, 1) k_xform(const XfArgs a) {
+template <int MODE, int NTB, int NW, bool EXACT, bool TRI, int PGB, bool TMAX>
+__global__ void __launch_bounds__(NW * 32, 1) k_xform(const XfArgs a, const __grid_constant__ CUtensorMap tmap) {
     constexpr int MT = NW * 32;
     constexpr int ROWS = 8 * NTB;
     constexpr int STG = ROWS * 8;  // doubles of one warp's staging block: [row][8 particles]
-    extern __shared__ double sm[];
+    extern __shared__ __align__(1024) double sm[];
     const int d = a.d, ntd = (d + 7) >> 3;
     double* Lf = sm;
     double* stg = Lf + lf_doubles<NTB, TRI>();
@@ -70,7 +70,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_xform(const XfArgs a) {
     double* vc = vm + 8 * NTB;    // LSF coefficients (MODE 1)
     double* bm = vc + 8 * NTB;    // Box-Muller tables (MODE 1, Philox noise)
     __shared__ ExpSums sh[32];
+    __shared__ __align__(8) unsigned long long xbars[NW];  // "the X tile of warp w has landed" (TMAX)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lc = lane & 3;
+    if (TMAX && tid < NW) mbar_init(smem_u32(&xbars[0]) + 8u * (uint32_t)tid, 1);
+    if (TMAX) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 
     pack_matrix<NTB, TRI, MT>(Lf, a.A, d);
     for (int j = tid; j < 8 * NTB; j += MT) {
@@ -96,18 +99,33 @@ __global__ void __launch_bounds__(NW * 32, 1) k_xform(const XfArgs a) {
     const int64_t nwt = (a.n + 7) >> 3;
     const int64_t stride = (int64_t)gridDim.x * NW;
 
-    auto prefetch = [&](int64_t wt) {  // every lane fetches the 16-byte chunks (row 8mt+lr, columns 2lc..2lc+1)
-        const double* src = a.x + wt * 8 + 2 * lc;  // wt*8 + 7 < ld (ld is a multiple of 8, ld >= n)
+    const uint32_t xbar = smem_u32(&xbars[warp]);
+    auto prefetch = [&](int64_t wt) {
+        if constexpr (TMAX) {  // one TMA box copy {8 particles, all rows} per warp tile (rows >= d arrive as zeros)
+            __syncwarp();
+            if (lane == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(xbar, (uint32_t)(STG * 8));
+                tma_load_2d(stg_w, &tmap, (int)(wt * 8), 0, xbar);
+            }
+        } else {  // every lane fetches the 16-byte chunks (row 8mt+lr, columns 2lc..2lc+1)
+            const double* src = a.x + wt * 8 + 2 * lc;  // wt*8 + 7 < ld (ld is a multiple of 8, ld >= n)
 #pragma unroll
-        for (int mt = 0; mt < NTB; ++mt) {
-            const int row = 8 * mt + lr;
-            if (row < d) cp_async16(own + (uint32_t)(mt * 512), src + (int64_t)row * a.ld);
+            for (int mt = 0; mt < NTB; ++mt) {
+                const int row = 8 * mt + lr;
+                if (row < d) cp_async16(own + (uint32_t)(mt * 512), src + (int64_t)row * a.ld);
+            }
         }
+    };
+    auto landed = [&](uint32_t parity) {
+        if constexpr (TMAX) mbar_wait(xbar, parity);
+        else cp_async_wait_all();
     };
     int64_t wt = (int64_t)blockIdx.x * NW + warp;
     if (wt < nwt) prefetch(wt);
 
-    for (; wt < nwt; wt += stride) {
+    uint32_t xk = 0;
+    for (; wt < nwt; wt += stride, ++xk) {
         const int64_t i0 = wt * 8;
         const int64_t ip = i0 + 2 * lc;  // first of this lane's two particle columns
         double c[NTB][2];
@@ -128,7 +146,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_xform(const XfArgs a) {
                 gen.particle = (uint64_t)(a.first + i0 + lr);
                 transform_tiles<NTB, TRI, EXACT, PGB>(lf_lane, ntd, gen, c);
             }
-            cp_async_wait_all();  // own elements only: no warp barrier needed
+            landed(xk & 1u);  // (cp.async: own elements only, no warp barrier needed)
             double se0 = 0.0, se1 = 0.0, sg0 = 0.0, sg1 = 0.0;
 #pragma unroll
             for (int mt = 0; mt < NTB; ++mt) {
@@ -171,8 +189,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_xform(const XfArgs a) {
                 }
             }
         } else {
-            cp_async_wait_all();
-            __syncwarp();  // the warp's block has landed (every lane waited for its own copies)
+            landed(xk & 1u);
+            __syncwarp();  // the warp's block has landed (cp.async: every lane waited for its own copies)
             GenStage gen;
             gen.addr = stg_w + (uint32_t)((lc * 8 + lr) * 8);
             gen.mean_addr = vm_addr + lc * 8;
@@ -242,13 +260,15 @@ struct GenNoise {  // B fragments of k-pair q from the consumer's noise buffer
 // behind the 16-cycle DMMAs of the shared pipe, so one producer per consumer is latency-bound at ~2.4 consumer tile
 // times.  With NPC > 1 the CTA has more than 512 threads; setmaxnreg moves registers from the producers (RP) to the
 // consumers (RC), whose 2 * NTB accumulators + fragment prefetch do not fit the launch-time allocation.
-template <int NTB, int NC, int NPC, bool EXACT, int PGB, int RC, int RP>
-__global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArgs a) {
+// TMAX: a consumer's X tile (8 particles x all rows) arrives by ONE TMA box copy issued by its lane 0 instead of 13
+// cp.async per lane with their 64-bit address arithmetic
+template <int NTB, int NC, int NPC, bool EXACT, int PGB, int RC, int RP, bool TMAX>
+__global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArgs a, const __grid_constant__ CUtensorMap tmap) {
     constexpr int MT = (1 + NPC) * NC * 32;
     constexpr int ROWS = 8 * NTB;
     constexpr int STG = ROWS * 8;   // doubles of one consumer's X staging block: [row][8 particles]
     constexpr int NZ = NTB * 64;    // doubles of one noise buffer: [k-pair][lane][2]
-    extern __shared__ double sm[];
+    extern __shared__ __align__(1024) double sm[];
     const int d = a.d, ntd = (d + 7) >> 3;
     double* Lf = sm;
     double* nz = Lf + lf_doubles<NTB, true>();
@@ -257,6 +277,7 @@ __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArg
     double* vc = vm + 8 * NTB;
     double* bm = vc + 8 * NTB;
     __shared__ __align__(8) unsigned long long bars[NC][2][2];  // [consumer][buffer][0: full, 1: empty]
+    __shared__ __align__(8) unsigned long long xbars[NC];       // "the X tile of consumer c has landed" (TMAX)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lc = lane & 3;
 
     pack_matrix<NTB, true, MT>(Lf, a.A, d);
@@ -267,6 +288,7 @@ __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArg
     for (int idx = tid; idx < NC * STG; idx += MT) stg[idx] = 0.0;
     bm_stage_tables(bm, tid, MT);
     if (tid < NC * 4) mbar_init(smem_u32(&bars[0][0][0]) + 8u * (uint32_t)tid, (tid & 1) ? 1 : NPC);
+    if (tid < NC) mbar_init(smem_u32(&xbars[0]) + 8u * (uint32_t)tid, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
@@ -321,12 +343,24 @@ __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArg
     const uint32_t vm_lane = smem_u32(vm) + (uint32_t)lr * 8u, vc_lane = smem_u32(vc) + (uint32_t)lr * 8u;
     const double e_const = (double)d * REE_LOG_2PI;
     const double tt = a.t;
+    const uint32_t xbar = smem_u32(&xbars[warp]);
     auto prefetch = [&](int64_t wt) {
-        const double* src = a.x + wt * 8 + 2 * lc;
+        if constexpr (TMAX) {
+            // the box {8 particles, all rows} of the ensemble's tensor map lands as [row][8] in the staging block; rows
+            // >= d arrive as zeros.  The proxy fence orders this warp's reads of the previous tile before the refill.
+            __syncwarp();
+            if (lane == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(xbar, (uint32_t)(STG * 8));
+                tma_load_2d(stg_w, &tmap, (int)(wt * 8), 0, xbar);
+            }
+        } else {
+            const double* src = a.x + wt * 8 + 2 * lc;
 #pragma unroll
-        for (int mt = 0; mt < NTB; ++mt) {
-            const int row = 8 * mt + lr;
-            if (row < d) cp_async16(own + (uint32_t)(mt * 512), src + (int64_t)row * a.ld);
+            for (int mt = 0; mt < NTB; ++mt) {
+                const int row = 8 * mt + lr;
+                if (row < d) cp_async16(own + (uint32_t)(mt * 512), src + (int64_t)row * a.ld);
+            }
         }
     };
     int64_t wt = (int64_t)blockIdx.x * NC + warp;
@@ -336,7 +370,8 @@ __global__ void __launch_bounds__((1 + NPC) * NC * 32, 1) k_xform_ws(const XfArg
         const int64_t ip = wt * 8 + 2 * lc;
         const uint32_t b = (uint32_t)k & 1u, ph = ((uint32_t)k >> 1) & 1u;
         double c2[NTB][2];
-        cp_async_wait_all();  // own elements only: no warp barrier needed
+        if constexpr (TMAX) mbar_wait(xbar, (uint32_t)k & 1u);
+        else cp_async_wait_all();  // own elements only: no warp barrier needed
 #pragma unroll
         for (int mt = 0; mt < NTB; ++mt) {
             const int row = 8 * mt + lr;
@@ -776,9 +811,25 @@ static int launch_xf(const XfArgs& a, int grid, cudaStream_t st) {
     constexpr size_t smem = ((size_t)lf_doubles<NTB, TRI>() + (size_t)NW * 8 * NTB * 8 + 2 * 8 * NTB +
                              (MODE == 1 ? BM_SMEM_DOUBLES : 0)) * sizeof(double);
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    auto kern = k_xform<MODE, NTB, NW, EXACT, TRI, PGB>;
-    REE_OPT_IN_SMEM(kern, smem);
-    kern<<<grid, NW * 32, smem, st>>>(a);
+    static int use_tma = -1;
+    if (use_tma < 0) {
+        const char* e = getenv("REE_XF_TMA");  // tuning / test hook: 0 = per-lane cp.async staging of the X tiles
+        use_tma = e ? atoi(e) : 1;
+    }
+    if (use_tma) {
+        auto kern = k_xform<MODE, NTB, NW, EXACT, TRI, PGB, true>;
+        REE_OPT_IN_SMEM(kern, smem);
+        CUtensorMap tmap;
+        int rc = make_ensemble_tmap(&tmap, a.x, a.ld, a.d, 8, 8 * NTB);
+        if (rc) return rc;
+        kern<<<grid, NW * 32, smem, st>>>(a, tmap);
+    } else {
+        auto kern = k_xform<MODE, NTB, NW, EXACT, TRI, PGB, false>;
+        REE_OPT_IN_SMEM(kern, smem);
+        CUtensorMap tmap;
+        memset(&tmap, 0, sizeof(tmap));
+        kern<<<grid, NW * 32, smem, st>>>(a, tmap);
+    }
     return ree_check_launch(MODE == 1 ? "k_xform<1>" : "k_xform<2>");
 }
 
@@ -791,16 +842,22 @@ static int xf_ws() {
     return v;
 }
 
-template <int NTB, int NC, int NPC, bool EXACT, int PGB, int RC, int RP>
+template <int NTB, int NC, int NPC, bool EXACT, int PGB, int RC, int RP, bool TMAX>
 static int launch_xf_ws(const XfArgs& a, int grid, cudaStream_t st) {
     constexpr size_t smem = ((size_t)lf_doubles<NTB, true>() + (size_t)NC * 3 * NTB * 64 + 2 * 8 * NTB +
                              BM_SMEM_DOUBLES) * sizeof(double);
     static_assert(smem <= 227 * 1024, "shared memory budget");
     static_assert(RC == 0 || (NC * RC + NC * NPC * RP) * 32 <= 65536 / ((1 + NPC) * NC * 32) / 8 * 8 * (1 + NPC) * NC * 32,
                   "register pool");
-    auto kern = k_xform_ws<NTB, NC, NPC, EXACT, PGB, RC, RP>;
+    auto kern = k_xform_ws<NTB, NC, NPC, EXACT, PGB, RC, RP, TMAX>;
     REE_OPT_IN_SMEM(kern, smem);
-    kern<<<grid, (1 + NPC) * NC * 32, smem, st>>>(a);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (TMAX) {
+        int rc = make_ensemble_tmap(&tmap, a.x, a.ld, a.d, 8, 8 * NTB);
+        if (rc) return rc;
+    }
+    kern<<<grid, (1 + NPC) * NC * 32, smem, st>>>(a, tmap);
     return ree_check_launch("k_xform_ws");
 }
 
@@ -815,11 +872,13 @@ static int launch_xf_ws_variants(const XfArgs& a, cudaStream_t st) {
         // with setmaxnreg 120 / 56 (measured slower: the extra DFMA streams take pipe slots from the consumers)
         // tuning hooks (profiles/r2_xform_variants.txt): 1 = four Box-Muller chains per producer batch, 2 = two producers
         // per consumer with setmaxnreg 120 / 56 -- both measured slower than the default
-        if (v == 1) return launch_xf_ws<NTB, NC, 1, true, 4, 0, 0>(a, grid, st);
-        if (v == 2) return launch_xf_ws<NTB, NC, 2, true, 2, 120, 56>(a, grid, st);
-        return launch_xf_ws<NTB, NC, 1, true, 2, 0, 0>(a, grid, st);
+        // 3 = per-lane cp.async staging of X instead of the TMA box copy (7.35 against 7.17 ms at N = 1e7, d = 100)
+        if (v == 1) return launch_xf_ws<NTB, NC, 1, true, 4, 0, 0, true>(a, grid, st);
+        if (v == 2) return launch_xf_ws<NTB, NC, 2, true, 2, 120, 56, true>(a, grid, st);
+        if (v == 3) return launch_xf_ws<NTB, NC, 1, true, 2, 0, 0, false>(a, grid, st);
+        return launch_xf_ws<NTB, NC, 1, true, 2, 0, 0, true>(a, grid, st);
     }
-    return launch_xf_ws<NTB, NC, 1, false, 2, 0, 0>(a, grid, st);
+    return launch_xf_ws<NTB, NC, 1, false, 2, 0, 0, true>(a, grid, st);
 }
 
 template <int MODE, int NTB, int NW, bool TRI>
