@@ -16,6 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=1_250_000)
 ap.add_argument("--d", type=int, default=100)
 ap.add_argument("--iters", type=int, default=2)
+ap.add_argument("--problem", default="linear", choices=["linear", "osc"])
 ap.add_argument("--skip", type=int, default=12, help="iterations before the recorded ones (the Brent search is active after ~9)")
 args = ap.parse_args()
 eng = Engine.get()
@@ -37,7 +38,10 @@ for name in NAMES:
         return inner
     setattr(eng, name, wrap())
 
-prob = ree.make_linear_problem(args.d)
+if args.problem == "osc":
+    prob, args.d = ree.prob_nonlin_osc, 6
+else:
+    prob = ree.make_linear_problem(args.d)
 prob.sample = DeviceSample(args.n, args.d, seed=0x5EED)
 solver = ree.CBREE(seed=1, convergence_check=False, divergence_check=False, quiet=True, num_steps=10**9)
 cl = solver.start(prob, recycle=True)
