@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define REE_ABI_VERSION 10
+#define REE_ABI_VERSION 9
 
 /* argument errors */
 #define REE_E_BADARG (-1)
@@ -181,10 +181,6 @@ typedef struct ree_adapt {
     double xtol;         /* hybrd: 1.49012e-8 */
     double factor;       /* hybrd: 100 */
     double epsfcn;       /* hybrd: machine epsilon */
-    int32_t spare_sms;   /* > 0: launch that many CTAs fewer than there are SMs -- for a search that runs NEXT TO
-                          * single-CTA kernels of other streams (the factorisations), whose SMs a full cooperative grid
-                          * would have to wait for */
-    int32_t reserved;
 } ree_adapt;
 /* g, e (e may be NULL): this rank's limit-state / energy values; ell: n doubles of scratch, on return the log-target
  * vector for the new sigma; workspace as for the reductions.

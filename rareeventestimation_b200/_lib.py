@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libree_b200.so")
 TGT_KINDS = {"algebraic": 0, "tanh": 1, "arctan": 2, "erf": 3, "relu": 4, "sigmoid": 5}
 LSF_EXTERNAL, LSF_AFFINE, LSF_CONVEX, LSF_FUJITA_RACKWITZ, LSF_OSCILLATOR, LSF_DIFFUSION = range(6)
 NOISE_INJECT, NOISE_PHILOX = 0, 1
-ABI_VERSION = 10
+ABI_VERSION = 9
 
 
 class ReeError(RuntimeError):
@@ -55,8 +55,6 @@ class ReeAdapt(C.Structure):
         ("xtol", C.c_double),
         ("factor", C.c_double),
         ("epsfcn", C.c_double),
-        ("spare_sms", C.c_int32),
-        ("reserved", C.c_int32),
     ]
 
 

@@ -571,10 +571,7 @@ extern "C" int ree_cbree_adapt(const double* g, const double* e, int64_t n, cons
     const int cap = opt_max_ctas(alg);
     if (cap < 1) return ree_set_error(REE_E_UNSUPPORTED, "ree_cbree_adapt: the persistent kernel does not fit this device");
     int64_t want = (n + 4 * OPT_THREADS - 1) / (4 * OPT_THREADS);
-    int ctas = (int)(want < 1 ? 1 : (want > cap ? cap : want));
-    // single-CTA kernels of other streams (the factorisations) keep their SMs: a cooperative grid that counted on them
-    // would only start once they have finished
-    if (p->spare_sms > 0 && ctas > cap - p->spare_sms) ctas = cap - p->spare_sms > 1 ? cap - p->spare_sms : 1;
+    const int ctas = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     AdaptArgs a{};
     a.g = g; a.e = e; a.n = n; a.ell = ell; a.ws = workspace; a.out = out16; a.p = *p;
     const PeerArgs* peer = p->use_peers ? ree_peer_args_current() : local_mailbox();

@@ -345,7 +345,7 @@ class Engine:
         self._scratch = {}
         self._staging = None
         self._pin_ring, self._pin_next, self._pin_down, self._side = None, 0, None, None
-        self._pin_slots = [None, None, None]
+        self._pin_slots = [None, None]
         self._open_post = None
         self.adapt_launches = 0
         self._fetch_buf = np.empty(64, dtype=np.float64)
@@ -424,16 +424,10 @@ class Engine:
         ev.record(torch.cuda.current_stream(self.device))
         return buf.numpy(), ev
 
-    def side_stream(self, which: int = 0) -> "torch.cuda.Stream":
-        """Streams for the single-CTA factorisations: 0 = factor of the weighted covariance (next step's noise),
-        1 = factorisation / inverse of the fitted covariance (runs next to the sigma / beta search)."""
-        if which == 0:
-            if self._side is None:
-                self._side = torch.cuda.Stream(self.device)
-            return self._side
-        if getattr(self, "_side1", None) is None:
-            self._side1 = torch.cuda.Stream(self.device)
-        return self._side1
+    def side_stream(self) -> "torch.cuda.Stream":
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
 
     # -- ensemble I/O ---------------------------------------------------------- #
     def alloc_ensemble(self, n: int, d: int, first: int = 0, with_vectors=True) -> Ensemble:
@@ -585,15 +579,14 @@ class Engine:
         return bool(comm.peer)
 
     def adapt(self, ens: Ensemble, tgt_kind: int, sigma: float, sigma_hi: Optional[float], cvar_tgt: float, beta: float,
-              do_beta: bool, ess_tgt_n: float, overlap=None, wait: bool = True, spare_sms: int = 0) -> Optional[np.ndarray]:
+              do_beta: bool, ess_tgt_n: float, overlap=None, wait: bool = True) -> Optional[np.ndarray]:
         """sigma / beta searches of one iteration in one persistent kernel (``ree_cbree_adapt``): bounded Brent over
         sigma in [sigma, sigma_hi] (skipped if ``sigma_hi`` is None), then the hybrd root find over beta (or only the ESS
-        of (sigma, beta)).  Returns the 16 result doubles on the host; needs :meth:`peers_connected`.  ``spare_sms``:
-        SMs left to single-CTA kernels that run on other streams at the same time (the factorisations)."""
+        of (sigma, beta)).  Returns the 16 result doubles on the host; needs :meth:`peers_connected`."""
         p = _lib.ReeAdapt(tgt_kind, 1 if sigma_hi is not None else 0, 1 if do_beta else 0, 500, 400,
                           1 if self.comm.enabled else 0, float(sigma),
                           float(sigma_hi) if sigma_hi is not None else float(sigma), float(cvar_tgt), 1e-5, float(beta),
-                          float(ess_tgt_n), 1.49012e-08, 100.0, float(np.finfo(np.float64).eps), int(spare_sms), 0)
+                          float(ess_tgt_n), 1.49012e-08, 100.0, float(np.finfo(np.float64).eps))
         ell = self.scratch("ell", ens.ld)
         out = self.scratch("adapt_out", 16)
         ws = self.workspace(ens.d)
@@ -602,8 +595,6 @@ class Engine:
               "ree_cbree_adapt")
         self.adapt_launches += 1  # (a search launched ahead is only adopted if no other search ran on this engine since)
         if not wait:
-            # (read back behind the kernel: whoever adopts the result does not have to drain the stream for it)
-            self._adapt_async = self.to_host_async(out, 2) + (self.adapt_launches,)
             return None
         if overlap is not None:
             overlap()
@@ -611,10 +602,6 @@ class Engine:
 
     def adapt_result(self) -> np.ndarray:
         """The 16 result doubles of the last :meth:`adapt` launch on this device (synchronising)."""
-        pend = getattr(self, "_adapt_async", None)
-        if pend is not None and pend[2] == self.adapt_launches:
-            pend[1].synchronize()
-            return pend[0].copy()
         return self.fetch(self.scratch("adapt_out", 16), 16)
 
     def vector_range(self, v: torch.Tensor, n: int, d: int) -> torch.Tensor:

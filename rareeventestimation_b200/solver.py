@@ -430,7 +430,7 @@ class CBREE(Solver):
     # post-processing of an ensemble: moments, IS density, weights  (device)
     # ------------------------------------------------------------------ #
     def _post_ensemble(self, cache: CBREECache, sums_ready=None,
-                       shift_u=None, shift_w=None, model=None, defer=False, mid_hook=None):
+                       shift_u=None, shift_w=None, model=None, defer=False):
         """Everything the reference derives from (X, g, e, sigma, beta) of one cache:
         unweighted mean/cov + factorisation (solver.py:670-674), ESS shift (my_softmax), Mahalanobis sweep with
         IS statistics (683-686, 843-846) and the weighted mean/cov (629-636).
@@ -438,25 +438,20 @@ class CBREE(Solver):
         Split path: what the NEXT iteration's control flow needs -- both means / covariances, the ESS tuple, the failure
         count -- is read back BEFORE the factorisation and the Mahalanobis / IS sweep are enqueued, so the host works on
         it while the GPU runs those; their results (pivot statistics, IS tuple) arrive with a second small readback.
-        ``defer=True`` returns after the first one; :meth:`_finish_post` completes the cache.  ``mid_hook(cache,
-        spare_sms)`` is called between the two (split path, Gaussian fit): the factorisation then runs on a side stream
-        and whatever the hook launches on the main stream -- the next iteration's sigma / beta search -- runs NEXT TO
-        it instead of behind it; the Mahalanobis sweep follows both.  ``cache._hooked`` tells whether it was called."""
+        ``defer=True`` returns after the first one; :meth:`_finish_post` completes the cache."""
         # (the pinned readback slots belong to the engine: an unfinished cache of ANY solver on it is completed first)
         self._finish_post(getattr(self._eng, "_open_post", None))
         eng, dev = self._eng, cache._dev
         d = dev.d
         kind = self._tgt_kind()
         slen = d + d * d + 2
-        # packed result buffer: [mean d | cov d*d | m_w d | C_w d*d | ess4 4 | sums_u tail 2 | sums_w tail 2 || stats 8 | is4 4]
-        # (first readback: everything before ||, second: the rest)
+        # packed result buffer: [mean d | cov d*d | m_w d | C_w d*d | stats 8 | is4 4 | ess4 4 | sums_u tail 2 | sums_w tail 2]
         res = eng.empty(2 * d + 2 * d * d + 20)
         mean, cov = res[0:d], res[d:d + d * d]
         m_w, C_w = res[d + d * d:2 * d + d * d], res[2 * d + d * d:2 * d + 2 * d * d]
         o = 2 * d + 2 * d * d
-        ess4, tails = res[o:o + 4], res[o + 4:o + 8]
-        ob = o + 8
-        stats, is4 = res[ob:ob + 8], res[ob + 8:ob + 12]
+        stats, is4, ess4 = res[o:o + 8], res[o + 8:o + 12], res[o + 12:o + 16]
+        tails = res[o + 16:o + 20]
         L, Linv = eng.empty(d * d), eng.empty(d * d)
         early = eng.path(d) == 2 and sums_ready is None
         if early:
@@ -500,39 +495,21 @@ class CBREE(Solver):
                 F0_event.record(side)
             res.record_stream(side)
             F0.record_stream(main)
-        hooked = early and mid_hook is not None and model is None
-        ev_fact = None
-
-        def second_half():  # density statistics of the new ensemble + their readback
+        if early:
+            host, ev_a = eng.to_host_async(res, 0)
+            # enqueued behind the readback: factorisation (+ inverse, eigenvalue brackets) and the Mahalanobis / IS sweep
+            eng.moments_chol(sums_u, shift_u, d, 1, False, mean, cov, L, Linv, stats)
             if model is None:
                 eng.cbree_maha(dev, mean, Linv, stats[0:1], cache.sigma, cache.beta, kind, None, None, is4)
             elif getattr(model, "_is4_dev", None) is not None:  # already computed with g and e of the redraw
                 is4.copy_(model._is4_dev)
             else:  # the ensemble was drawn from the fitted vMFN model: its density replaces the Gaussian fit
                 model.logpdf_device(eng, dev, is4=is4)
-            return eng.to_host_async(res[ob:ob + 12], 1)
-
-        if early:
-            main = torch.cuda.current_stream(eng.device)
-            if hooked:  # factorisation (+ inverse, eigenvalue brackets) next to the readback AND the hook's launches
-                side1 = eng.side_stream(1)
-                ready1 = torch.cuda.Event()
-                ready1.record(main)
-                with torch.cuda.stream(side1):
-                    side1.wait_event(ready1)
-                    eng.moments_chol(sums_u, shift_u, d, 1, False, mean, cov, L, Linv, stats)
-                    ev_fact = torch.cuda.Event()
-                    ev_fact.record(side1)
-                host, ev_a = eng.to_host_async(res[0:ob], 0)
-                host_b = ev_b = None
-            else:  # enqueued behind the readback: factorisation and the Mahalanobis / IS sweep
-                host, ev_a = eng.to_host_async(res[0:ob], 0)
-                eng.moments_chol(sums_u, shift_u, d, 1, False, mean, cov, L, Linv, stats)
-                host_b, ev_b = second_half()
+            host_b, ev_b = eng.to_host_async(res[o:o + 12], 1)
             ev_a.synchronize()
         else:
             host = eng.to_host(res)  # the one synchronising D2H of the iteration (pinned)
-            host_b, ev_b = host[ob:ob + 12], None
+            host_b, ev_b = host[o:o + 12], None
         self._peer_checks = getattr(self, "_peer_checks", 0) + 1
         if self._peer_checks % 16 == 1:  # (a 4-byte synchronising copy of the time-out flag: not every iteration)
             eng.comm.check_peers()
@@ -540,21 +517,12 @@ class CBREE(Solver):
         cache.ens_cov = host[d:d + d * d].reshape(d, d).copy()
         cache.weighted_mean = host[d + d * d:2 * d + d * d].copy()
         cache.weighted_cov = host[2 * d + d * d:o].reshape(d, d).copy()
-        e4, tl = host[o:o + 4], host[o + 4:o + 8]
+        e4, tl = host[o + 12:o + 16], host[o + 16:o + 20]
         cache._stats = dict(C_w=C_w, F0=F0, F0_event=F0_event)  # views into `res`; the O(N) scratch is released here
         cache._vmfn_density = model is not None
         cache.num_failed = float(tl[0])
         cache._ess4 = e4.copy()
         cache._n_total = float(tl[1])
-        cache._hooked = False
-        if hooked:
-            try:
-                if e4[3] > 0:
-                    cache._hooked = True
-                    mid_hook(cache, 2 if self.noise == "philox" else 1)
-            finally:  # (the sweep is enqueued whatever the hook did: L, Linv and stats are in flight on the side stream)
-                main.wait_event(ev_fact)
-                host_b, ev_b = second_half()
         cache._pending_b = (host_b, ev_b)
         eng._open_post = cache
         if e4[3] <= 0:  # my_softmax on an all-non-finite vector (utilities.py:121)
@@ -780,24 +748,21 @@ class CBREE(Solver):
         return (float(sigma), None if sigma_hi is None else float(sigma_hi), note, float(cache.beta),
                 bool(self.beta_adaptivity), float(self.ess_tgt * cache._n_total), self._tgt_kind(), float(self.cvar_tgt))
 
-    def _launch_search(self, cache: CBREECache, args: tuple, overlap=None, wait=True, spare_sms=0):
+    def _launch_search(self, cache: CBREECache, args: tuple, overlap=None, wait=True):
         sigma, sigma_hi, _, beta, do_beta, ess_n, kind, cvar_tgt = args
-        return self._eng.adapt(cache._dev, kind, sigma, sigma_hi, cvar_tgt, beta, do_beta, ess_n, overlap=overlap, wait=wait,
-                               spare_sms=spare_sms)
+        return self._eng.adapt(cache._dev, kind, sigma, sigma_hi, cvar_tgt, beta, do_beta, ess_n, overlap=overlap, wait=wait)
 
-    def _speculate_search(self, cache_list: list, spare_sms: int = 0):
-        """Launch the NEXT iteration's sigma / beta search now: its inputs -- g, e, the failure count, the step size the
-        controller will choose -- are all known once the moments of the new ensemble are on the host.  Split path: the
-        launch comes between the two halves of :meth:`_post_ensemble`, the search runs next to the factorisations
-        (``spare_sms`` SMs are left to them) and ahead of the Mahalanobis sweep; otherwise behind the sweep.  Nothing of
-        the cache is modified; the next :meth:`advance` recomputes the arguments and takes the result over if they are
-        identical (else it searches again)."""
+    def _speculate_search(self, cache_list: list):
+        """Launch the NEXT iteration's sigma / beta search now (behind the Mahalanobis sweep already in the stream): its
+        inputs -- g, e, the failure count, the step size the controller will choose -- are all known once the moments
+        of the new ensemble are on the host.  Nothing of the cache is modified; the next :meth:`advance` recomputes the
+        arguments and takes the result over if they are identical (else it searches again)."""
         cache = cache_list[-1]
         t_next = cache.t_step
         if self.stepsize_adaptivity and len(cache_list) > 1 and cache.iteration % 2 == 0:
             t_next = self._stepsize_value(cache_list)
         args = self._search_args(cache, t_next)
-        self._launch_search(cache, args, wait=False, spare_sms=spare_sms)
+        self._launch_search(cache, args, wait=False)
         pend = dict(cache=cache, args=args, t_next=t_next, prep=None, token=self._eng.adapt_launches)
         try:  # the step's host-side preparation as well (it only depends on the step size), while the GPU is busy
             keep, cache.t_step = cache.t_step, t_next
@@ -879,11 +844,9 @@ class CBREE(Solver):
         small = eng.to_device_small(np.concatenate([m_noise, shift_u_h, cache.weighted_mean]))
         return dict(t=t, small=small, dst=eng.alloc_ensemble(n, d, first=src.first), desc=self._lsf_descriptor(d))
 
-    def _perform_step(self, cache: CBREECache, prep: Optional[dict] = None, defer: bool = False,
-                      mid_hook=None) -> CBREECache:
+    def _perform_step(self, cache: CBREECache, prep: Optional[dict] = None, defer: bool = False) -> CBREECache:
         """solver.py:642-694 (GM branch).  sweep 1 (``ree_cbree_step``) + post-processing (sweep 2).  With ``defer`` the
-        new cache comes back as soon as the moments are on the host; :meth:`_complete_step` finishes it.  ``mid_hook``:
-        see :meth:`_post_ensemble`."""
+        new cache comes back as soon as the moments are on the host; :meth:`_complete_step` finishes it."""
         eng, src = self._eng, cache._dev
         n, d = src.n, src.d
         if isinstance(prep, dict) and "error" in prep:
@@ -937,8 +900,7 @@ class CBREE(Solver):
         new.t_step = cache.t_step
         new.num_lsf_evals = self.lsf.counter
         new._cw_dirty = False
-        self._post_ensemble(new, sums_ready=sums, shift_u=shift_u, shift_w=shift_w, model=model, defer=defer,
-                            mid_hook=mid_hook)
+        self._post_ensemble(new, sums_ready=sums, shift_u=shift_u, shift_w=shift_w, model=model, defer=defer)
         if not defer:
             self._complete_step(new)
         return new
@@ -1190,15 +1152,10 @@ class CBREE(Solver):
         # The next search can be launched before this step's Mahalanobis sweep has finished when nothing can change the
         # new cache in between (no callback) and the search runs on the device.
         speculate = self.callback is None and self.search == "device" and self._eng.peers_connected()
-        def search_ahead(new, spare_sms):  # (between the two halves of the new cache's post-processing)
-            self._pending = self._speculate_search(cache_list + [new], spare_sms)
-
         try:
-            ahead = speculate and self._search_ahead(cache_list[-1]._dev)
-            new = self._perform_step(cache_list[-1], prep, defer=speculate, mid_hook=search_ahead if ahead else None)
+            new = self._perform_step(cache_list[-1], prep, defer=speculate)
             if speculate:
-                if not new._hooked:
-                    self._pending = self._speculate_search(cache_list + [new])
+                self._pending = self._speculate_search(cache_list + [new])
                 self._complete_step(new)
             cache_list.append(new)
         except Exception as e:
@@ -1223,17 +1180,6 @@ class CBREE(Solver):
         if self.verbose:
             self._print_row(self._table, cache_list)
         return True
-
-    @staticmethod
-    def _search_ahead(dev) -> bool:
-        """Where the next iteration's search goes: between the two halves of the post-processing, next to the
-        factorisation (hides its 0.2 ms, exposes ~0.1 ms of host bookkeeping after the sweep), or behind the Mahalanobis
-        sweep.  Measured (profiles/r2_timeline_1p25e6.txt, r2_xform_variants.txt): ahead wins 0.06 ms per iteration at
-        1.25e6 x 100 per rank, behind wins 0.06 ms at 1e7 x 100.  REE_SEARCH_AHEAD=0 / 1 forces one of them."""
-        env = os.environ.get("REE_SEARCH_AHEAD")
-        if env is not None:
-            return env != "0"
-        return dev is not None and dev.n * dev.d <= 300_000_000
 
     def _drop_pending(self, pending) -> None:
         if pending is not None and pending.get("prep"):
