@@ -345,7 +345,7 @@ class Engine:
         self._scratch = {}
         self._staging = None
         self._pin_ring, self._pin_next, self._pin_down, self._side = None, 0, None, None
-        self._pin_slots = [None, None]
+        self._pin_slots = [None, None, None]
         self._open_post = None
         self.adapt_launches = 0
         self._fetch_buf = np.empty(64, dtype=np.float64)
@@ -595,6 +595,8 @@ class Engine:
               "ree_cbree_adapt")
         self.adapt_launches += 1  # (a search launched ahead is only adopted if no other search ran on this engine since)
         if not wait:
+            # (read back behind the kernel: whoever adopts the result does not have to launch a fetch for it)
+            self._adapt_async = self.to_host_async(out, 2) + (self.adapt_launches,)
             return None
         if overlap is not None:
             overlap()
@@ -602,6 +604,10 @@ class Engine:
 
     def adapt_result(self) -> np.ndarray:
         """The 16 result doubles of the last :meth:`adapt` launch on this device (synchronising)."""
+        pend = getattr(self, "_adapt_async", None)
+        if pend is not None and pend[2] == self.adapt_launches:
+            pend[1].synchronize()
+            return pend[0].copy()
         return self.fetch(self.scratch("adapt_out", 16), 16)
 
     def vector_range(self, v: torch.Tensor, n: int, d: int) -> torch.Tensor:
