@@ -24,7 +24,7 @@ Deliberate deviations from the reference (all <= 2e-14 relative):
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Callable, List, Optional
 
 import numpy as np

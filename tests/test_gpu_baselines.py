@@ -3,7 +3,6 @@ conditional sampling, built on the same CUDA primitives as CBREE and called thro
 
 Reference: solver.py:1203-1271 (CMC), solver.py:1111-1200 -> sis/SIS_aCS.py:64-306 (SIS-aCS).
 """
-import ctypes as C
 import os
 
 import numpy as np
