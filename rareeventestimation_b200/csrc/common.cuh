@@ -285,12 +285,22 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+        // high / low halves asked for separately: they still end up in one IMAD.WIDE each, but the 64-bit product form
+        // dragged extra integer adds along (250 -> 180 SASS instructions for the four blocks of a particle at d <= 8,
+        // profiles/r2_xform_variants.txt).  Same bits.
+        uint32_t n0 = __umulhi(M1, c[2]) ^ c[1] ^ k0;
+        uint32_t n1 = M1 * c[2];
+        uint32_t n2 = __umulhi(M0, c[0]) ^ c[3] ^ k1;
+        uint32_t n3 = M0 * c[0];
+#else
         uint64_t p0 = (uint64_t)M0 * c[0];
         uint64_t p1 = (uint64_t)M1 * c[2];
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
         uint32_t n1 = (uint32_t)p1;
         uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
         uint32_t n3 = (uint32_t)p0;
+#endif
         c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
         k0 += W0;
         k1 += W1;
